@@ -1,0 +1,293 @@
+"""Host-side mirror of the reference's interface for the hot path, over the C ABI.
+
+Mirrors (same names, argument meaning, error behaviour):
+  * FeaturePoint / FrameFeature           src/detected_points.rs:6-17
+  * RvecTvec                              src/types.rs:13-39
+  * GenericModel (params/width/height)    camera-intrinsic-model ^0.8 (call sites src/util.rs:391,418,472)
+  * calib_camera(...)                     src/util.rs:384-490  -> Optional[(GenericModel, {frame_idx: RvecTvec})]
+plus a thin `Problem` class over the step-wise entry points used by the parity tests and the bench.
+
+Everything numerical happens inside libccrs_b200.so (CUDA). This module only reshapes arrays.
+The initial per-frame poses (SQPnP in the reference, util.rs:418-439) are an input here: pose
+initialisation is outside the accelerated path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _abi
+from ._abi import CcrsError, Options, Summary, check, default_options
+
+MODELS = {"ucm": 0, "eucm": 1, "eucmt": 2, "kb4": 3, "opencv5": 4, "ftheta": 5}
+MIN_POINTS_PER_FRAME = 10  # util.rs:431-433
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _up(a):
+    return a.ctypes.data_as(C.POINTER(C.c_ubyte)) if a is not None else None
+
+
+@dataclass
+class FeaturePoint:
+    p2d: Tuple[float, float]
+    p3d: Tuple[float, float, float]
+
+
+@dataclass
+class FrameFeature:
+    time_ns: int
+    img_w_h: Tuple[int, int]
+    features: Dict[int, FeaturePoint] = field(default_factory=dict)
+
+
+@dataclass
+class RvecTvec:
+    rvec: Tuple[float, float, float]
+    tvec: Tuple[float, float, float]
+
+    def as_array(self) -> np.ndarray:
+        return np.array([*self.rvec, *self.tvec], dtype=np.float64)
+
+
+@dataclass
+class GenericModel:
+    model: str
+    params: np.ndarray
+    width: int
+    height: int
+
+    def model_id(self) -> int:
+        return MODELS[self.model]
+
+
+class Problem:
+    """One device-resident calibration problem (or a batch of independent ones)."""
+
+    def __init__(self, model, width: int, height: int, frame_offsets, x, y, z, u, v, xy_same_focal: bool = False,
+                 huber_delta: float = 1.0, device: int = 0, problem_frame_offsets=None):
+        self.lib = _abi.load()
+        self.model = MODELS[model] if isinstance(model, str) else int(model)
+        fo = np.ascontiguousarray(frame_offsets, dtype=np.int32)
+        xs, ys, zs, us, vs = map(_f64, (x, y, z, u, v))
+        n = int(fo[-1])
+        for a in (xs, ys, zs, us, vs):
+            if a.shape != (n,):
+                raise ValueError("observation arrays must have frame_offsets[-1] entries")
+        self.h = C.c_void_p()
+        ip = C.POINTER(C.c_int32)
+        if problem_frame_offsets is None:
+            check(self.lib.ccrs_problem_create(C.byref(self.h), self.model, width, height, int(xy_same_focal),
+                                               len(fo) - 1, fo.ctypes.data_as(ip), _dp(xs), _dp(ys), _dp(zs), _dp(us),
+                                               _dp(vs), float(huber_delta), int(device)))
+        else:
+            pfo = np.ascontiguousarray(problem_frame_offsets, dtype=np.int32)
+            check(self.lib.ccrs_batch_create(C.byref(self.h), self.model, width, height, int(xy_same_focal),
+                                             len(pfo) - 1, pfo.ctypes.data_as(ip), len(fo) - 1, fo.ctypes.data_as(ip),
+                                             _dp(xs), _dp(ys), _dp(zs), _dp(us), _dp(vs), float(huber_delta), int(device)))
+        self.d = self.lib.ccrs_problem_dim(self.h)
+        self.nblk = self.lib.ccrs_problem_nblk(self.h)
+        self.n_frames = self.lib.ccrs_problem_n_frames(self.h)
+        self.n_obs = self.lib.ccrs_problem_n_obs(self.h)
+        self.n_problems = self.lib.ccrs_problem_n_problems(self.h)
+        self.nout = self.d * self.d + 3 * self.d + 1
+
+    @classmethod
+    def from_synth(cls, s, **kw):
+        return cls(s.model, s.width, s.height, s.frame_offsets, s.x, s.y, s.z, s.u, s.v, **kw)
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.ccrs_problem_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- state ----
+    def set_poses(self, poses):
+        p = _f64(poses).reshape(-1)
+        assert p.size == 6 * self.n_frames
+        check(self.lib.ccrs_set_poses(self.h, _dp(p)))
+
+    def get_poses(self) -> np.ndarray:
+        p = np.empty(6 * self.n_frames)
+        check(self.lib.ccrs_get_poses(self.h, _dp(p)))
+        return p.reshape(-1, 6)
+
+    # ---- step-wise path ----
+    def eval_rj(self, intr, poses=None, apply_loss=True, want_j=True):
+        intr = _f64(intr)
+        r = np.empty(2 * self.n_obs)
+        J = np.empty((2 * self.n_obs, self.d + 6)) if want_j else None
+        pp = _f64(poses).reshape(-1) if poses is not None else None
+        check(self.lib.ccrs_eval_rj(self.h, _dp(intr), _dp(pp), int(apply_loss), _dp(r), _dp(J)))
+        return r, J
+
+    def linearize(self, intr, which=0) -> np.ndarray:
+        intr = _f64(intr).reshape(-1)
+        sq = np.empty(self.n_problems)
+        check(self.lib.ccrs_linearize(self.h, _dp(intr), int(which), _dp(sq)))
+        return sq
+
+    def frame_blocks(self, which=0) -> np.ndarray:
+        b = np.empty((self.n_frames, self.nblk))
+        check(self.lib.ccrs_get_frame_blocks(self.h, int(which), _dp(b)))
+        return b
+
+    def compute_scale(self, which=0) -> np.ndarray:
+        c = np.empty((self.n_problems, self.d))
+        check(self.lib.ccrs_compute_scale(self.h, int(which), _dp(c)))
+        return c
+
+    def set_intr_scale(self, scale):
+        s = _f64(scale).reshape(-1) if scale is not None else None
+        check(self.lib.ccrs_set_intr_scale(self.h, _dp(s)))
+
+    def reduce(self, which=0, u=None, use_scale=False, min_diag=1e-6, max_diag=1e32):
+        """Returns dict of per-problem arrays S (P,d,d), g_s, g_a, diag_a (P,d), sq_err (P,)."""
+        uu = _f64(np.broadcast_to(u, (self.n_problems,))) if u is not None else None
+        out = np.empty((self.n_problems, self.nout))
+        check(self.lib.ccrs_reduce(self.h, int(which), _dp(uu), int(use_scale), float(min_diag), float(max_diag), _dp(out)))
+        d = self.d
+        return dict(S=out[:, :d * d].reshape(-1, d, d), g_s=out[:, d * d:d * d + d], g_a=out[:, d * d + d:d * d + 2 * d],
+                    diag_a=out[:, d * d + 2 * d:d * d + 3 * d], sq_err=out[:, -1])
+
+    def backsub(self, y_a, u=None, in_place=False, want_model_dec=True):
+        y = _f64(y_a).reshape(-1)
+        uu = _f64(np.broadcast_to(u, (self.n_problems,))) if u is not None else None
+        md = np.empty(self.n_problems) if want_model_dec else None
+        check(self.lib.ccrs_backsub(self.h, _dp(y), _dp(uu), int(in_place), _dp(md)))
+        return md
+
+    def eval_cost(self, intr, which=0) -> np.ndarray:
+        intr = _f64(intr).reshape(-1)
+        sq = np.empty(self.n_problems)
+        check(self.lib.ccrs_eval_cost(self.h, _dp(intr), int(which), _dp(sq)))
+        return sq
+
+    def accept(self, mask=None):
+        m = np.ascontiguousarray(mask, dtype=np.uint8) if mask is not None else None
+        check(self.lib.ccrs_accept(self.h, _up(m)))
+
+    # ---- controllers ----
+    def _solve(self, fn, intr, lo, hi, fixed, options):
+        a = _f64(intr).reshape(-1).copy()
+        assert a.size == self.n_problems * self.d
+        o = options or default_options()
+        s = Summary()
+        hist = np.full(max(o.max_iteration, 1), np.nan)
+        lo_a = _f64(lo) if lo is not None else None
+        hi_a = _f64(hi) if hi is not None else None
+        fx = np.ascontiguousarray(fixed, dtype=np.uint8) if fixed is not None else None
+        code = fn(self.h, _dp(a), _dp(lo_a), _dp(hi_a), _up(fx), C.byref(o), C.byref(s), _dp(hist))
+        if code not in (0, -4, -5):
+            check(code)
+        out = a.reshape(self.n_problems, self.d) if self.n_problems > 1 else a
+        return out, s, hist[: s.iterations]
+
+    def solve_gn(self, intr, lo=None, hi=None, fixed=None, options: Optional[Options] = None):
+        """GaussNewtonOptimizer::optimize on the device state. Returns (intr, Summary, err_hist)."""
+        return self._solve(self.lib.ccrs_solve_gn, intr, lo, hi, fixed, options)
+
+    def solve_lm(self, intr, lo=None, hi=None, fixed=None, options: Optional[Options] = None):
+        return self._solve(self.lib.ccrs_solve_lm, intr, lo, hi, fixed, options)
+
+    # ---- multi-GPU ----
+    def comm_init(self, unique_id: bytes, rank: int, world: int, deterministic: bool = True):
+        buf = C.create_string_buffer(unique_id, 128)
+        check(self.lib.ccrs_comm_init(self.h, buf, rank, world))
+        check(self.lib.ccrs_comm_set_deterministic(self.h, int(deterministic)))
+
+    # ---- measurement ----
+    def time_linearize(self, intr, reps=20, flush_l2=False) -> float:
+        intr = _f64(intr).reshape(-1)
+        ms = C.c_double(0.0)
+        check(self.lib.ccrs_time_linearize(self.h, _dp(intr), int(reps), int(flush_l2), C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.ccrs_launch_count(self.h))
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    check(_abi.load().ccrs_comm_unique_id(buf))
+    return buf.raw
+
+
+def measure_fp64_peak(device: int = 0) -> float:
+    t = C.c_double(0.0)
+    check(_abi.load().ccrs_measure_fp64_peak(int(device), C.byref(t)))
+    return t.value
+
+
+def model_bounds(model, width, height):
+    m = MODELS[model] if isinstance(model, str) else int(model)
+    n = _abi.load().ccrs_model_nparams(m)
+    lo, hi = np.empty(n), np.empty(n)
+    check(_abi.load().ccrs_model_bounds(m, int(width), int(height), _dp(lo), _dp(hi)))
+    return lo, hi
+
+
+def pack_frames(frame_feature_list: Sequence[Optional[FrameFeature]], initial_poses: Dict[int, RvecTvec]):
+    """FrameFeature list -> SoA arrays. Frames that are None, have no initial pose, or fewer than 10 points
+    are skipped like util.rs:401,431-433. f32 -> f64 widening as factors.rs:141-143."""
+    valid, offs, xs, ys, zs, us, vs, poses = [], [0], [], [], [], [], [], []
+    for i, ff in enumerate(frame_feature_list):
+        if ff is None or i not in initial_poses or len(ff.features) < MIN_POINTS_PER_FRAME:
+            continue
+        for fp in ff.features.values():
+            p3 = np.asarray(fp.p3d, dtype=np.float32).astype(np.float64)
+            p2 = np.asarray(fp.p2d, dtype=np.float32).astype(np.float64)
+            xs.append(p3[0]); ys.append(p3[1]); zs.append(p3[2]); us.append(p2[0]); vs.append(p2[1])
+        offs.append(len(xs))
+        valid.append(i)
+        poses.append(initial_poses[i].as_array())
+    return (valid, np.asarray(offs, dtype=np.int32), _f64(xs), _f64(ys), _f64(zs), _f64(us), _f64(vs),
+            _f64(poses).reshape(-1, 6))
+
+
+def calib_camera(frame_feature_list: Sequence[Optional[FrameFeature]], generic_camera: GenericModel,
+                 xy_same_focal: bool, disabled_distortions: int, fixed_focal: bool,
+                 initial_poses: Dict[int, RvecTvec], use_lm: bool = False, options: Optional[Options] = None,
+                 device: int = 0) -> Optional[Tuple[GenericModel, Dict[int, RvecTvec]]]:
+    """Mirror of calib_camera (src/util.rs:384-490). Returns None where the reference returns None
+    (optimiser failure: NaN error or Cholesky failure)."""
+    lib = _abi.load()
+    valid, offs, x, y, z, u, v, poses = pack_frames(frame_feature_list, initial_poses)
+    if not valid:
+        return None
+    params = _f64(generic_camera.params).copy()
+    poses = poses.copy()
+    s = Summary()
+    o = options or default_options()
+    code = lib.ccrs_calib_camera(generic_camera.model_id(), int(generic_camera.width), int(generic_camera.height),
+                                 len(valid), offs.ctypes.data_as(C.POINTER(C.c_int32)), _dp(x), _dp(y), _dp(z), _dp(u), _dp(v),
+                                 _dp(params), _dp(poses.reshape(-1)), int(xy_same_focal), int(disabled_distortions),
+                                 int(fixed_focal), int(use_lm), C.byref(o), C.byref(s), int(device))
+    if code in (-4, -5):
+        return None
+    check(code)
+    cam = GenericModel(generic_camera.model, params, generic_camera.width, generic_camera.height)
+    rt = {i: RvecTvec(tuple(poses[k, :3]), tuple(poses[k, 3:])) for k, i in enumerate(valid)}
+    return cam, rt

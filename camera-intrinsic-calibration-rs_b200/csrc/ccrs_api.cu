@@ -1,0 +1,827 @@
+// ccrs_api.cu — the C ABI (include/ccrs_b200.h): problem handle, device buffers, kernel sequencing,
+// the CUDA implementation of ccrs_backend, NCCL exchange of the reduced system, calib_camera entry point.
+#include "../../include/ccrs_b200.h"
+#include "ccrs_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <limits>
+#include <vector>
+
+using namespace ccrs;
+
+// ---- minimal NCCL surface, resolved at run time from the libnccl.so.2 the host process already loaded ----
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+namespace {
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+constexpr int kNcclFloat64 = 8;  // ncclFloat64 / ncclDouble
+constexpr int kNcclSum = 0;
+
+NcclApi& nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    api.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.h) api.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (api.h) {
+      api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.h, "ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.h, "ncclCommInitRank");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.h, "ncclCommDestroy");
+      api.AllGather = (decltype(api.AllGather))dlsym(api.h, "ncclAllGather");
+      api.AllReduce = (decltype(api.AllReduce))dlsym(api.h, "ncclAllReduce");
+      api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.h, "ncclGetErrorString");
+      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.AllReduce;
+    }
+  }
+  return api;
+}
+
+thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t _e = (call);                                                                         \
+    if (_e != cudaSuccess) return fail(CCRS_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    n = count;
+    return cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; }
+};
+template <class T>
+struct PinBuf {
+  T* p = nullptr;
+  cudaError_t alloc(size_t count) { return cudaMallocHost((void**)&p, std::max<size_t>(count, 1) * sizeof(T)); }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; }
+};
+}  // namespace
+
+struct ccrs_problem {
+  int model = 0, width = 0, height = 0, one_focal = 0;
+  int D = 0, NA = 0, NBLK = 0, NACC = 0, NRED = 0, NOUT = 0;
+  int n_frames = 0, n_problems = 1, Fs = 0;
+  int64_t n_obs = 0;
+  bool batch = false;
+  int device = 0;
+  int n_sms = 148;
+  cudaStream_t stream = nullptr;
+  int G = 1, FPC = 128, n_lin_ctas = 0;
+  double huber = 1.0;
+  int64_t launches = 0;
+
+  DevBuf<double> x, y, z, u, v;
+  DevBuf<int32_t> frame_offsets, frame_problem, problem_frame_offsets, obs_frame, cur, acc_to_blk;
+  DevBuf<double> poses[2], blocks[2], frame_cost[2];
+  DevBuf<double> elim, frame_red, pose_scale, frame_md;
+  DevBuf<double> red_out, stat_out, gather, intr_dev, ya_dev, u_dev, scale_dev, l2_flush;
+  DevBuf<unsigned char> mask_dev;
+  PinBuf<double> h_red, h_stat, h_small;
+  bool have_scale = false, have_obs_frame = false;
+  std::vector<int32_t> h_frame_offsets, h_problem_frame_offsets;
+  // state of the last reduce(), needed by backsub
+  bool last_use_scale = false;
+  // communicator
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1, deterministic = 1;
+
+  ProblemDev dev() const {
+    ProblemDev d{};
+    d.x = x.p; d.y = y.p; d.z = z.p; d.u = u.p; d.v = v.p;
+    d.frame_offsets = frame_offsets.p;
+    d.frame_problem = batch ? frame_problem.p : nullptr;
+    d.problem_frame_offsets = problem_frame_offsets.p;
+    d.obs_frame = obs_frame.p;
+    d.cur = cur.p;
+    for (int i = 0; i < 2; ++i) { d.poses[i] = poses[i].p; d.blocks[i] = blocks[i].p; d.frame_cost[i] = frame_cost[i].p; }
+    d.n_frames = n_frames; d.n_problems = n_problems; d.Fs = Fs;
+    d.huber_delta = huber;
+    return d;
+  }
+};
+
+namespace {
+
+// Lanes per frame G: the G that minimises (waves of CTAs) x (observations per lane) for this device.
+void choose_slicing(ccrs_problem* p) {
+  const int slots = p->n_sms * kLinCtasPerSm;  // resident CTAs
+  int max_cnt = 1;
+  for (int f = 0; f < p->n_frames; ++f) max_cnt = std::max(max_cnt, p->h_frame_offsets[f + 1] - p->h_frame_offsets[f]);
+  double best = 1e300;
+  int bestG = 1;
+  for (int G = 1; G <= kLinThreads; ++G) {
+    const int fpc = kLinThreads / G;
+    const int ctas = (p->n_frames + fpc - 1) / fpc;
+    const int waves = (ctas + slots - 1) / slots;
+    const int per_lane = (max_cnt + G - 1) / G;
+    // cost model: per-lane observations dominate; a small per-slice constant covers the basis change + reduction
+    const double cost = (double)waves * (per_lane + 2.0);
+    if (cost < best - 1e-12) { best = cost; bestG = G; }
+  }
+  p->G = bestG;
+  p->FPC = kLinThreads / bestG;
+  p->n_lin_ctas = (p->n_frames + p->FPC - 1) / p->FPC;
+}
+
+int upload_problem(ccrs_problem* p, int n_problems, const int32_t* problem_frame_offsets, int n_frames,
+                   const int32_t* frame_offsets, const double* x, const double* y, const double* z, const double* u,
+                   const double* v) {
+  p->n_frames = n_frames;
+  p->n_problems = n_problems;
+  p->n_obs = frame_offsets[n_frames];
+  p->Fs = (n_frames + 31) / 32 * 32;
+  p->h_frame_offsets.assign(frame_offsets, frame_offsets + n_frames + 1);
+  if (problem_frame_offsets) p->h_problem_frame_offsets.assign(problem_frame_offsets, problem_frame_offsets + n_problems + 1);
+  else p->h_problem_frame_offsets = {0, n_frames};
+  const size_t N = (size_t)p->n_obs, F = (size_t)n_frames, Fs = (size_t)p->Fs, P = (size_t)n_problems;
+  CK(p->x.alloc(N)); CK(p->y.alloc(N)); CK(p->z.alloc(N)); CK(p->u.alloc(N)); CK(p->v.alloc(N));
+  CK(p->frame_offsets.alloc(F + 1));
+  CK(p->problem_frame_offsets.alloc(P + 1));
+  CK(p->cur.alloc(P));
+  CK(p->acc_to_blk.alloc(p->NACC));
+  for (int i = 0; i < 2; ++i) {
+    CK(p->poses[i].alloc(F * 6));
+    CK(p->blocks[i].alloc((size_t)p->NBLK * Fs));
+    CK(p->frame_cost[i].alloc(Fs));
+    CK(cudaMemsetAsync(p->blocks[i].p, 0, (size_t)p->NBLK * Fs * sizeof(double), p->stream));  // structural zeros stay zero
+    CK(cudaMemsetAsync(p->poses[i].p, 0, F * 6 * sizeof(double), p->stream));
+  }
+  CK(p->elim.alloc((size_t)(6 * p->D + 18) * Fs));
+  const size_t n_schur_ctas = (F + 127) / 128;
+  CK(p->frame_red.alloc(std::max((size_t)p->NRED * Fs, n_schur_ctas * (size_t)p->NRED)));
+  CK(p->pose_scale.alloc(6 * Fs));
+  CK(p->frame_md.alloc(Fs));
+  CK(p->red_out.alloc(P * p->NRED));
+  CK(p->stat_out.alloc(P * 2));
+  CK(p->intr_dev.alloc(P * p->D)); CK(p->ya_dev.alloc(P * p->D)); CK(p->u_dev.alloc(P)); CK(p->scale_dev.alloc(P * p->D));
+  CK(p->mask_dev.alloc(P));
+  CK(p->h_red.alloc(P * p->NRED)); CK(p->h_stat.alloc(P * 2)); CK(p->h_small.alloc(P * (p->D + 2)));
+  CK(cudaMemsetAsync(p->cur.p, 0, P * sizeof(int32_t), p->stream));
+  CK(cudaMemsetAsync(p->u_dev.p, 0, P * sizeof(double), p->stream));
+  cudaStream_t s = p->stream;
+  CK(cudaMemcpyAsync(p->x.p, x, N * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(p->y.p, y, N * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(p->z.p, z, N * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(p->u.p, u, N * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(p->v.p, v, N * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(p->frame_offsets.p, frame_offsets, (F + 1) * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(p->problem_frame_offsets.p, p->h_problem_frame_offsets.data(), (P + 1) * 4, cudaMemcpyHostToDevice, s));
+  std::vector<int32_t> tbl(p->NACC);
+  fill_acc_to_blk(p->model, p->one_focal, tbl.data());
+  CK(cudaMemcpyAsync(p->acc_to_blk.p, tbl.data(), tbl.size() * 4, cudaMemcpyHostToDevice, s));
+  if (p->batch) {
+    std::vector<int32_t> fp(F);
+    for (int b = 0; b < n_problems; ++b)
+      for (int f = problem_frame_offsets[b]; f < problem_frame_offsets[b + 1]; ++f) fp[f] = b;
+    CK(p->frame_problem.alloc(F));
+    CK(cudaMemcpyAsync(p->frame_problem.p, fp.data(), F * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  CK(cudaStreamSynchronize(s));
+  choose_slicing(p);
+  return 0;
+}
+
+int create_common(ccrs_problem** out, int model, int width, int height, int xy_same_focal, int n_problems,
+                  const int32_t* problem_frame_offsets, int n_frames, const int32_t* frame_offsets, const double* x,
+                  const double* y, const double* z, const double* u, const double* v, double huber_delta, int device_id,
+                  bool batch) {
+  if (!out || !frame_offsets || !x || !y || !z || !u || !v || n_frames <= 0 || n_problems <= 0)
+    return fail(CCRS_ERR_INVALID, "null pointer or empty problem");
+  if (model < 0 || model > 5) return fail(CCRS_ERR_INVALID, "unknown model %d", model);
+  for (int f = 0; f < n_frames; ++f)
+    if (frame_offsets[f + 1] < frame_offsets[f]) return fail(CCRS_ERR_INVALID, "frame_offsets not monotone at %d", f);
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    return fail(CCRS_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
+  }
+  if (device_id < 0 || device_id >= n_dev) return fail(CCRS_ERR_INVALID, "device %d out of range", device_id);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device_id));
+  if (prop.major != 10) return fail(CCRS_ERR_NO_DEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only", device_id, prop.major, prop.minor);
+  CK(cudaSetDevice(device_id));
+  ccrs_problem* p = new ccrs_problem();
+  p->model = model; p->width = width; p->height = height; p->one_focal = xy_same_focal ? 1 : 0;
+  p->huber = huber_delta; p->device = device_id; p->batch = batch; p->n_sms = prop.multiProcessorCount;
+  model_dims(model, p->one_focal, &p->D, &p->NA, &p->NBLK, &p->NACC);
+  p->NRED = nred_of(p->D);
+  p->NOUT = p->D * p->D + 3 * p->D + 1;
+  cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete p; return fail(CCRS_ERR_CUDA, "stream: %s", cudaGetErrorString(e)); }
+  int st = upload_problem(p, n_problems, problem_frame_offsets, n_frames, frame_offsets, x, y, z, u, v);
+  if (st != 0) { ccrs_problem_destroy(p); return st; }
+  *out = p;
+  return 0;
+}
+
+// sum `count` doubles across ranks on the device (stream-ordered); in == out allowed
+int exchange(ccrs_problem* p, double* buf, size_t count) {
+  if (!p->comm) return 0;
+  NcclApi& n = nccl();
+  if (p->deterministic) {
+    if (p->gather.n < count * p->world) { p->gather.release(); CK(p->gather.alloc(count * p->world)); }
+    int r = n.AllGather(buf, p->gather.p, count, kNcclFloat64, p->comm, p->stream);
+    if (r != 0) return fail(CCRS_ERR_COMM, "ncclAllGather: %s", n.GetErrorString ? n.GetErrorString(r) : "?");
+    CK(launch_sum_partials(p->gather.p, p->world, (int)count, buf, p->stream));  // rank order
+    p->launches++;
+  } else {
+    int r = n.AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, p->comm, p->stream);
+    if (r != 0) return fail(CCRS_ERR_COMM, "ncclAllReduce: %s", n.GetErrorString ? n.GetErrorString(r) : "?");
+  }
+  return 0;
+}
+
+int upload_intr(ccrs_problem* p, const double* intr) {
+  const size_t n = (size_t)p->n_problems * p->D;
+  CK(cudaMemcpyAsync(p->intr_dev.p, intr, n * 8, cudaMemcpyHostToDevice, p->stream));
+  return 0;
+}
+
+int do_linearize(ccrs_problem* p, const double* intr, int which, bool cost_only) {
+  LinParams prm{};
+  prm.pb = p->dev();
+  prm.which = which; prm.G = p->G; prm.FPC = p->FPC;
+  prm.acc_to_blk = p->acc_to_blk.p;
+  if (p->batch) {
+    int st = upload_intr(p, intr);
+    if (st) return st;
+    prm.intr_dev = p->intr_dev.p;
+  } else {
+    if (p->one_focal) { prm.intr[0] = intr[0]; prm.intr[1] = intr[0]; for (int i = 1; i < p->D; ++i) prm.intr[i + 1] = intr[i]; }
+    else for (int i = 0; i < p->D; ++i) prm.intr[i] = intr[i];
+  }
+  CK(launch_linearize(p->model, p->one_focal, p->batch, cost_only, prm, p->n_lin_ctas, p->stream));
+  p->launches++;
+  return 0;
+}
+
+// per-problem sum of a per-frame array [NV][Fs] -> out_dev[n_problems][NV]
+int reduce_frames(ccrs_problem* p, const double* in, int NV, double* out_dev) {
+  CK(launch_segreduce(in, NV, p->Fs, p->problem_frame_offsets.p, p->n_problems, out_dev, p->stream));
+  p->launches++;
+  return 0;
+}
+
+int do_reduce(ccrs_problem* p, int which, const double* u, int use_scale, double min_diag, double max_diag, double* out) {
+  const int D = p->D, P = p->n_problems;
+  if (use_scale && !p->have_scale) return fail(CCRS_ERR_INVALID, "use_scale without ccrs_compute_scale/ccrs_set_intr_scale");
+  if (u) CK(cudaMemcpyAsync(p->u_dev.p, u, (size_t)P * 8, cudaMemcpyHostToDevice, p->stream));
+  else CK(cudaMemsetAsync(p->u_dev.p, 0, (size_t)P * 8, p->stream));
+  SchurParams prm{};
+  prm.pb = p->dev();
+  prm.which = which;
+  prm.u_dev = p->u_dev.p;
+  prm.intr_scale = use_scale ? p->scale_dev.p : nullptr;
+  prm.pose_scale = use_scale ? p->pose_scale.p : nullptr;
+  prm.min_diag = min_diag; prm.max_diag = max_diag;
+  prm.elim = p->elim.p;
+  prm.frame_red = p->frame_red.p;
+  p->last_use_scale = use_scale != 0;
+  CK(launch_schur(D, prm, p->stream));
+  p->launches++;
+  if (p->batch) {
+    int st = reduce_frames(p, p->frame_red.p, p->NRED, p->red_out.p);
+    if (st) return st;
+  } else {
+    CK(launch_sum_partials(p->frame_red.p, (p->n_frames + 127) / 128, p->NRED, p->red_out.p, p->stream));
+    p->launches++;
+  }
+  int st = exchange(p, p->red_out.p, (size_t)P * p->NRED);
+  if (st) return st;
+  CK(cudaMemcpyAsync(p->h_red.p, p->red_out.p, (size_t)P * p->NRED * 8, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  // unpack: packed upper S -> full row-major
+  const int NS = D * (D + 1) / 2;
+  for (int q = 0; q < P; ++q) {
+    const double* r = p->h_red.p + (size_t)q * p->NRED;
+    double* o = out + (size_t)q * p->NOUT;
+    int e = 0;
+    for (int a = 0; a < D; ++a)
+      for (int b = a; b < D; ++b) { o[a * D + b] = r[e]; o[b * D + a] = r[e]; ++e; }
+    for (int i = 0; i < 3 * D + 1; ++i) o[D * D + i] = r[NS + i];
+  }
+  return 0;
+}
+
+int do_backsub(ccrs_problem* p, const double* y_a, const double* u, const unsigned char* active, int in_place, bool want_md) {
+  const int P = p->n_problems, D = p->D;
+  CK(cudaMemcpyAsync(p->ya_dev.p, y_a, (size_t)P * D * 8, cudaMemcpyHostToDevice, p->stream));
+  if (u) CK(cudaMemcpyAsync(p->u_dev.p, u, (size_t)P * 8, cudaMemcpyHostToDevice, p->stream));
+  else CK(cudaMemsetAsync(p->u_dev.p, 0, (size_t)P * 8, p->stream));
+  BacksubParams prm{};
+  prm.pb = p->dev();
+  prm.elim = p->elim.p;
+  prm.y_a = p->ya_dev.p;
+  prm.u_dev = p->u_dev.p;
+  prm.pose_scale = p->last_use_scale ? p->pose_scale.p : nullptr;
+  prm.frame_md = want_md ? p->frame_md.p : nullptr;
+  prm.in_place = in_place;
+  prm.active = nullptr;
+  if (active) {
+    CK(cudaMemcpyAsync(p->mask_dev.p, active, (size_t)P, cudaMemcpyHostToDevice, p->stream));
+    prm.active = p->mask_dev.p;
+  }
+  CK(launch_backsub(D, prm, p->stream));
+  p->launches++;
+  return 0;
+}
+
+// ---- CUDA implementation of the controller's backend table ------------------------------------------------------
+int be_linearize(void* ctx, const double* intr, int which) { return do_linearize((ccrs_problem*)ctx, intr, which, false); }
+int be_compute_scale(void* ctx, int which, double* col_sq) { return ccrs_compute_scale((ccrs_problem*)ctx, which, col_sq); }
+int be_set_intr_scale(void* ctx, const double* s) { return ccrs_set_intr_scale((ccrs_problem*)ctx, s); }
+int be_reduce(void* ctx, int which, const double* u, int use_scale, double mn, double mx, double* out) {
+  return do_reduce((ccrs_problem*)ctx, which, u, use_scale, mn, mx, out);
+}
+int be_backsub(void* ctx, const double* y_a, const double* u, const unsigned char* active, int in_place) {
+  return do_backsub((ccrs_problem*)ctx, y_a, u, active, in_place, !in_place);
+}
+int be_trial_stats(void* ctx, const double* intr_trial, int speculative, double* out) {
+  ccrs_problem* p = (ccrs_problem*)ctx;
+  const int P = p->n_problems;
+  int st = do_linearize(p, intr_trial, 1, !speculative);
+  if (st) return st;
+  // stat_out[q] = {model_dec pose part, sq_err at the trial point}, reduced per problem in a fixed order
+  CK(launch_trial_stats(p->dev(), p->NBLK - 1, speculative, p->frame_md.p, p->stat_out.p, p->stream));
+  p->launches++;
+  st = exchange(p, p->stat_out.p, (size_t)P * 2);
+  if (st) return st;
+  CK(cudaMemcpyAsync(p->h_stat.p, p->stat_out.p, (size_t)P * 2 * 8, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  std::memcpy(out, p->h_stat.p, (size_t)P * 2 * 8);
+  return 0;
+}
+int be_accept(void* ctx, const unsigned char* mask) { return ccrs_accept((ccrs_problem*)ctx, mask); }
+
+ccrs_backend cuda_backend(ccrs_problem* p) {
+  ccrs_backend be{};
+  be.ctx = p; be.d = p->D; be.n_problems = p->n_problems;
+  be.linearize = be_linearize; be.compute_scale = be_compute_scale; be.set_intr_scale = be_set_intr_scale;
+  be.reduce = be_reduce; be.backsub = be_backsub; be.trial_stats = be_trial_stats; be.accept = be_accept;
+  be.allreduce = nullptr;  // exchanged on the device (NCCL) inside reduce / compute_scale / trial_stats
+  return be;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ccrs_model_nparams(int model) {
+  int D = 0;
+  if (model_dims(model, 0, &D, nullptr, nullptr, nullptr) != 0) return -1;
+  return D;
+}
+
+const char* ccrs_last_error(void) { return g_err; }
+
+int ccrs_problem_create(ccrs_problem** out, int model, int width, int height, int xy_same_focal, int n_frames,
+                        const int32_t* frame_offsets, const double* x, const double* y, const double* z,
+                        const double* u, const double* v, double huber_delta, int device_id) {
+  return create_common(out, model, width, height, xy_same_focal, 1, nullptr, n_frames, frame_offsets, x, y, z, u, v,
+                       huber_delta, device_id, false);
+}
+
+int ccrs_batch_create(ccrs_problem** out, int model, int width, int height, int xy_same_focal, int n_problems,
+                      const int32_t* problem_frame_offsets, int n_frames, const int32_t* frame_offsets, const double* x,
+                      const double* y, const double* z, const double* u, const double* v, double huber_delta,
+                      int device_id) {
+  if (!problem_frame_offsets || problem_frame_offsets[0] != 0 || problem_frame_offsets[n_problems] != n_frames)
+    return fail(CCRS_ERR_INVALID, "problem_frame_offsets must span [0, n_frames]");
+  return create_common(out, model, width, height, xy_same_focal, n_problems, problem_frame_offsets, n_frames,
+                       frame_offsets, x, y, z, u, v, huber_delta, device_id, true);
+}
+
+int ccrs_problem_destroy(ccrs_problem* p) {
+  if (!p) return 0;
+  cudaSetDevice(p->device);
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  if (p->comm && nccl().ok) nccl().CommDestroy(p->comm);
+  p->x.release(); p->y.release(); p->z.release(); p->u.release(); p->v.release();
+  p->frame_offsets.release(); p->frame_problem.release(); p->problem_frame_offsets.release(); p->obs_frame.release();
+  p->cur.release(); p->acc_to_blk.release();
+  for (int i = 0; i < 2; ++i) { p->poses[i].release(); p->blocks[i].release(); p->frame_cost[i].release(); }
+  p->elim.release(); p->frame_red.release(); p->pose_scale.release(); p->frame_md.release();
+  p->red_out.release(); p->stat_out.release(); p->gather.release(); p->intr_dev.release(); p->ya_dev.release();
+  p->u_dev.release(); p->scale_dev.release(); p->l2_flush.release(); p->mask_dev.release();
+  p->h_red.release(); p->h_stat.release(); p->h_small.release();
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+  return 0;
+}
+
+int ccrs_problem_dim(const ccrs_problem* p) { return p ? p->D : -1; }
+int ccrs_problem_nblk(const ccrs_problem* p) { return p ? p->NBLK : -1; }
+int ccrs_problem_n_frames(const ccrs_problem* p) { return p ? p->n_frames : -1; }
+int64_t ccrs_problem_n_obs(const ccrs_problem* p) { return p ? p->n_obs : -1; }
+int ccrs_problem_n_problems(const ccrs_problem* p) { return p ? p->n_problems : -1; }
+int64_t ccrs_launch_count(const ccrs_problem* p) { return p ? p->launches : -1; }
+
+int ccrs_set_poses(ccrs_problem* p, const double* poses) {
+  if (!p || !poses) return fail(CCRS_ERR_INVALID, "null");
+  CK(cudaSetDevice(p->device));
+  // "current" may differ per problem after accepts; resetting poses also resets the buffer selector
+  CK(cudaMemsetAsync(p->cur.p, 0, (size_t)p->n_problems * sizeof(int32_t), p->stream));
+  CK(cudaMemcpyAsync(p->poses[0].p, poses, (size_t)p->n_frames * 6 * 8, cudaMemcpyHostToDevice, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  return 0;
+}
+
+int ccrs_get_poses(ccrs_problem* p, double* poses) {
+  if (!p || !poses) return fail(CCRS_ERR_INVALID, "null");
+  CK(cudaSetDevice(p->device));
+  std::vector<int32_t> cur(p->n_problems);
+  std::vector<double> b0((size_t)p->n_frames * 6), b1;
+  CK(cudaMemcpyAsync(cur.data(), p->cur.p, cur.size() * 4, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaMemcpyAsync(b0.data(), p->poses[0].p, b0.size() * 8, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  bool any1 = false;
+  for (int c : cur) any1 |= (c != 0);
+  if (any1) {
+    b1.resize(b0.size());
+    CK(cudaMemcpyAsync(b1.data(), p->poses[1].p, b1.size() * 8, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+  }
+  for (int q = 0; q < p->n_problems; ++q) {
+    const std::vector<double>& src = cur[q] ? b1 : b0;
+    const size_t a = (size_t)p->h_problem_frame_offsets[q] * 6, b = (size_t)p->h_problem_frame_offsets[q + 1] * 6;
+    std::memcpy(poses + a, src.data() + a, (b - a) * 8);
+  }
+  return 0;
+}
+
+int ccrs_eval_rj(ccrs_problem* p, const double* intr, const double* poses, int apply_loss, double* r, double* J) {
+  if (!p || !intr || !r) return fail(CCRS_ERR_INVALID, "null");
+  if (p->batch) return fail(CCRS_ERR_INVALID, "ccrs_eval_rj is for single-problem handles");
+  CK(cudaSetDevice(p->device));
+  const size_t N = (size_t)p->n_obs;
+  if (!p->have_obs_frame) {
+    std::vector<int32_t> of(N);
+    for (int f = 0; f < p->n_frames; ++f)
+      for (int k = p->h_frame_offsets[f]; k < p->h_frame_offsets[f + 1]; ++k) of[k] = f;
+    CK(p->obs_frame.alloc(N));
+    CK(cudaMemcpyAsync(p->obs_frame.p, of.data(), N * 4, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    p->have_obs_frame = true;
+  }
+  const int n = p->D + 6;
+  DevBuf<double> d_r, d_J, d_pose;
+  CK(d_r.alloc(2 * N));
+  if (J) CK(d_J.alloc(2 * N * n));
+  int st = upload_intr(p, intr);
+  if (st) return st;
+  const double* pose_ptr = nullptr;
+  if (poses) {
+    CK(d_pose.alloc((size_t)p->n_frames * 6));
+    CK(cudaMemcpyAsync(d_pose.p, poses, (size_t)p->n_frames * 48, cudaMemcpyHostToDevice, p->stream));
+    pose_ptr = d_pose.p;
+  } else {
+    int32_t cur = 0;
+    CK(cudaMemcpyAsync(&cur, p->cur.p, 4, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    pose_ptr = p->poses[cur].p;
+  }
+  CK(launch_eval_rj(p->model, p->one_focal, p->dev(), p->intr_dev.p, pose_ptr, apply_loss, d_r.p, J ? d_J.p : nullptr,
+                    p->n_obs, p->stream));
+  p->launches++;
+  CK(cudaMemcpyAsync(r, d_r.p, 2 * N * 8, cudaMemcpyDeviceToHost, p->stream));
+  if (J) CK(cudaMemcpyAsync(J, d_J.p, 2 * N * n * 8, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  d_r.release(); d_J.release(); d_pose.release();
+  return 0;
+}
+
+int ccrs_linearize(ccrs_problem* p, const double* intr, int which, double* sq_err) {
+  if (!p || !intr) return fail(CCRS_ERR_INVALID, "null");
+  CK(cudaSetDevice(p->device));
+  int st = do_linearize(p, intr, which, false);
+  if (st) return st;
+  if (sq_err) {
+    CK(launch_trial_stats(p->dev(), p->NBLK - 1, which ? 1 : 2, nullptr, p->stat_out.p, p->stream));
+    p->launches++;
+    st = exchange(p, p->stat_out.p, (size_t)p->n_problems * 2);
+    if (st) return st;
+    CK(cudaMemcpyAsync(p->h_stat.p, p->stat_out.p, (size_t)p->n_problems * 16, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    for (int q = 0; q < p->n_problems; ++q) sq_err[q] = p->h_stat.p[2 * q + 1];
+  }
+  return 0;
+}
+
+int ccrs_get_frame_blocks(ccrs_problem* p, int which, double* blocks) {
+  if (!p || !blocks) return fail(CCRS_ERR_INVALID, "null");
+  CK(cudaSetDevice(p->device));
+  const size_t n = (size_t)p->NBLK * p->Fs;
+  std::vector<double> b[2];
+  std::vector<int32_t> cur(p->n_problems);
+  CK(cudaMemcpyAsync(cur.data(), p->cur.p, cur.size() * 4, cudaMemcpyDeviceToHost, p->stream));
+  for (int i = 0; i < 2; ++i) { b[i].resize(n); CK(cudaMemcpyAsync(b[i].data(), p->blocks[i].p, n * 8, cudaMemcpyDeviceToHost, p->stream)); }
+  CK(cudaStreamSynchronize(p->stream));
+  for (int q = 0; q < p->n_problems; ++q) {
+    const std::vector<double>& src = b[cur[q] ^ (which ? 1 : 0)];
+    for (int f = p->h_problem_frame_offsets[q]; f < p->h_problem_frame_offsets[q + 1]; ++f)
+      for (int e = 0; e < p->NBLK; ++e) blocks[(size_t)f * p->NBLK + e] = src[(size_t)e * p->Fs + f];
+  }
+  return 0;
+}
+
+int ccrs_compute_scale(ccrs_problem* p, int which, double* col_sq) {
+  if (!p || !col_sq) return fail(CCRS_ERR_INVALID, "null");
+  CK(cudaSetDevice(p->device));
+  // frame_red is free between reduce() calls: use it for the per-frame A_aa diagonals [D][Fs]
+  CK(launch_compute_scale(p->D, p->dev(), which, p->pose_scale.p, p->frame_red.p, p->stream));
+  p->launches++;
+  int st = reduce_frames(p, p->frame_red.p, p->D, p->red_out.p);
+  if (st) return st;
+  st = exchange(p, p->red_out.p, (size_t)p->n_problems * p->D);
+  if (st) return st;
+  CK(cudaMemcpyAsync(p->h_red.p, p->red_out.p, (size_t)p->n_problems * p->D * 8, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  std::memcpy(col_sq, p->h_red.p, (size_t)p->n_problems * p->D * 8);
+  return 0;
+}
+
+int ccrs_set_intr_scale(ccrs_problem* p, const double* intr_scale) {
+  if (!p) return fail(CCRS_ERR_INVALID, "null");
+  CK(cudaSetDevice(p->device));
+  if (!intr_scale) { p->have_scale = false; return 0; }
+  CK(cudaMemcpyAsync(p->scale_dev.p, intr_scale, (size_t)p->n_problems * p->D * 8, cudaMemcpyHostToDevice, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  p->have_scale = true;
+  return 0;
+}
+
+int ccrs_reduce(ccrs_problem* p, int which, const double* u, int use_scale, double min_diag, double max_diag, double* out) {
+  if (!p || !out) return fail(CCRS_ERR_INVALID, "null");
+  CK(cudaSetDevice(p->device));
+  return do_reduce(p, which, u, use_scale, min_diag, max_diag, out);
+}
+
+int ccrs_backsub(ccrs_problem* p, const double* y_a, const double* u, int in_place, double* model_dec) {
+  if (!p || !y_a) return fail(CCRS_ERR_INVALID, "null");
+  CK(cudaSetDevice(p->device));
+  int st = do_backsub(p, y_a, u, nullptr, in_place, model_dec != nullptr);
+  if (st) return st;
+  if (model_dec) {
+    CK(launch_trial_stats(p->dev(), p->NBLK - 1, 3, p->frame_md.p, p->stat_out.p, p->stream));
+    p->launches++;
+    st = exchange(p, p->stat_out.p, (size_t)p->n_problems * 2);
+    if (st) return st;
+    CK(cudaMemcpyAsync(p->h_stat.p, p->stat_out.p, (size_t)p->n_problems * 16, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    for (int q = 0; q < p->n_problems; ++q) model_dec[q] = p->h_stat.p[2 * q];
+  } else {
+    CK(cudaStreamSynchronize(p->stream));
+  }
+  return 0;
+}
+
+int ccrs_eval_cost(ccrs_problem* p, const double* intr, int which, double* sq_err) {
+  if (!p || !intr || !sq_err) return fail(CCRS_ERR_INVALID, "null");
+  CK(cudaSetDevice(p->device));
+  int st = do_linearize(p, intr, which, true);
+  if (st) return st;
+  CK(launch_trial_stats(p->dev(), p->NBLK - 1, which ? 0 : 4, nullptr, p->stat_out.p, p->stream));
+  p->launches++;
+  st = exchange(p, p->stat_out.p, (size_t)p->n_problems * 2);
+  if (st) return st;
+  CK(cudaMemcpyAsync(p->h_stat.p, p->stat_out.p, (size_t)p->n_problems * 16, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  for (int q = 0; q < p->n_problems; ++q) sq_err[q] = p->h_stat.p[2 * q + 1];
+  return 0;
+}
+
+int ccrs_accept(ccrs_problem* p, const unsigned char* mask) {
+  if (!p) return fail(CCRS_ERR_INVALID, "null");
+  CK(cudaSetDevice(p->device));
+  const unsigned char* md = nullptr;
+  if (mask) {
+    CK(cudaMemcpyAsync(p->mask_dev.p, mask, (size_t)p->n_problems, cudaMemcpyHostToDevice, p->stream));
+    md = p->mask_dev.p;
+  }
+  CK(launch_flip_cur(p->cur.p, md, p->n_problems, p->stream));
+  p->launches++;
+  return 0;
+}
+
+int ccrs_comm_unique_id(void* unique_id_128) {
+  NcclApi& n = nccl();
+  if (!n.ok) return fail(CCRS_ERR_COMM, "libnccl.so.2 not loadable: %s", dlerror());
+  ncclUniqueId id;
+  int r = n.GetUniqueId(&id);
+  if (r != 0) return fail(CCRS_ERR_COMM, "ncclGetUniqueId failed (%d)", r);
+  std::memcpy(unique_id_128, &id, 128);
+  return 0;
+}
+
+int ccrs_comm_init(ccrs_problem* p, const void* unique_id_128, int rank, int world_size) {
+  if (!p || !unique_id_128 || world_size < 1 || rank < 0 || rank >= world_size) return fail(CCRS_ERR_INVALID, "bad comm args");
+  NcclApi& n = nccl();
+  if (!n.ok) return fail(CCRS_ERR_COMM, "libnccl.so.2 not loadable");
+  CK(cudaSetDevice(p->device));
+  ncclUniqueId id;
+  std::memcpy(&id, unique_id_128, 128);
+  int r = n.CommInitRank(&p->comm, world_size, id, rank);
+  if (r != 0) return fail(CCRS_ERR_COMM, "ncclCommInitRank: %s", n.GetErrorString ? n.GetErrorString(r) : "?");
+  p->rank = rank; p->world = world_size;
+  return 0;
+}
+
+int ccrs_comm_set_deterministic(ccrs_problem* p, int deterministic) {
+  if (!p) return fail(CCRS_ERR_INVALID, "null");
+  p->deterministic = deterministic ? 1 : 0;
+  return 0;
+}
+
+static int timed_solve(ccrs_problem* p, bool lm, double* intr, const double* lo, const double* hi,
+                       const unsigned char* fixed, const ccrs_options* opt, ccrs_summary* summary, double* err_hist) {
+  if (!p || !intr) return fail(CCRS_ERR_INVALID, "null");
+  CK(cudaSetDevice(p->device));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, p->stream));
+  ccrs_backend be = cuda_backend(p);
+  ccrs_summary local;
+  if (!summary) summary = &local;
+  int st = lm ? ccrs_controller_lm(&be, intr, lo, hi, fixed, opt, summary, err_hist)
+              : ccrs_controller_gn(&be, intr, lo, hi, fixed, opt, summary, err_hist);
+  cudaEventRecord(e1, p->stream);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  summary->device_ms = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (st == CCRS_ERR_CHOLESKY) fail(st, "Cholesky failure (non-positive pivot)");
+  if (st == CCRS_ERR_NUMERIC) fail(st, "NaN error");
+  return st;
+}
+
+int ccrs_solve_gn(ccrs_problem* p, double* intr, const double* lo, const double* hi, const unsigned char* fixed,
+                  const ccrs_options* opt, ccrs_summary* summary, double* err_hist) {
+  return timed_solve(p, false, intr, lo, hi, fixed, opt, summary, err_hist);
+}
+int ccrs_solve_lm(ccrs_problem* p, double* intr, const double* lo, const double* hi, const unsigned char* fixed,
+                  const ccrs_options* opt, ccrs_summary* summary, double* err_hist) {
+  return timed_solve(p, true, intr, lo, hi, fixed, opt, summary, err_hist);
+}
+
+int ccrs_model_bounds(int model, int width, int height, double* lo, double* hi) {
+  const int n = ccrs_model_nparams(model);
+  if (n < 0 || !lo || !hi) return fail(CCRS_ERR_INVALID, "bad model");
+  const double inf = std::numeric_limits<double>::infinity();
+  for (int i = 0; i < n; ++i) { lo[i] = -inf; hi[i] = inf; }
+  lo[0] = 0; hi[0] = 1e4; lo[1] = 0; hi[1] = 1e4;       // util.rs:36-37
+  lo[2] = 0; hi[2] = width; lo[3] = 0; hi[3] = height;  // util.rs:38-39
+  // GenericModel::distortion_params_bound() — restated (unpinned)
+  switch (model) {
+    case CCRS_UCM: lo[4] = 1e-6; hi[4] = 1.0; break;
+    case CCRS_EUCM: case CCRS_EUCMT: lo[4] = 1e-6; hi[4] = 1.0; lo[5] = 1e-6; hi[5] = 100.0;
+      if (model == CCRS_EUCMT) { lo[6] = lo[7] = -1.0; hi[6] = hi[7] = 1.0; }
+      break;
+    case CCRS_KB4: case CCRS_FTHETA: for (int i = 4; i < 8; ++i) { lo[i] = -1.0; hi[i] = 1.0; } break;
+    case CCRS_OPENCV5: for (int i = 4; i < 9; ++i) { lo[i] = -1.0; hi[i] = 1.0; } break;
+  }
+  return 0;
+}
+
+int ccrs_calib_camera(int model, int width, int height, int n_frames, const int32_t* frame_offsets, const double* x,
+                      const double* y, const double* z, const double* u, const double* v, double* params, double* poses,
+                      int xy_same_focal, int disabled_distortions, int fixed_focal, int use_lm, const ccrs_options* opt,
+                      ccrs_summary* summary, int device_id) {
+  if (!params || !poses) return fail(CCRS_ERR_INVALID, "null");
+  const int nfull = ccrs_model_nparams(model);
+  if (nfull < 0) return fail(CCRS_ERR_INVALID, "bad model");
+  const int shift = xy_same_focal ? 1 : 0;
+  const int d = nfull - shift;
+  if (disabled_distortions < 0 || disabled_distortions > nfull - 4) return fail(CCRS_ERR_INVALID, "disabled_distortions out of range");
+  ccrs_problem* p = nullptr;
+  int st = ccrs_problem_create(&p, model, width, height, xy_same_focal, n_frames, frame_offsets, x, y, z, u, v, 1.0, device_id);
+  if (st) return st;
+  // params.remove_row(1) (util.rs:391-395)
+  std::vector<double> intr(d), lo(d), hi(d), flo(nfull), fhi(nfull);
+  std::vector<unsigned char> fixed(d, 0);
+  ccrs_model_bounds(model, width, height, flo.data(), fhi.data());
+  for (int i = 0, j = 0; i < nfull; ++i) {
+    if (xy_same_focal && i == 1) continue;
+    intr[j] = params[i]; lo[j] = flo[i]; hi[j] = fhi[i]; ++j;
+  }
+  // set_problem_parameter_disabled (util.rs:50-71): fix + zero the last N distortion parameters
+  for (int i = 0; i < disabled_distortions; ++i) { const int idx = nfull - 1 - shift - i; fixed[idx] = 1; intr[idx] = 0.0; }
+  st = ccrs_set_poses(p, poses);
+  ccrs_summary s1{}, s2{};
+  if (!st) st = use_lm ? ccrs_solve_lm(p, intr.data(), lo.data(), hi.data(), fixed.data(), opt, &s1, nullptr)
+                       : ccrs_solve_gn(p, intr.data(), lo.data(), hi.data(), fixed.data(), opt, &s1, nullptr);
+  if (!st && fixed_focal) {  // util.rs:459-464: fix params[0], reset it to the input focal, optimise again
+    fixed[0] = 1;
+    intr[0] = params[0];
+    st = use_lm ? ccrs_solve_lm(p, intr.data(), lo.data(), hi.data(), fixed.data(), opt, &s2, nullptr)
+                : ccrs_solve_gn(p, intr.data(), lo.data(), hi.data(), fixed.data(), opt, &s2, nullptr);
+    s1.iterations += s2.iterations; s1.device_ms += s2.device_ms; s1.final_error = s2.final_error;
+    s1.stop_reason = s2.stop_reason; s1.n_accepted += s2.n_accepted; s1.n_rejected += s2.n_rejected;
+  }
+  s1.status = st;
+  if (summary) *summary = s1;
+  if (!st) {
+    // new_params.insert_row(1, new_params[0]) (util.rs:466-470)
+    for (int i = 0, j = 0; i < nfull; ++i) {
+      if (xy_same_focal && i == 1) { params[1] = intr[0]; continue; }
+      params[i] = intr[j++];
+    }
+    st = ccrs_get_poses(p, poses);
+  }
+  ccrs_problem_destroy(p);
+  return st;
+}
+
+int ccrs_measure_fp64_peak(int device_id, double* tflops) {
+  if (!tflops) return fail(CCRS_ERR_INVALID, "null");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { cudaGetLastError(); return fail(CCRS_ERR_NO_DEVICE, "no CUDA device"); }
+  CK(cudaSetDevice(device_id));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device_id));
+  const int ctas = prop.multiProcessorCount * 8, iters = 1 << 14;
+  double* out = nullptr;
+  CK(cudaMalloc((void**)&out, (size_t)ctas * 256 * 8));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(e0, 0));
+    CK(launch_fp64_peak(out, ctas, iters, 0));
+    CK(cudaEventRecord(e1, 0));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 8.0 * iters * (double)ctas * 256.0;
+    best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = best;
+  return 0;
+}
+
+int ccrs_time_linearize(ccrs_problem* p, const double* intr, int reps, int flush_l2, double* avg_ms) {
+  if (!p || !intr || !avg_ms || reps <= 0) return fail(CCRS_ERR_INVALID, "bad args");
+  CK(cudaSetDevice(p->device));
+  const size_t flush_n = (size_t)64 << 20;  // 512 MB of doubles > 126 MB L2
+  if (flush_l2 && !p->l2_flush.p) CK(p->l2_flush.alloc(flush_n));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  double total = 0.0;
+  for (int w = 0; w < 3; ++w) { int st = do_linearize(p, intr, 0, false); if (st) return st; }
+  CK(cudaStreamSynchronize(p->stream));
+  if (flush_l2) {
+    for (int r = 0; r < reps; ++r) {
+      CK(launch_l2_flush(p->l2_flush.p, flush_n, p->stream));
+      CK(cudaEventRecord(e0, p->stream));
+      int st = do_linearize(p, intr, 0, false);
+      if (st) return st;
+      CK(cudaEventRecord(e1, p->stream));
+      CK(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      total += ms;
+    }
+  } else {
+    CK(cudaEventRecord(e0, p->stream));
+    for (int r = 0; r < reps; ++r) { int st = do_linearize(p, intr, 0, false); if (st) return st; }
+    CK(cudaEventRecord(e1, p->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    total = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *avg_ms = total / reps;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,239 @@
+// ccrs_controller.cpp — host-side loop controllers, backend-agnostic (plain C++, no CUDA).
+//
+// Replaces tiny_solver::GaussNewtonOptimizer::optimize (the loop the reference runs: src/util.rs:443-464,
+// :668-670) and tiny-solver's LevenbergMarquardtOptimizer::optimize (named by north_star),
+// keeping on the host exactly what north_star keeps there: damping and accept/reject control, the small
+// (d x d) intrinsic solve, bounds clamp and fixed-variable reset (src/util.rs:29-71; tiny-solver
+// ParameterBlock::update_params). Everything per-observation / per-frame happens behind ccrs_backend.
+#include "../../include/ccrs_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+// Restated tiny-solver constants (unverifiable here — see SURVEY App. B; mirrored in oracle/ccrs_oracle.hpp)
+constexpr bool kErrorIsL2Norm = true;   // optimisers compare ||r||, not ||r||^2
+constexpr double kLmRejectFactor0 = 2.0;
+
+inline double err_metric(double sq) { return kErrorIsL2Norm ? std::sqrt(sq) : sq; }
+
+// in-place lower Cholesky of a dense n x n SPD matrix; false on a non-positive pivot
+bool chol_factor(double* A, int n) {
+  for (int j = 0; j < n; ++j) {
+    double s = A[j * n + j];
+    for (int k = 0; k < j; ++k) s -= A[j * n + k] * A[j * n + k];
+    if (!(s > 0.0)) return false;
+    const double l = std::sqrt(s);
+    A[j * n + j] = l;
+    for (int i = j + 1; i < n; ++i) {
+      double t = A[i * n + j];
+      for (int k = 0; k < j; ++k) t -= A[i * n + k] * A[j * n + k];
+      A[i * n + j] = t / l;
+    }
+  }
+  return true;
+}
+void chol_solve(const double* L, int n, double* b) {
+  for (int i = 0; i < n; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= L[i * n + k] * b[k]; b[i] = s / L[i * n + i]; }
+  for (int i = n - 1; i >= 0; --i) { double s = b[i]; for (int k = i + 1; k < n; ++k) s -= L[k * n + i] * b[k]; b[i] = s / L[i * n + i]; }
+}
+
+struct Reduced {  // view into one problem's slice of the reduce() output
+  const double *S, *gs, *ga, *diag;
+  double sq_err;
+};
+inline Reduced view(const double* out, int d) {
+  return Reduced{out, out + d * d, out + d * d + d, out + d * d + 2 * d, out[d * d + 3 * d]};
+}
+
+// Solve the damped intrinsic system of one problem. Returns 0 / CCRS_ERR_CHOLESKY / CCRS_ERR_NUMERIC.
+int solve_intrinsics(const Reduced& r, int d, double u, double min_diag, double max_diag, const unsigned char* fixed,
+                     int fixed_mode, double* y, double* model_dec_a) {
+  std::vector<double> S(r.S, r.S + d * d), g(r.gs, r.gs + d);
+  std::vector<double> dd(d);
+  for (int i = 0; i < d; ++i) {
+    dd[i] = std::min(std::max(r.diag[i], min_diag), max_diag);
+    S[i * d + i] += u * dd[i];
+  }
+  if (fixed && fixed_mode == 1)
+    for (int i = 0; i < d; ++i)
+      if (fixed[i]) { for (int j = 0; j < d; ++j) { S[i * d + j] = 0; S[j * d + i] = 0; } S[i * d + i] = 1; g[i] = 0; }
+  for (int i = 0; i < d * d; ++i) if (std::isnan(S[i])) return CCRS_ERR_CHOLESKY;  // poisoned by a failed frame pivot
+  if (!chol_factor(S.data(), d)) return CCRS_ERR_CHOLESKY;
+  for (int i = 0; i < d; ++i) y[i] = g[i];
+  chol_solve(S.data(), d, y);
+  if (model_dec_a) {  // y_a^T g'_a + u * sum dd_i y_i^2 (intrinsic part of y^T(2g' - H'y), using H_reg y = g')
+    double md = 0.0;
+    for (int i = 0; i < d; ++i) md += y[i] * r.ga[i] + u * dd[i] * y[i] * y[i];
+    *model_dec_a = md;
+  }
+  return 0;
+}
+
+// ParameterBlock::update_params: new = old + dx ; clamp bounded indices ; fixed indices keep the old value
+void update_intr(int d, const double* intr, const double* dx, const double* lo, const double* hi,
+                 const unsigned char* fixed, double* out) {
+  for (int i = 0; i < d; ++i) {
+    double v = intr[i] + dx[i];
+    if (lo && hi) v = std::min(std::max(v, lo[i]), hi[i]);
+    if (fixed && fixed[i]) v = intr[i];
+    out[i] = v;
+  }
+}
+
+#define BE(call)                         \
+  do {                                   \
+    int _st = (call);                    \
+    if (_st != 0) { sum->status = _st; return _st; } \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+void ccrs_default_options(ccrs_options* o) {
+  o->max_iteration = 100;
+  o->min_abs_decrease = 1e-5;
+  o->min_rel_decrease = 1e-5;
+  o->min_error = 1e-10;
+  o->lm_initial_radius = 1e4;
+  o->lm_min_diag = 1e-6;
+  o->lm_max_diag = 1e32;
+  o->fixed_mode = 0;
+  o->speculative = 1;
+  o->verbose = 0;
+}
+
+int ccrs_controller_gn(const ccrs_backend* be, double* intr, const double* lo, const double* hi,
+                       const unsigned char* fixed, const ccrs_options* opt_in, ccrs_summary* sum, double* err_hist) {
+  ccrs_options opt;
+  if (opt_in) opt = *opt_in; else ccrs_default_options(&opt);
+  ccrs_summary local_sum;
+  if (!sum) sum = &local_sum;
+  std::memset(sum, 0, sizeof(*sum));
+  const int d = be->d, P = be->n_problems, NOUT = d * d + 3 * d + 1;
+  std::vector<double> out((size_t)P * NOUT), y((size_t)P * d, 0.0), last_err(P, 0.0);
+  std::vector<unsigned char> active(P, 1);
+  std::vector<int> stop(P, 0);
+  int worst = 0;
+  for (int it = 0; it < opt.max_iteration; ++it) {
+    BE(be->linearize(be->ctx, intr, 0));
+    BE(be->reduce(be->ctx, 0, nullptr, 0, opt.lm_min_diag, opt.lm_max_diag, out.data()));
+    if (be->allreduce) BE(be->allreduce(be->ctx, out.data(), (int)out.size()));
+    sum->iterations = it + 1;
+    int n_active = 0;
+    for (int p = 0; p < P; ++p) {
+      if (!active[p]) continue;
+      const Reduced r = view(&out[(size_t)p * NOUT], d);
+      const double err = err_metric(r.sq_err);
+      if (p == 0) { if (err_hist) err_hist[it] = err; sum->final_error = err; }
+      if (err < opt.min_error) { active[p] = 0; stop[p] = 1; continue; }
+      if (std::isnan(err)) { active[p] = 0; worst = CCRS_ERR_NUMERIC; continue; }
+      if (it > 0) {
+        if (std::fabs(last_err[p] - err) < opt.min_abs_decrease) { active[p] = 0; stop[p] = 2; continue; }
+        if (std::fabs(last_err[p] - err) / last_err[p] < opt.min_rel_decrease) { active[p] = 0; stop[p] = 3; continue; }
+      }
+      last_err[p] = err;
+      double* yp = &y[(size_t)p * d];
+      const int st = solve_intrinsics(r, d, 0.0, opt.lm_min_diag, opt.lm_max_diag, fixed, opt.fixed_mode, yp, nullptr);
+      if (st != 0) { active[p] = 0; worst = st; continue; }
+      update_intr(d, intr + (size_t)p * d, yp, lo, hi, fixed, intr + (size_t)p * d);
+      ++n_active;
+    }
+    if (n_active == 0) break;
+    BE(be->backsub(be->ctx, y.data(), nullptr, P > 1 ? active.data() : nullptr, 1));
+  }
+  sum->stop_reason = stop[0];
+  sum->status = worst;
+  return worst;
+}
+
+int ccrs_controller_lm(const ccrs_backend* be, double* intr, const double* lo, const double* hi,
+                       const unsigned char* fixed, const ccrs_options* opt_in, ccrs_summary* sum, double* err_hist) {
+  ccrs_options opt;
+  if (opt_in) opt = *opt_in; else ccrs_default_options(&opt);
+  ccrs_summary local_sum;
+  if (!sum) sum = &local_sum;
+  std::memset(sum, 0, sizeof(*sum));
+  const int d = be->d, P = be->n_problems, NOUT = d * d + 3 * d + 1;
+  std::vector<double> out((size_t)P * NOUT), y((size_t)P * d, 0.0), scale((size_t)P * d, 1.0), colsq((size_t)P * d);
+  std::vector<double> u(P, 1.0 / opt.lm_initial_radius), v(P, kLmRejectFactor0), cur_err(P, 0.0), md_a(P, 0.0);
+  std::vector<double> trial((size_t)P * d), dx(d), stats((size_t)P * 2);
+  std::vector<unsigned char> active(P, 1), acc_mask(P, 0);
+  std::vector<int> stop(P, 0);
+  int worst = 0;
+
+  BE(be->linearize(be->ctx, intr, 0));
+  // Jacobi scaling 1/(1+||J[:,c]||) from the first (loss-corrected) Jacobian
+  BE(be->compute_scale(be->ctx, 0, colsq.data()));
+  if (be->allreduce) BE(be->allreduce(be->ctx, colsq.data(), (int)colsq.size()));
+  for (size_t i = 0; i < scale.size(); ++i) scale[i] = 1.0 / (1.0 + std::sqrt(colsq[i]));
+  BE(be->set_intr_scale(be->ctx, scale.data()));
+
+  for (int it = 0; it < opt.max_iteration; ++it) {
+    BE(be->reduce(be->ctx, 0, u.data(), 1, opt.lm_min_diag, opt.lm_max_diag, out.data()));
+    if (be->allreduce) BE(be->allreduce(be->ctx, out.data(), (int)out.size()));
+    sum->iterations = it + 1;
+    int n_active = 0;
+    for (int p = 0; p < P; ++p) {
+      std::memcpy(&trial[(size_t)p * d], intr + (size_t)p * d, d * sizeof(double));
+      if (!active[p]) continue;
+      const Reduced r = view(&out[(size_t)p * NOUT], d);
+      if (it == 0) cur_err[p] = err_metric(r.sq_err);
+      double* yp = &y[(size_t)p * d];
+      const int st = solve_intrinsics(r, d, u[p], opt.lm_min_diag, opt.lm_max_diag, fixed, opt.fixed_mode, yp, &md_a[p]);
+      if (st != 0) { active[p] = 0; worst = st; continue; }
+      for (int i = 0; i < d; ++i) dx[i] = scale[(size_t)p * d + i] * yp[i];
+      update_intr(d, intr + (size_t)p * d, dx.data(), lo, hi, fixed, &trial[(size_t)p * d]);
+      ++n_active;
+    }
+    if (n_active == 0) break;
+    BE(be->backsub(be->ctx, y.data(), u.data(), P > 1 ? active.data() : nullptr, 0));
+    BE(be->trial_stats(be->ctx, trial.data(), opt.speculative, stats.data()));
+    if (be->allreduce) BE(be->allreduce(be->ctx, stats.data(), (int)stats.size()));
+    bool any_accept = false;
+    for (int p = 0; p < P; ++p) {
+      acc_mask[p] = 0;
+      if (!active[p]) continue;
+      const Reduced r = view(&out[(size_t)p * NOUT], d);
+      const double new_sq = stats[2 * p + 1];
+      const double rho = (r.sq_err - new_sq) / (md_a[p] + stats[2 * p]);
+      const double last_err = cur_err[p];
+      bool accepted = false;
+      if (rho > 0.0) {
+        accepted = true; acc_mask[p] = 1; any_accept = true;
+        std::memcpy(intr + (size_t)p * d, &trial[(size_t)p * d], d * sizeof(double));
+        const double t = 2.0 * rho - 1.0;
+        u[p] *= std::max(1.0 / 3.0, 1.0 - t * t * t);
+        v[p] = kLmRejectFactor0;
+        cur_err[p] = err_metric(new_sq);
+        if (p == 0) sum->n_accepted++;
+      } else {
+        u[p] *= v[p]; v[p] *= 2.0;
+        if (p == 0) sum->n_rejected++;
+      }
+      if (p == 0) { if (err_hist) err_hist[it] = cur_err[p]; sum->final_error = cur_err[p]; }
+      if (cur_err[p] < opt.min_error) { active[p] = 0; stop[p] = 1; }
+      else if (std::isnan(cur_err[p]) || std::isnan(rho)) { active[p] = 0; worst = CCRS_ERR_NUMERIC; }
+      else if (accepted) {  // stop tests compare successive ACCEPTED errors
+        if (std::fabs(last_err - cur_err[p]) < opt.min_abs_decrease) { active[p] = 0; stop[p] = 2; }
+        else if (std::fabs(last_err - cur_err[p]) / last_err < opt.min_rel_decrease) { active[p] = 0; stop[p] = 3; }
+      }
+    }
+    if (any_accept) {
+      BE(be->accept(be->ctx, acc_mask.data()));
+      if (!opt.speculative) BE(be->linearize(be->ctx, intr, 0));
+    }
+    bool any_active = false;
+    for (int p = 0; p < P; ++p) any_active |= (active[p] != 0);
+    if (!any_active) break;
+  }
+  sum->stop_reason = stop[0];
+  sum->status = worst;
+  return worst;
+}
+
+}  // extern "C"

@@ -1,0 +1,739 @@
+// ccrs_kernels.cu — hand-written sm_100a FP64 kernels of the linearisation path.
+//
+//  K1 k_eval_rj      parity hook: per-observation residual (2) + Jacobian (2 x (d+6)), materialised (HBM-bound)
+//  K2 k_linearize    fused residual + analytic Jacobian + Huber corrector + per-frame Gram blocks, no per-observation
+//                    output (FP64-pipe-bound); COST_ONLY variant = K5 (residual-only robust cost)
+//  K3 k_schur        per-frame damping, 6x6 Cholesky, elimination onto the intrinsic system, fixed-order reduction
+//  K4 k_backsub      pose back-substitution, trial poses, LM model-decrease
+// They replace, per iteration, tiny-solver's Problem::compute_residual_and_jacobian (num-dual autodiff of
+// ReprojectionFactor::residual_func, reference src/optimization/factors.rs:152-173), the sparse J^T J product and
+// the sparse LLT (call sites src/util.rs:455,463,670). No tensor cores: there is no dense contraction, the
+// per-frame blocks are 6x6 / 6xd. Determinism: no floating-point atomics anywhere; every sum has a fixed order.
+#include "ccrs_device.cuh"
+#include "ccrs_kernels.cuh"
+
+#include <type_traits>
+
+namespace ccrs {
+
+template <int B, int E, class F>
+CCRS_D void static_for(F&& f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, B>{});
+    static_for<B + 1, E>(f);
+  }
+}
+
+// Compile-time shape of one (model, one_focal) instantiation.
+// Column order of a row of [J | r]: [intrinsics (D) | phi/rvec (3) | tvec (3) | r].
+// Structural sparsity: the u-row never touches fy,cy and the v-row never touches fx,cx
+// (u = fx*mx + cx, v = fy*my + cy), so those products are never formed nor stored in registers.
+template <int MODEL, bool OF>
+struct Cfg {
+  static constexpr int ND = model_nd(MODEL);
+  static constexpr int DFULL = 4 + ND;
+  static constexpr int D = DFULL - (OF ? 1 : 0);
+  static constexpr int N = D + 6;
+  static constexpr int NA = N + 1;
+  static constexpr int NBLK = NA * (NA + 1) / 2;
+  static constexpr int KOFF = OF ? 3 : 4;  // first distortion column
+  CCRS_HD static constexpr bool nzu(int c) { return OF ? (c != 2) : (c != 1 && c != 3); }
+  CCRS_HD static constexpr bool nzv(int c) { return OF ? (c != 1) : (c != 0 && c != 2); }
+  CCRS_HD static constexpr bool hasu(int i, int j) { return nzu(i) && nzu(j); }
+  CCRS_HD static constexpr bool hasv(int i, int j) { return nzv(i) && nzv(j); }
+  CCRS_HD static constexpr bool has(int i, int j) { return hasu(i, j) || hasv(i, j); }
+  // index of (i<=j) among the structurally non-zero upper entries, row-major; -1 if structurally zero
+  CCRS_HD static constexpr int kidx(int i, int j) {
+    if (!has(i, j)) return -1;
+    int k = 0;
+    for (int a = 0; a < NA; ++a)
+      for (int b = a; b < NA; ++b) {
+        if (a == i && b == j) return k;
+        if (has(a, b)) ++k;
+      }
+    return -1;
+  }
+  CCRS_HD static constexpr int nacc() {
+    int k = 0;
+    for (int a = 0; a < NA; ++a)
+      for (int b = a; b < NA; ++b)
+        if (has(a, b)) ++k;
+    return k;
+  }
+  static constexpr int NACC = nacc();
+};
+
+// One observation: weighted rows au, av of [J | r] in the LOCAL rotation basis (d/dphi, not d/drvec).
+// Returns the corrected squared residual. Structurally-zero entries of au/av are left untouched.
+template <int MODEL, bool OF, bool WITH_J>
+CCRS_D double obs_rows(const double* __restrict__ ip /* full intrinsics */, const double* __restrict__ fc /* R t */,
+                       double px, double py, double pz, double ou, double ov, double delta,
+                       double* __restrict__ au, double* __restrict__ av) {
+  using C = Cfg<MODEL, OF>;
+  const double fx = ip[0], fy = OF ? ip[0] : ip[1], cx = ip[2], cy = ip[3];
+  // q = R p ; P = q + t       (Isometry3::new(tvec, rvec) * p3d, factors.rs:162-163)
+  const double qx = fma(fc[0], px, fma(fc[1], py, fc[2] * pz));
+  const double qy = fma(fc[3], px, fma(fc[4], py, fc[5] * pz));
+  const double qz = fma(fc[6], px, fma(fc[7], py, fc[8] * pz));
+  const double X = qx + fc[9], Y = qy + fc[10], Z = qz + fc[11];
+  double m[2], dP[2][3], dk[2][kMaxNd];
+  model_eval<MODEL, WITH_J>(ip + 4, X, Y, Z, m, dP, dk);   // project_one (factors.rs:165)
+  const double ru = fma(fx, m[0], cx) - ou;                 // - p2d (factors.rs:167-171)
+  const double rv = fma(fy, m[1], cy) - ov;
+  const double s = ru * ru + rv * rv;
+  const double w = huber_weight(s, delta);                  // Corrector: r *= sqrt(rho'), J *= sqrt(rho')
+  if constexpr (WITH_J) {
+    const double wfx = w * fx, wfy = w * fy;
+    const double du0 = wfx * dP[0][0], du1 = wfx * dP[0][1], du2 = wfx * dP[0][2];
+    const double dv0 = wfy * dP[1][0], dv1 = wfy * dP[1][1], dv2 = wfy * dP[1][2];
+    if constexpr (OF) {
+      au[0] = w * m[0]; av[0] = w * m[1];  // shared focal column
+      au[1] = w;                            // cx
+      av[2] = w;                            // cy
+    } else {
+      au[0] = w * m[0]; av[1] = w * m[1];
+      au[2] = w; av[3] = w;
+    }
+#pragma unroll
+    for (int j = 0; j < C::ND; ++j) { au[C::KOFF + j] = wfx * dk[0][j]; av[C::KOFF + j] = wfy * dk[1][j]; }
+    // d/dphi row = (q x d)^T   since d(Exp(phi) q)/dphi = -[q]x
+    au[C::D + 0] = qy * du2 - qz * du1; au[C::D + 1] = qz * du0 - qx * du2; au[C::D + 2] = qx * du1 - qy * du0;
+    av[C::D + 0] = qy * dv2 - qz * dv1; av[C::D + 1] = qz * dv0 - qx * dv2; av[C::D + 2] = qx * dv1 - qy * dv0;
+    au[C::D + 3] = du0; au[C::D + 4] = du1; au[C::D + 5] = du2;
+    av[C::D + 3] = dv0; av[C::D + 4] = dv1; av[C::D + 5] = dv2;
+    au[C::N] = w * ru; av[C::N] = w * rv;
+  }
+  return s * w * w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 / K5. One CTA owns FPC consecutive frames; G lanes cooperate on a frame, lane j taking observations
+// j, j+G, ... (so the G lanes read G consecutive doubles of each SoA array: coalesced, no reliance on L1).
+// Every lane keeps the whole packed Gram block of its slice in registers (NACC FP64 accumulators), rotates it
+// from the local rotation basis to the rvec basis once (J_l), then the slices of a frame are summed in lane
+// order through shared memory and the frame block is written SoA to HBM.
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, bool OF, bool BATCH, bool COST_ONLY>
+__global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const __grid_constant__ LinParams prm) {
+  using C = Cfg<MODEL, OF>;
+  extern __shared__ double smem[];
+  const ProblemDev& pb = prm.pb;
+  const int t = threadIdx.x;
+  const int G = prm.G, FPC = prm.FPC;
+  const int f0 = blockIdx.x * FPC;
+  const int nf = min(FPC, pb.n_frames - f0);
+  double* s_fc = smem;                                   // [FPC][kFrameConst]
+  double* s_intr = s_fc + FPC * kFrameConst;             // [FPC][kMaxFull]   (BATCH only)
+  double* s_red = s_intr + (BATCH ? FPC * kMaxFull : 0); // [kRedChunk][kLinThreads]
+
+  if (t < nf) {
+    const int f = f0 + t;
+    const int prob = BATCH ? pb.frame_problem[f] : 0;
+    const int buf = pb.cur[prob] ^ prm.which;
+    FramePose fp;
+    pose_from_rvec_tvec(pb.poses[buf] + 6 * (size_t)f, fp);
+    double* o = s_fc + t * kFrameConst;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) o[i] = fp.R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o[9 + i] = fp.t[i];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) o[12 + i] = fp.Jl[i];
+    if constexpr (BATCH) {
+      const double* a = prm.intr_dev + (size_t)prob * C::D;
+      double* si = s_intr + t * kMaxFull;
+      if constexpr (OF) { si[0] = a[0]; si[1] = a[0]; for (int i = 1; i < C::D; ++i) si[i + 1] = a[i]; }
+      else { for (int i = 0; i < C::D; ++i) si[i] = a[i]; }
+    }
+  }
+  __syncthreads();
+
+  const int fl = t / G;
+  const int lane = t - fl * G;
+  const bool active = fl < nf;
+  const double* ip = BATCH ? (s_intr + (active ? fl : 0) * kMaxFull) : prm.intr;
+  const double* fc = s_fc + (active ? fl : 0) * kFrameConst;
+
+  double acc[COST_ONLY ? 1 : C::NACC];
+#pragma unroll
+  for (int i = 0; i < (COST_ONLY ? 1 : C::NACC); ++i) acc[i] = 0.0;
+
+  if (active) {
+    const int f = f0 + fl;
+    const int end = pb.frame_offsets[f + 1];
+    for (int k = pb.frame_offsets[f] + lane; k < end; k += G) {
+      const double px = pb.x[k], py = pb.y[k], pz = pb.z[k], ou = pb.u[k], ov = pb.v[k];
+      double au[C::NA], av[C::NA];
+      const double c = obs_rows<MODEL, OF, !COST_ONLY>(ip, fc, px, py, pz, ou, ov, pb.huber_delta, au, av);
+      if constexpr (COST_ONLY) {
+        acc[0] += c;
+      } else {
+        static_for<0, C::NA>([&](auto I) {
+          static_for<decltype(I)::value, C::NA>([&](auto J) {
+            constexpr int i = decltype(I)::value, j = decltype(J)::value;
+            constexpr int kk = C::kidx(i, j);
+            if constexpr (kk >= 0) {
+              if constexpr (C::hasu(i, j)) acc[kk] = fma(au[i], au[j], acc[kk]);
+              if constexpr (C::hasv(i, j)) acc[kk] = fma(av[i], av[j], acc[kk]);
+            }
+          });
+        });
+      }
+    }
+    if constexpr (!COST_ONLY) {
+      // basis change phi -> rvec on this slice's block: H <- T^T H T, T = blkdiag(I_D, J_l, I_3, 1)
+      const double* Jl = fc + 12;
+      static_for<0, C::NA>([&](auto Cc) {
+        constexpr int c = decltype(Cc)::value;
+        if constexpr (c < C::D || c >= C::D + 3) {
+          constexpr int k0 = c < C::D ? C::kidx(c, C::D + 0) : C::kidx(C::D + 0, c);
+          constexpr int k1 = c < C::D ? C::kidx(c, C::D + 1) : C::kidx(C::D + 1, c);
+          constexpr int k2 = c < C::D ? C::kidx(c, C::D + 2) : C::kidx(C::D + 2, c);
+          const double h0 = acc[k0], h1 = acc[k1], h2 = acc[k2];
+          acc[k0] = fma(Jl[0], h0, fma(Jl[3], h1, Jl[6] * h2));
+          acc[k1] = fma(Jl[1], h0, fma(Jl[4], h1, Jl[7] * h2));
+          acc[k2] = fma(Jl[2], h0, fma(Jl[5], h1, Jl[8] * h2));
+        }
+      });
+      {
+        constexpr int p = C::D;
+        const double h00 = acc[C::kidx(p, p)], h01 = acc[C::kidx(p, p + 1)], h02 = acc[C::kidx(p, p + 2)];
+        const double h11 = acc[C::kidx(p + 1, p + 1)], h12 = acc[C::kidx(p + 1, p + 2)], h22 = acc[C::kidx(p + 2, p + 2)];
+        double tmp[3][3];  // H_pp * Jl
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          tmp[0][c] = fma(h00, Jl[c], fma(h01, Jl[3 + c], h02 * Jl[6 + c]));
+          tmp[1][c] = fma(h01, Jl[c], fma(h11, Jl[3 + c], h12 * Jl[6 + c]));
+          tmp[2][c] = fma(h02, Jl[c], fma(h12, Jl[3 + c], h22 * Jl[6 + c]));
+        }
+        auto g = [&](int a, int b) { return fma(Jl[a], tmp[0][b], fma(Jl[3 + a], tmp[1][b], Jl[6 + a] * tmp[2][b])); };
+        acc[C::kidx(p, p)] = g(0, 0); acc[C::kidx(p, p + 1)] = g(0, 1); acc[C::kidx(p, p + 2)] = g(0, 2);
+        acc[C::kidx(p + 1, p + 1)] = g(1, 1); acc[C::kidx(p + 1, p + 2)] = g(1, 2); acc[C::kidx(p + 2, p + 2)] = g(2, 2);
+      }
+    }
+  }
+
+  // ---- sum the G slices of each frame in lane order (fixed order -> deterministic) and store SoA ----
+  if constexpr (COST_ONLY) {
+    s_red[t] = acc[0];
+    __syncthreads();
+    if (t < nf) {
+      double s = 0.0;
+      for (int j = 0; j < G; ++j) s += s_red[t * G + j];
+      const int f = f0 + t;
+      const int prob = BATCH ? pb.frame_problem[f] : 0;
+      pb.frame_cost[pb.cur[prob] ^ prm.which][f] = s;
+    }
+  } else {
+    constexpr int NCH = (C::NACC + kRedChunk - 1) / kRedChunk;
+    static_for<0, NCH>([&](auto CH) {
+      constexpr int ch = decltype(CH)::value;
+      constexpr int cnt = (C::NACC - ch * kRedChunk) < kRedChunk ? (C::NACC - ch * kRedChunk) : kRedChunk;
+      if (ch > 0) __syncthreads();
+      if (active) {
+        static_for<0, cnt>([&](auto E) {
+          constexpr int e = decltype(E)::value;
+          s_red[e * kLinThreads + t] = acc[ch * kRedChunk + e];
+        });
+      }
+      __syncthreads();
+      for (int o = t; o < cnt * nf; o += kLinThreads) {
+        const int e = o / nf, ff = o - e * nf;
+        const double* src = s_red + e * kLinThreads + ff * G;
+        double s = 0.0;
+        for (int j = 0; j < G; ++j) s += src[j];
+        const int f = f0 + ff;
+        const int prob = BATCH ? pb.frame_problem[f] : 0;
+        double* out = pb.blocks[pb.cur[prob] ^ prm.which];
+        out[(size_t)prm.acc_to_blk[ch * kRedChunk + e] * pb.Fs + f] = s;
+      }
+    });
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 parity hook: one thread per observation, r and J materialised (HBM-bound: 248 B/obs for EUCM).
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, bool OF>
+__global__ void __launch_bounds__(128) k_eval_rj(ProblemDev pb, const double* __restrict__ intr_dev,
+                                                 const double* __restrict__ poses, int apply_loss,
+                                                 double* __restrict__ r, double* __restrict__ J, int64_t n_obs) {
+  using C = Cfg<MODEL, OF>;
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_obs) return;
+  const int f = pb.obs_frame[k];
+  double ip[kMaxFull];
+  if constexpr (OF) { ip[0] = intr_dev[0]; ip[1] = intr_dev[0]; for (int i = 1; i < C::D; ++i) ip[i + 1] = intr_dev[i]; }
+  else { for (int i = 0; i < C::D; ++i) ip[i] = intr_dev[i]; }
+  FramePose fp;
+  pose_from_rvec_tvec(poses + 6 * (size_t)f, fp);
+  double fc[12];
+  for (int i = 0; i < 9; ++i) fc[i] = fp.R[i];
+  for (int i = 0; i < 3; ++i) fc[9 + i] = fp.t[i];
+  double au[C::NA], av[C::NA];
+  for (int i = 0; i < C::NA; ++i) { au[i] = 0.0; av[i] = 0.0; }
+  obs_rows<MODEL, OF, true>(ip, fc, pb.x[k], pb.y[k], pb.z[k], pb.u[k], pb.v[k], apply_loss ? pb.huber_delta : 0.0, au, av);
+  r[2 * k] = au[C::N]; r[2 * k + 1] = av[C::N];
+  if (J) {
+    double* j0 = J + (size_t)(2 * k) * C::N;
+    double* j1 = j0 + C::N;
+    for (int i = 0; i < C::D; ++i) { j0[i] = C::nzu(i) ? au[i] : 0.0; j1[i] = C::nzv(i) ? av[i] : 0.0; }
+    for (int c = 0; c < 3; ++c) {  // d/drvec = d/dphi * J_l
+      j0[C::D + c] = au[C::D] * fp.Jl[c] + au[C::D + 1] * fp.Jl[3 + c] + au[C::D + 2] * fp.Jl[6 + c];
+      j1[C::D + c] = av[C::D] * fp.Jl[c] + av[C::D + 1] * fp.Jl[3 + c] + av[C::D + 2] * fp.Jl[6 + c];
+      j0[C::D + 3 + c] = au[C::D + 3 + c];
+      j1[C::D + 3 + c] = av[C::D + 3 + c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3. One thread per frame: scale + damp C_f, Cholesky (registers), Y = L^-1 B'^T, S_f = A'_f - Y^T Y,
+// g_s = g'_a - Y^T L^-1 g'_p, X = L^-T Y and cg = C^-1 g'_p stored for the back-substitution.
+// Single problem: the CTA's frame contributions are summed in thread order in shared memory and one
+// partial per CTA is written (summed in CTA order by k_sum_partials). Batch: per-frame contributions are
+// written and reduced per problem by k_segreduce.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSchurThreads = 128;
+
+template <int D, bool BATCH>
+__global__ void __launch_bounds__(kSchurThreads) k_schur(const __grid_constant__ SchurParams prm, double* __restrict__ partials) {
+  constexpr int N = D + 6, NA = N + 1;
+  constexpr int NS = D * (D + 1) / 2;
+  constexpr int NRED = NS + 3 * D + 1;
+  extern __shared__ double s_red[];  // [NRED][kSchurThreads+1]   (single problem only)
+  const ProblemDev& pb = prm.pb;
+  const int f = blockIdx.x * kSchurThreads + threadIdx.x;
+  const bool valid = f < pb.n_frames;
+  double red[NRED];
+#pragma unroll
+  for (int i = 0; i < NRED; ++i) red[i] = 0.0;
+  int bad = 0;
+  if (valid) {
+    const int prob = BATCH ? pb.frame_problem[f] : 0;
+    const double* blk = pb.blocks[pb.cur[prob] ^ prm.which] + f;
+    const size_t Fs = pb.Fs;
+    auto H = [&](int i, int j) { return blk[(size_t)tri_idx(NA, i, j) * Fs]; };
+    const double u = prm.u_dev ? prm.u_dev[prob] : 0.0;
+    double sa[D], sp[6];
+#pragma unroll
+    for (int a = 0; a < D; ++a) sa[a] = prm.intr_scale ? prm.intr_scale[prob * D + a] : 1.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) sp[i] = prm.pose_scale ? prm.pose_scale[(size_t)i * Fs + f] : 1.0;
+    // C' (lower, in place Cholesky), damping
+    double L[6][6], gp[6], dd[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+      for (int j = 0; j <= i; ++j) L[i][j] = sp[i] * H(D + j, D + i) * sp[j];
+      gp[i] = -sp[i] * H(D + i, N);
+      dd[i] = fmin(fmax(L[i][i], prm.min_diag), prm.max_diag);
+      L[i][i] = fma(u, dd[i], L[i][i]);
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      double s = L[j][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+      if (!(s > 0.0)) bad = 1;
+      const double l = sqrt(s), il = 1.0 / l;
+      L[j][j] = il;  // store the reciprocal of the pivot
+#pragma unroll
+      for (int i = j + 1; i < 6; ++i) {
+        double tt = L[i][j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) tt -= L[i][k] * L[j][k];
+        L[i][j] = tt * il;
+      }
+    }
+    // Y[a] = L^-1 B'[a,:]^T
+    double Yv[D][6];
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        double s = sa[a] * H(a, D + i) * sp[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) s -= L[i][k] * Yv[a][k];
+        Yv[a][i] = s * L[i][i];
+      }
+    }
+    double yg[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double s = gp[i];
+#pragma unroll
+      for (int k = 0; k < i; ++k) s -= L[i][k] * yg[k];
+      yg[i] = s * L[i][i];
+    }
+    // reduced-system contributions
+    {
+      int e = 0;
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+#pragma unroll
+        for (int b = a; b < D; ++b) {
+          double s = sa[a] * H(a, b) * sa[b];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) s -= Yv[a][i] * Yv[b][i];
+          red[e++] = s;
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        const double ga = -sa[a] * H(a, N);
+        double s = ga;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) s -= Yv[a][i] * yg[i];
+        red[NS + a] = s;
+        red[NS + D + a] = ga;
+        red[NS + 2 * D + a] = sa[a] * H(a, a) * sa[a];
+      }
+      red[NS + 3 * D] = H(N, N);
+    }
+    // X = L^-T Y, cg = L^-T yg  -> elim (SoA)
+    double* el = prm.elim + f;
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+#pragma unroll
+      for (int i = 5; i >= 0; --i) {
+        double s = Yv[a][i];
+#pragma unroll
+        for (int k = i + 1; k < 6; ++k) s -= L[k][i] * Yv[a][k];
+        Yv[a][i] = s * L[i][i];
+        el[(size_t)(i * D + a) * Fs] = Yv[a][i];
+      }
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+      double s = yg[i];
+#pragma unroll
+      for (int k = i + 1; k < 6; ++k) s -= L[k][i] * yg[k];
+      yg[i] = s * L[i][i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      el[(size_t)(6 * D + i) * Fs] = yg[i];
+      el[(size_t)(6 * D + 6 + i) * Fs] = gp[i];
+      el[(size_t)(6 * D + 12 + i) * Fs] = dd[i];
+    }
+    if (bad) {  // poison the reduced system so the host sees the Cholesky failure (tiny-solver returns None)
+#pragma unroll
+      for (int i = 0; i < NRED; ++i) red[i] = nan("");
+    }
+  }
+  if constexpr (BATCH) {
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < NRED; ++i) prm.frame_red[(size_t)i * pb.Fs + f] = red[i];
+    }
+  } else {
+    constexpr int LD = kSchurThreads + 1;
+#pragma unroll
+    for (int i = 0; i < NRED; ++i) s_red[i * LD + threadIdx.x] = red[i];
+    __syncthreads();
+    if (threadIdx.x < NRED) {
+      const double* src = s_red + threadIdx.x * LD;
+      double s = 0.0;
+      for (int j = 0; j < kSchurThreads; ++j) s += src[j];
+      partials[(size_t)blockIdx.x * NRED + threadIdx.x] = s;
+    }
+  }
+}
+
+// out[v] = sum_b partials[b][v], b ascending (fixed order)
+__global__ void k_sum_partials(const double* __restrict__ partials, int n_part, int NV, double* __restrict__ out) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= NV) return;
+  double s = 0.0;
+  for (int b = 0; b < n_part; ++b) s += partials[(size_t)b * NV + v];
+  out[v] = s;
+}
+
+// out[seg][v] = sum_{f in segment} in[v][f]; one CTA per segment; fixed strided order + fixed tree
+constexpr int kSegThreads = 256;
+__global__ void __launch_bounds__(kSegThreads) k_segreduce(const double* __restrict__ in, int NV, int Fs,
+                                                           const int32_t* __restrict__ seg_off, double* __restrict__ out) {
+  __shared__ double sh[kSegThreads];
+  const int seg = blockIdx.x;
+  const int b = seg_off[seg], e = seg_off[seg + 1];
+  for (int v = 0; v < NV; ++v) {
+    double s = 0.0;
+    for (int f = b + threadIdx.x; f < e; f += kSegThreads) s += in[(size_t)v * Fs + f];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = kSegThreads / 2; w > 0; w >>= 1) {
+      if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[(size_t)seg * NV + v] = sh[0];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4. y_p = cg - X y_a ; dpose = D_p y_p ; trial = pose + dpose. LM model decrease (pose part):
+// y^T(2g' - H'y) restricted to this frame = y_p^T g'_p + u * sum_i dd_i y_p,i^2   (uses H_reg y = g').
+// ------------------------------------------------------------------------------------------------
+template <int D, bool BATCH>
+__global__ void __launch_bounds__(128) k_backsub(const __grid_constant__ BacksubParams prm) {
+  const ProblemDev& pb = prm.pb;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= pb.n_frames) return;
+  const int prob = BATCH ? pb.frame_problem[f] : 0;
+  const size_t Fs = pb.Fs;
+  const double* el = prm.elim + f;
+  const double* ya = prm.y_a + (size_t)prob * D;
+  const double u = prm.u_dev ? prm.u_dev[prob] : 0.0;
+  const int cur = pb.cur[prob];
+  const double* src = pb.poses[cur] + 6 * (size_t)f;
+  double* dst = pb.poses[prm.in_place ? cur : (cur ^ 1)] + 6 * (size_t)f;
+  double md = 0.0;
+  if (prm.active && !prm.active[prob]) {  // converged problem of a batch: its poses stay put
+    if (!prm.in_place) for (int i = 0; i < 6; ++i) dst[i] = src[i];
+    if (prm.frame_md) prm.frame_md[f] = 0.0;
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double yp = el[(size_t)(6 * D + i) * Fs];
+#pragma unroll
+    for (int a = 0; a < D; ++a) yp -= el[(size_t)(i * D + a) * Fs] * ya[a];
+    const double sp = prm.pose_scale ? prm.pose_scale[(size_t)i * Fs + f] : 1.0;
+    dst[i] = src[i] + sp * yp;
+    md += yp * el[(size_t)(6 * D + 6 + i) * Fs] + u * el[(size_t)(6 * D + 12 + i) * Fs] * yp * yp;
+  }
+  if (prm.frame_md) prm.frame_md[f] = md;
+}
+
+// Jacobi scaling (tiny-solver LM, iteration 0): pose scales 1/(1+sqrt(C_ii)); per-frame A_aa diag for the host.
+template <int D, bool BATCH>
+__global__ void __launch_bounds__(128) k_compute_scale(ProblemDev pb, int which, double* __restrict__ pose_scale,
+                                                       double* __restrict__ frame_colsq) {
+  constexpr int NA = D + 7;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= pb.n_frames) return;
+  const int prob = BATCH ? pb.frame_problem[f] : 0;
+  const double* blk = pb.blocks[pb.cur[prob] ^ which] + f;
+  const size_t Fs = pb.Fs;
+  for (int i = 0; i < 6; ++i) pose_scale[(size_t)i * Fs + f] = 1.0 / (1.0 + sqrt(blk[(size_t)tri_idx(NA, D + i, D + i) * Fs]));
+  for (int a = 0; a < D; ++a) frame_colsq[(size_t)a * Fs + f] = blk[(size_t)tri_idx(NA, a, a) * Fs];
+}
+
+// per-problem {sum of frame_md, sum of per-frame cost}; one CTA per problem, fixed strided order + fixed tree
+__global__ void __launch_bounds__(kSegThreads) k_trial_stats(ProblemDev pb, int rr_idx, int mode,
+                                                             const double* __restrict__ frame_md,
+                                                             double* __restrict__ stat_out) {
+  __shared__ double sh0[kSegThreads], sh1[kSegThreads];
+  const int q = blockIdx.x;
+  const int b = pb.problem_frame_offsets[q], e = pb.problem_frame_offsets[q + 1];
+  const int cur = pb.cur[q];
+  const double* cost = nullptr;
+  if (mode == 0) cost = pb.frame_cost[cur ^ 1];
+  else if (mode == 4) cost = pb.frame_cost[cur];
+  else if (mode == 1) cost = pb.blocks[cur ^ 1] + (size_t)rr_idx * pb.Fs;
+  else if (mode == 2) cost = pb.blocks[cur] + (size_t)rr_idx * pb.Fs;
+  double s0 = 0.0, s1 = 0.0;
+  for (int f = b + threadIdx.x; f < e; f += kSegThreads) {
+    if (frame_md) s0 += frame_md[f];
+    if (cost) s1 += cost[f];
+  }
+  sh0[threadIdx.x] = s0; sh1[threadIdx.x] = s1;
+  __syncthreads();
+  for (int w = kSegThreads / 2; w > 0; w >>= 1) {
+    if (threadIdx.x < w) { sh0[threadIdx.x] += sh0[threadIdx.x + w]; sh1[threadIdx.x] += sh1[threadIdx.x + w]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { stat_out[2 * q] = sh0[0]; stat_out[2 * q + 1] = sh1[0]; }
+}
+
+__global__ void k_flip_cur(int32_t* cur, const unsigned char* mask, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (!mask || mask[i])) cur[i] ^= 1;
+}
+
+// FP64 FMA throughput microbenchmark: 8 independent chains per thread.
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+__global__ void k_l2_flush(double* buf, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] = (double)i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side dispatch
+// ------------------------------------------------------------------------------------------------
+template <class F>
+static auto dispatch_model(int model, int of, F&& f) {
+#define CCRS_CASE(M)                                                                         \
+  case M:                                                                                    \
+    return of ? f(std::integral_constant<int, M>{}, std::true_type{}) : f(std::integral_constant<int, M>{}, std::false_type{});
+  switch (model) {
+    CCRS_CASE(UCM) CCRS_CASE(EUCM) CCRS_CASE(EUCMT) CCRS_CASE(KB4) CCRS_CASE(OPENCV5) CCRS_CASE(FTHETA)
+  }
+#undef CCRS_CASE
+  return f(std::integral_constant<int, EUCM>{}, std::false_type{});
+}
+
+int model_dims(int model, int one_focal, int* D, int* NA, int* NBLK, int* NACC) {
+  if (model < 0 || model > 5) return -1;
+  return dispatch_model(model, one_focal, [&](auto M, auto OF) {
+    using C = Cfg<decltype(M)::value, decltype(OF)::value>;
+    if (D) *D = C::D;
+    if (NA) *NA = C::NA;
+    if (NBLK) *NBLK = C::NBLK;
+    if (NACC) *NACC = C::NACC;
+    return 0;
+  });
+}
+
+void fill_acc_to_blk(int model, int one_focal, int32_t* table) {
+  dispatch_model(model, one_focal, [&](auto M, auto OF) {
+    using C = Cfg<decltype(M)::value, decltype(OF)::value>;
+    int k = 0;
+    for (int i = 0; i < C::NA; ++i)
+      for (int j = i; j < C::NA; ++j)
+        if (C::has(i, j)) table[k++] = tri_idx(C::NA, i, j);
+    return 0;
+  });
+}
+
+static size_t lin_smem_bytes(int FPC, bool batch, bool cost_only) {
+  size_t d = (size_t)FPC * kFrameConst + (batch ? (size_t)FPC * kMaxFull : 0);
+  d += cost_only ? kLinThreads : (size_t)kRedChunk * kLinThreads;
+  return d * sizeof(double);
+}
+
+template <int MODEL, bool OF, bool BATCH, bool COST>
+static cudaError_t launch_lin_t(const LinParams& prm, int n_ctas, cudaStream_t s) {
+  auto kern = k_linearize<MODEL, OF, BATCH, COST>;
+  const size_t smem = lin_smem_bytes(prm.FPC, BATCH, COST);
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<n_ctas, kLinThreads, smem, s>>>(prm);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_linearize(int model, int one_focal, bool batch, bool cost_only, const LinParams& prm, int n_ctas,
+                             cudaStream_t s) {
+  return dispatch_model(model, one_focal, [&](auto M, auto OF) {
+    constexpr int m = decltype(M)::value;
+    constexpr bool of = decltype(OF)::value;
+    if (batch) return cost_only ? launch_lin_t<m, of, true, true>(prm, n_ctas, s) : launch_lin_t<m, of, true, false>(prm, n_ctas, s);
+    return cost_only ? launch_lin_t<m, of, false, true>(prm, n_ctas, s) : launch_lin_t<m, of, false, false>(prm, n_ctas, s);
+  });
+}
+
+cudaError_t launch_eval_rj(int model, int one_focal, const ProblemDev& pb, const double* intr_dev, const double* poses,
+                           int apply_loss, double* r, double* J, int64_t n_obs, cudaStream_t s) {
+  return dispatch_model(model, one_focal, [&](auto M, auto OF) {
+    const int nb = (int)((n_obs + 127) / 128);
+    k_eval_rj<decltype(M)::value, decltype(OF)::value><<<nb, 128, 0, s>>>(pb, intr_dev, poses, apply_loss, r, J, n_obs);
+    return cudaGetLastError();
+  });
+}
+
+template <class F>
+static cudaError_t dispatch_d(int D, F&& f) {
+  switch (D) {
+    case 4: return f(std::integral_constant<int, 4>{});
+    case 5: return f(std::integral_constant<int, 5>{});
+    case 6: return f(std::integral_constant<int, 6>{});
+    case 7: return f(std::integral_constant<int, 7>{});
+    case 8: return f(std::integral_constant<int, 8>{});
+    case 9: return f(std::integral_constant<int, 9>{});
+  }
+  return cudaErrorInvalidValue;
+}
+
+// single problem: partials buffer = frame_red (reused as [n_ctas][NRED]); result summed into red_out by the caller
+cudaError_t launch_schur(int D, const SchurParams& prm, cudaStream_t s) {
+  const bool batch = prm.pb.frame_problem != nullptr;
+  const int nb = (prm.pb.n_frames + kSchurThreads - 1) / kSchurThreads;
+  return dispatch_d(D, [&](auto DD) {
+    constexpr int d = decltype(DD)::value;
+    constexpr int NRED = d * (d + 1) / 2 + 3 * d + 1;
+    if (batch) {
+      k_schur<d, true><<<nb, kSchurThreads, 0, s>>>(prm, nullptr);
+    } else {
+      const size_t smem = (size_t)NRED * (kSchurThreads + 1) * sizeof(double);
+      auto kern = k_schur<d, false>;
+      static bool configured = false;
+      if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e != cudaSuccess) return e;
+        configured = true;
+      }
+      kern<<<nb, kSchurThreads, smem, s>>>(prm, prm.frame_red);
+    }
+    return cudaGetLastError();
+  });
+}
+
+cudaError_t launch_sum_partials(const double* partials, int n_part, int NV, double* out, cudaStream_t s) {
+  k_sum_partials<<<(NV + 127) / 128, 128, 0, s>>>(partials, n_part, NV, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_backsub(int D, const BacksubParams& prm, cudaStream_t s) {
+  const bool batch = prm.pb.frame_problem != nullptr;
+  const int nb = (prm.pb.n_frames + 127) / 128;
+  return dispatch_d(D, [&](auto DD) {
+    constexpr int d = decltype(DD)::value;
+    if (batch) k_backsub<d, true><<<nb, 128, 0, s>>>(prm);
+    else k_backsub<d, false><<<nb, 128, 0, s>>>(prm);
+    return cudaGetLastError();
+  });
+}
+
+cudaError_t launch_compute_scale(int D, const ProblemDev& pb, int which, double* pose_scale, double* frame_colsq,
+                                 cudaStream_t s) {
+  const bool batch = pb.frame_problem != nullptr;
+  const int nb = (pb.n_frames + 127) / 128;
+  return dispatch_d(D, [&](auto DD) {
+    constexpr int d = decltype(DD)::value;
+    if (batch) k_compute_scale<d, true><<<nb, 128, 0, s>>>(pb, which, pose_scale, frame_colsq);
+    else k_compute_scale<d, false><<<nb, 128, 0, s>>>(pb, which, pose_scale, frame_colsq);
+    return cudaGetLastError();
+  });
+}
+
+cudaError_t launch_segreduce(const double* in, int NV, int Fs, const int32_t* seg_off, int n_seg, double* out,
+                             cudaStream_t s) {
+  k_segreduce<<<n_seg, kSegThreads, 0, s>>>(in, NV, Fs, seg_off, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_trial_stats(const ProblemDev& pb, int rr_idx, int mode, const double* frame_md, double* stat_out,
+                               cudaStream_t s) {
+  k_trial_stats<<<pb.n_problems, kSegThreads, 0, s>>>(pb, rr_idx, mode, frame_md, stat_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_flip_cur(int32_t* cur, const unsigned char* mask_dev, int n_problems, cudaStream_t s) {
+  k_flip_cur<<<(n_problems + 127) / 128, 128, 0, s>>>(cur, mask_dev, n_problems);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fp64_peak(double* out, int n_ctas, int iters, cudaStream_t s) {
+  k_fp64_peak<<<n_ctas, 256, 0, s>>>(out, iters);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_l2_flush(double* buf, size_t n, cudaStream_t s) {
+  k_l2_flush<<<148 * 8, 256, 0, s>>>(buf, n);
+  return cudaGetLastError();
+}
+
+}  // namespace ccrs

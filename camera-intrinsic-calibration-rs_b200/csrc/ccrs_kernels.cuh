@@ -1,0 +1,86 @@
+// ccrs_kernels.cuh — kernel parameter blocks and launch entry points shared by ccrs_kernels.cu / ccrs_api.cu.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ccrs {
+
+constexpr int kLinThreads = 128;     // K2 CTA size
+constexpr int kLinCtasPerSm = 2;     // K2 __launch_bounds__ occupancy target (255 regs x 128 x 2 = one register file)
+constexpr int kRedChunk = 48;        // accumulators staged per smem reduction round (48 x 128 x 8 B = 48 KB / CTA)
+constexpr int kFrameConst = 21;      // R(9) t(3) Jl(9) per frame in shared memory
+
+// Observation arrays and per-frame state as the kernels see them.
+struct ProblemDev {
+  const double *x, *y, *z, *u, *v;        // [N] SoA
+  const int32_t* frame_offsets;            // [F+1]
+  const int32_t* frame_problem;            // [F] problem of each frame (batch) — nullptr for a single problem
+  const int32_t* problem_frame_offsets;    // [n_problems+1]
+  const int32_t* obs_frame;                // [N] frame of each observation (K1 only)
+  const int32_t* cur;                      // [n_problems] which of the two state buffers is "current"
+  double* poses[2];                        // [F][6]
+  double* blocks[2];                       // [NBLK][Fs] SoA packed frame blocks
+  double* frame_cost[2];                   // [Fs] per-frame sum of corrected r^2 (cost-only pass)
+  int n_frames, n_problems, Fs;            // Fs = padded frame stride
+  double huber_delta;
+};
+
+struct LinParams {
+  ProblemDev pb;
+  const double* intr_dev;   // [n_problems][D] (batch) — single problem passes intr[] by value below
+  double intr[9];           // full vector fx fy cx cy k.. (single problem; constant bank operands)
+  const int32_t* acc_to_blk;  // [NACC] sparse accumulator -> dense packed block index
+  int which;                // 0 = current point, 1 = trial point
+  int G;                    // lanes per frame
+  int FPC;                  // frames per CTA = kLinThreads / G
+};
+
+struct SchurParams {
+  ProblemDev pb;
+  int which;
+  const double* u_dev;          // [n_problems] damping
+  const double* intr_scale;     // [n_problems][D] or nullptr
+  const double* pose_scale;     // [6][Fs] or nullptr
+  double min_diag, max_diag;
+  double* elim;                 // [(6D+18)][Fs]: X (6xD), cg (6), g'_p (6), Dd (6)
+  double* frame_red;            // [NRED][Fs] per-frame contributions to the reduced system
+};
+
+struct BacksubParams {
+  ProblemDev pb;
+  const double* elim;
+  const double* y_a;            // [n_problems][D] device
+  const double* u_dev;
+  const double* pose_scale;     // [6][Fs] or nullptr
+  double* frame_md;             // [Fs] per-frame model-decrease part (nullable)
+  int in_place;                 // GN: write the update into the current poses
+  const unsigned char* active;  // [n_problems] nullable: problems whose poses must not move
+};
+
+// number of values K3 reduces per problem: S upper (D(D+1)/2) + g_s (D) + g_a (D) + diag_a (D) + sq_err (1)
+inline int nred_of(int D) { return D * (D + 1) / 2 + 3 * D + 1; }
+
+int model_dims(int model, int one_focal, int* D, int* NA, int* NBLK, int* NACC);
+void fill_acc_to_blk(int model, int one_focal, int32_t* table);
+
+cudaError_t launch_linearize(int model, int one_focal, bool batch, bool cost_only, const LinParams& prm, int n_ctas,
+                             cudaStream_t s);
+cudaError_t launch_eval_rj(int model, int one_focal, const ProblemDev& pb, const double* intr_dev, const double* poses,
+                           int apply_loss, double* r, double* J, int64_t n_obs, cudaStream_t s);
+cudaError_t launch_schur(int D, const SchurParams& prm, cudaStream_t s);
+cudaError_t launch_backsub(int D, const BacksubParams& prm, cudaStream_t s);
+cudaError_t launch_compute_scale(int D, const ProblemDev& pb, int which, double* pose_scale, double* frame_colsq,
+                                 cudaStream_t s);
+// out[n_seg][NV] = sum over frames of in[v][f], f in [seg_off[s], seg_off[s+1]) in a fixed order.
+cudaError_t launch_segreduce(const double* in, int NV, int Fs, const int32_t* seg_off, int n_seg, double* out,
+                             cudaStream_t s);
+cudaError_t launch_sum_partials(const double* partials, int n_part, int NV, double* out, cudaStream_t s);
+// stat_out[n_problems][2] = { sum_f frame_md[f] (0 if null), sum_f cost_f } with cost_f taken from
+// mode 0: frame_cost[trial]  1: (r,r) entry of blocks[trial]  2: (r,r) of blocks[current]  3: none  4: frame_cost[current]
+cudaError_t launch_trial_stats(const ProblemDev& pb, int rr_idx, int mode, const double* frame_md, double* stat_out,
+                               cudaStream_t s);
+cudaError_t launch_flip_cur(int32_t* cur, const unsigned char* mask_dev, int n_problems, cudaStream_t s);
+cudaError_t launch_fp64_peak(double* out, int n_ctas, int iters, cudaStream_t s);
+cudaError_t launch_l2_flush(double* buf, size_t n, cudaStream_t s);
+
+}  // namespace ccrs

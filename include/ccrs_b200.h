@@ -1,0 +1,238 @@
+/* ccrs_b200.h — C ABI of the B200-native linearisation library (libccrs_b200.so).
+ *
+ * The reference (powei-lin/camera-intrinsic-calibration-rs v0.11.2) has no FFI: its hot path sits
+ * behind two Rust-level interfaces:
+ *   (1) tiny_solver::factors::Factor::residual_func  (src/optimization/factors.rs:152-173, :204-228),
+ *       registered per corner by Problem::add_residual_block with HuberLoss::new(1.0)
+ *       (src/util.rs:409-414, :603-631), constrained by set_variable_bounds / fix_variable
+ *       (src/util.rs:29-71) and solved by GaussNewtonOptimizer::optimize (src/util.rs:443-464, :668-670);
+ *   (2) the entry points calib_camera (src/util.rs:384-490) and
+ *       calib_all_camera_with_extrinsics (src/util.rs:567-715).
+ * Per-corner dual-number callbacks cannot cross to a GPU, so the boundary moves up to
+ * "whole problem in, reduced normal equations / converged parameters out". Every entry point below
+ * names the reference interface it replaces. A Rust `-sys` crate binding these symbols is under
+ * camera-intrinsic-calibration-rs_b200/rust/ (source only: no Rust toolchain in the build image).
+ *
+ * Conventions: plain pointers and sizes, FP64 everywhere, all arrays are caller-owned HOST memory
+ * unless a name ends in _dev. Every function returns 0 on success or a negative ccrs_status; no
+ * exceptions cross the ABI. A handle is used by one host thread at a time. Work is enqueued on the
+ * handle's stream; host outputs are valid on return. There is NO CPU fallback: without an sm_100
+ * device ccrs_problem_create fails with CCRS_ERR_NO_DEVICE.
+ */
+#ifndef CCRS_B200_H
+#define CCRS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCRS_ABI_VERSION 1
+
+/* GenericModel variants of camera-intrinsic-model ^0.8 (CLI names: src/bin/camera_calibration.rs:35).
+ * Parameter order:
+ *   UCM     fx fy cx cy alpha              EUCM    fx fy cx cy alpha beta
+ *   EUCMT   fx fy cx cy alpha beta t1 t2   KB4     fx fy cx cy k1 k2 k3 k4
+ *   OPENCV5 fx fy cx cy k1 k2 p1 p2 k3     FTHETA  fx fy cx cy k1 k2 k3 k4                         */
+enum ccrs_model { CCRS_UCM = 0, CCRS_EUCM = 1, CCRS_EUCMT = 2, CCRS_KB4 = 3, CCRS_OPENCV5 = 4, CCRS_FTHETA = 5 };
+
+enum ccrs_status {
+  CCRS_OK = 0,
+  CCRS_ERR_INVALID = -1,    /* bad argument */
+  CCRS_ERR_CUDA = -2,       /* CUDA runtime error (see ccrs_last_error) */
+  CCRS_ERR_NO_DEVICE = -3,  /* no sm_100 device: the library has no CPU path */
+  CCRS_ERR_NUMERIC = -4,    /* NaN error — tiny-solver returns None */
+  CCRS_ERR_CHOLESKY = -5,   /* non-positive pivot — tiny-solver returns None */
+  CCRS_ERR_COMM = -6        /* collective failed / NCCL unavailable */
+};
+
+typedef struct ccrs_problem ccrs_problem; /* opaque: device buffers, stream, (optional) communicator */
+
+/* Number of parameters of `model` (full vector, fy included). */
+int ccrs_model_nparams(int model);
+
+/* Thread-local text of the last error on this thread. */
+const char* ccrs_last_error(void);
+
+/* ---- problem construction: replaces calib_camera's Problem assembly (src/util.rs:399-441) ---------
+ * One 2-residual block per (frame, corner) = ReprojectionFactor::new (factors.rs:134-150) +
+ * add_residual_block(2, ["params","rvec{i}","tvec{i}"], .., HuberLoss(1.0)) (util.rs:407-414).
+ * Observations are SoA, CSR by frame: frame f owns [frame_offsets[f], frame_offsets[f+1]).
+ * x,y,z = FeaturePoint.p3d, u,v = FeaturePoint.p2d widened f32->f64 (factors.rs:141-143).
+ * xy_same_focal: the optimised intrinsic vector has fy removed (util.rs:391-395), d = nparams-1.
+ * huber_delta <= 0 disables the loss. The arrays are copied to the device; nothing is retained. */
+int ccrs_problem_create(ccrs_problem** out, int model, int width, int height, int xy_same_focal,
+                        int n_frames, const int32_t* frame_offsets,
+                        const double* x, const double* y, const double* z,
+                        const double* u, const double* v,
+                        double huber_delta, int device_id);
+
+/* Batch of independent calibrations in one handle (BASELINE config 5): problem b owns frames
+ * [problem_frame_offsets[b], problem_frame_offsets[b+1]). Same model/size/flags for all problems.
+ * Intrinsic arrays passed to the calls below are then [n_problems][d]; scalars become [n_problems]. */
+int ccrs_batch_create(ccrs_problem** out, int model, int width, int height, int xy_same_focal,
+                      int n_problems, const int32_t* problem_frame_offsets,
+                      int n_frames, const int32_t* frame_offsets,
+                      const double* x, const double* y, const double* z,
+                      const double* u, const double* v,
+                      double huber_delta, int device_id);
+
+int ccrs_problem_destroy(ccrs_problem* p);
+
+/* Sizes. d = optimised intrinsics per problem; nblk = (d+7)(d+8)/2 packed entries per frame block. */
+int ccrs_problem_dim(const ccrs_problem* p);
+int ccrs_problem_nblk(const ccrs_problem* p);
+int ccrs_problem_n_frames(const ccrs_problem* p);
+int64_t ccrs_problem_n_obs(const ccrs_problem* p);
+int ccrs_problem_n_problems(const ccrs_problem* p);
+
+/* Pose state (the "rvec{i}"/"tvec{i}" variables, util.rs:435-441) lives on the device.
+ * poses = [n_frames][6] = rvec(3), tvec(3) per frame (types.rs:13-17 RvecTvec). */
+int ccrs_set_poses(ccrs_problem* p, const double* poses);
+int ccrs_get_poses(ccrs_problem* p, double* poses);
+
+/* ---- parity hook: replaces ReprojectionFactor::residual_func evaluated with f64 and with duals ----
+ * (factors.rs:152-173; tiny-solver residual_and_jacobian + Corrector).
+ * r: [2N]; J: [2N][d+6] row-major, columns [intrinsics | rvec | tvec]; J may be NULL.
+ * apply_loss != 0 returns the Huber-corrected r and J that tiny-solver assembles.
+ * poses may be NULL (use the device pose state). Single-problem handles only. */
+int ccrs_eval_rj(ccrs_problem* p, const double* intr, const double* poses, int apply_loss, double* r, double* J);
+
+/* ---- step-wise hot path: replaces Problem::compute_residual_and_jacobian + J^T J assembly + the
+ * per-iteration sparse LLT of tiny-solver (call sites util.rs:455,463,670) ---------- */
+
+/* K2: fused residual + analytic Jacobian + Huber + per-frame Gram blocks at the CURRENT (which=0) or
+ * TRIAL (which=1) pose state with intrinsics `intr`. sq_err[n_problems] = sum of corrected r^2. */
+int ccrs_linearize(ccrs_problem* p, const double* intr, int which, double* sq_err);
+
+/* Per-frame packed blocks of the last linearisation (parity hook): [n_frames][nblk], upper triangle,
+ * row-major, of [J r]^T [J r] with column order [intrinsics | rvec | tvec | r]. */
+int ccrs_get_frame_blocks(ccrs_problem* p, int which, double* blocks);
+
+/* Jacobi column scaling 1/(1+||J[:,c]||) (tiny-solver LM, first iteration): computes the pose scales on
+ * the device from the `which` linearisation and returns the LOCAL squared column norms of the
+ * intrinsic columns, col_sq[n_problems][d]; the caller sums them across ranks and calls ccrs_set_intr_scale. */
+int ccrs_compute_scale(ccrs_problem* p, int which, double* col_sq);
+int ccrs_set_intr_scale(ccrs_problem* p, const double* intr_scale /* [n_problems][d] or NULL = none */);
+
+/* K3: per-frame damping + 6x6 Cholesky elimination + fixed-order reduction onto the intrinsic system.
+ * u[n_problems] = LM damping of the POSE blocks (NULL/0 for Gauss-Newton); use_scale applies the Jacobi scaling.
+ * out[n_problems][d*d + 3d + 1]:  S (d*d row-major, = A' - sum_f B' C'^-1 B'^T, intrinsic damping NOT yet
+ * added: it needs the global diag), g_s (d, reduced rhs), g_a (d, unreduced scaled gradient -J_a^T r),
+ * diag_a (d, undamped scaled diag of A), sq_err (sum of corrected r^2). Summed over ranks when a
+ * communicator is attached. */
+int ccrs_reduce(ccrs_problem* p, int which, const double* u, int use_scale, double min_diag, double max_diag,
+                double* out);
+
+/* K4: pose back-substitution y_p = C^-1 (g_p - B^T y_a), trial_poses = poses + D y_p.
+ * y_a[n_problems][d] is the (scaled) intrinsic solution, u[n_problems] the damping used in ccrs_reduce (nullable).
+ * in_place = 1 writes the update into the current poses (Gauss-Newton). model_dec[n_problems] (nullable)
+ * receives the pose part of the LM gain-ratio denominator y^T (2 g' - H' y). */
+int ccrs_backsub(ccrs_problem* p, const double* y_a, const double* u, int in_place, double* model_dec);
+
+/* K5: residual-only Huber cost at the current (0) / trial (1) poses. sq_err[n_problems]. */
+int ccrs_eval_cost(ccrs_problem* p, const double* intr, int which, double* sq_err);
+
+/* Accept the trial point: trial poses (and, if present, the trial linearisation) become current.
+ * mask[n_problems] nullable = accept all. */
+int ccrs_accept(ccrs_problem* p, const unsigned char* mask);
+
+/* ---- multi-GPU: frames are sharded across ranks; one exchange of the reduced system per linearisation.
+ * The library dlopen()s libnccl.so.2 (the copy torch loaded). unique_id is the 128-byte ncclUniqueId
+ * produced by ccrs_comm_unique_id on rank 0 and distributed by the host (torch.distributed / MPI). */
+int ccrs_comm_unique_id(void* unique_id_128);
+int ccrs_comm_init(ccrs_problem* p, const void* unique_id_128, int rank, int world_size);
+/* deterministic = 1: all-gather the per-rank partials and sum in rank order on every rank (default);
+ * 0: ncclAllReduce(sum) as north_star names. */
+int ccrs_comm_set_deterministic(ccrs_problem* p, int deterministic);
+
+/* ---- loop controllers (host side): replace GaussNewtonOptimizer::optimize (util.rs:443-464) and
+ * tiny-solver's LevenbergMarquardtOptimizer::optimize (named by north_star). ------------------------ */
+typedef struct ccrs_options {
+  int max_iteration;          /* 100  OptimizerOptions::default() */
+  double min_abs_decrease;    /* 1e-5 */
+  double min_rel_decrease;    /* 1e-5 */
+  double min_error;           /* 1e-10 */
+  double lm_initial_radius;   /* 1e4 */
+  double lm_min_diag;         /* 1e-6 */
+  double lm_max_diag;         /* 1e32 */
+  int fixed_mode;             /* 0: fixed variables stay in the system and are reset after the update
+                                 (tiny-solver ParameterBlock::update_params); 1: eliminated */
+  int speculative;            /* LM: 1 = linearise at the trial point instead of a residual-only pass (default) */
+  int verbose;
+} ccrs_options;
+void ccrs_default_options(ccrs_options* o);
+
+typedef struct ccrs_summary {
+  int iterations;   /* linearisations (GN) / LM iterations performed (max over problems) */
+  int status;       /* ccrs_status */
+  int stop_reason;  /* 0 max_iter, 1 error<min, 2 abs decrease, 3 rel decrease (problem 0) */
+  double final_error;
+  int n_accepted, n_rejected;
+  double device_ms; /* CUDA-event time of the whole loop */
+} ccrs_summary;
+
+/* intr[n_problems][d] in/out; lo/hi [d] nullable (set_variable_bounds, util.rs:29-49);
+ * fixed[d] nullable (fix_variable, util.rs:50-71, :459-464). Poses are the device pose state.
+ * err_hist nullable [max_iteration] (problem 0). */
+int ccrs_solve_gn(ccrs_problem* p, double* intr, const double* lo, const double* hi, const unsigned char* fixed,
+                  const ccrs_options* opt, ccrs_summary* summary, double* err_hist);
+int ccrs_solve_lm(ccrs_problem* p, double* intr, const double* lo, const double* hi, const unsigned char* fixed,
+                  const ccrs_options* opt, ccrs_summary* summary, double* err_hist);
+
+/* ---- backend-agnostic controllers: the same GN / LM loops driven through a table of callbacks.
+ * ccrs_solve_gn/lm call these with the CUDA backend; CPU tests (world_size-2 gloo) drive them with
+ * their own callbacks. All buffers host memory; n_problems systems of dimension d. */
+typedef struct ccrs_backend {
+  void* ctx;
+  int d;
+  int n_problems;
+  /* K2 at the current (0) / trial (1) point; asynchronous, no output */
+  int (*linearize)(void* ctx, const double* intr, int which);
+  /* local squared intrinsic column norms [n_problems][d]; pose scales stay inside the backend */
+  int (*compute_scale)(void* ctx, int which, double* col_sq);
+  int (*set_intr_scale)(void* ctx, const double* intr_scale /* nullable */);
+  /* K3: out[n_problems][d*d + 3d + 1] = S | g_s | g_a | diag_a | sq_err  (see ccrs_reduce) */
+  int (*reduce)(void* ctx, int which, const double* u, int use_scale, double min_diag, double max_diag, double* out);
+  /* K4: active[n_problems] nullable; in_place = 1 updates the current poses (Gauss-Newton) */
+  int (*backsub)(void* ctx, const double* y_a, const double* u, const unsigned char* active, int in_place);
+  /* out[n_problems][2] = pose part of the model decrease, sq_err at the trial point.
+   * speculative: obtain sq_err by linearising the trial point (its blocks become current on accept) */
+  int (*trial_stats)(void* ctx, const double* intr_trial, int speculative, double* out);
+  int (*accept)(void* ctx, const unsigned char* mask);
+  /* in-place sum over ranks, identical result on every rank. NULL = the outputs above are already global
+   * (single rank, or the backend exchanges on the device as the CUDA backend does with NCCL). */
+  int (*allreduce)(void* ctx, double* buf, int count);
+} ccrs_backend;
+
+int ccrs_controller_gn(const ccrs_backend* be, double* intr, const double* lo, const double* hi,
+                       const unsigned char* fixed, const ccrs_options* opt, ccrs_summary* summary, double* err_hist);
+int ccrs_controller_lm(const ccrs_backend* be, double* intr, const double* lo, const double* hi,
+                       const unsigned char* fixed, const ccrs_options* opt, ccrs_summary* summary, double* err_hist);
+
+/* ---- reference entry point: calib_camera (src/util.rs:384-490) from "Problem assembled" onwards ----
+ * params[nparams] in/out (FULL vector incl. fy); poses[n_frames][6] in/out (initial = SQPnP poses the
+ * caller computed, util.rs:435-441). Semantics of xy_same_focal / disabled_distortions / fixed_focal as
+ * util.rs:391-395, :446-454, :459-464. use_lm = 0 runs Gauss-Newton like the reference. */
+int ccrs_calib_camera(int model, int width, int height, int n_frames, const int32_t* frame_offsets,
+                      const double* x, const double* y, const double* z, const double* u, const double* v,
+                      double* params, double* poses, int xy_same_focal, int disabled_distortions, int fixed_focal,
+                      int use_lm, const ccrs_options* opt, ccrs_summary* summary, int device_id);
+
+/* Distortion bounds of GenericModel::distortion_params_bound() for the FULL parameter vector
+ * (lo/hi [nparams]; +-inf where unbounded), plus fx,fy in [0,1e4], cx in [0,w], cy in [0,h] (util.rs:36-39). */
+int ccrs_model_bounds(int model, int width, int height, double* lo, double* hi);
+
+/* ---- measurement helpers ------------------------------------------------------------------------ */
+/* FP64 FMA throughput microbenchmark (TFLOP/s) — the roofline denominator SURVEY §8(d) asks to measure. */
+int ccrs_measure_fp64_peak(int device_id, double* tflops);
+/* Time `reps` back-to-back launches of K2 (linearise) with CUDA events on the handle's stream. */
+int ccrs_time_linearize(ccrs_problem* p, const double* intr, int reps, int flush_l2, double* avg_ms);
+/* Kernel launches issued by this handle since creation. */
+int64_t ccrs_launch_count(const ccrs_problem* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCRS_B200_H */
