@@ -10,7 +10,8 @@ from ._abi import CcrsError, Options, Summary, default_options, LIB_PATH, SYMBOL
 from .calib import (MODELS, FeaturePoint, FrameFeature, GenericModel, Problem, RvecTvec, calib_camera, comm_unique_id,
                     measure_fp64_peak, model_bounds, pack_frames)
 from . import synth
+from . import dist
 
 __all__ = ["CcrsError", "Options", "Summary", "default_options", "LIB_PATH", "SYMBOLS", "MODELS", "FeaturePoint",
            "FrameFeature", "GenericModel", "Problem", "RvecTvec", "calib_camera", "comm_unique_id", "measure_fp64_peak",
-           "model_bounds", "pack_frames", "synth"]
+           "model_bounds", "pack_frames", "synth", "dist"]
