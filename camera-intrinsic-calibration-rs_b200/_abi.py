@@ -18,9 +18,9 @@ SYMBOLS = [
     "ccrs_problem_dim", "ccrs_problem_nblk", "ccrs_problem_n_frames", "ccrs_problem_n_obs", "ccrs_problem_n_problems",
     "ccrs_set_poses", "ccrs_get_poses", "ccrs_eval_rj", "ccrs_linearize", "ccrs_get_frame_blocks",
     "ccrs_compute_scale", "ccrs_set_intr_scale", "ccrs_reduce", "ccrs_backsub", "ccrs_eval_cost", "ccrs_accept",
-    "ccrs_comm_unique_id", "ccrs_comm_init", "ccrs_comm_set_deterministic", "ccrs_default_options",
+    "ccrs_comm_unique_id", "ccrs_comm_init", "ccrs_comm_finalize", "ccrs_comm_set_deterministic", "ccrs_default_options",
     "ccrs_solve_gn", "ccrs_solve_lm", "ccrs_controller_gn", "ccrs_controller_lm", "ccrs_calib_camera",
-    "ccrs_model_bounds", "ccrs_measure_fp64_peak", "ccrs_time_linearize", "ccrs_launch_count",
+    "ccrs_model_bounds", "ccrs_measure_fp64_peak", "ccrs_time_linearize", "ccrs_bench_lm_steps", "ccrs_launch_count",
 ]
 
 STATUS = {0: "CCRS_OK", -1: "CCRS_ERR_INVALID", -2: "CCRS_ERR_CUDA", -3: "CCRS_ERR_NO_DEVICE",
@@ -114,6 +114,7 @@ def load():
     lib.ccrs_model_bounds.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp]
     lib.ccrs_measure_fp64_peak.argtypes = [C.c_int, _dp]
     lib.ccrs_time_linearize.argtypes = [vp, _dp, C.c_int, C.c_int, _dp]
+    lib.ccrs_bench_lm_steps.argtypes = [vp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.POINTER(C.c_int64)]
     _lib = lib
     return lib
 

@@ -213,8 +213,9 @@ class Problem:
         return self._solve(self.lib.ccrs_solve_lm, intr, lo, hi, fixed, options)
 
     # ---- multi-GPU ----
-    def comm_init(self, unique_id: bytes, rank: int, world: int, deterministic: bool = True):
-        buf = C.create_string_buffer(unique_id, 128)
+    def comm_init(self, unique_id, rank: int = 0, world: int = 1, deterministic: bool = True):
+        """unique_id=None attaches the process-wide communicator created by an earlier call."""
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
         check(self.lib.ccrs_comm_init(self.h, buf, rank, world))
         check(self.lib.ccrs_comm_set_deterministic(self.h, int(deterministic)))
 
@@ -224,6 +225,16 @@ class Problem:
         ms = C.c_double(0.0)
         check(self.lib.ccrs_time_linearize(self.h, _dp(intr), int(reps), int(flush_l2), C.byref(ms)))
         return ms.value
+
+    def bench_lm_steps(self, intr0, poses0, warmup=3, steps=10, reset_every=4, flush_l2=True):
+        """Returns (step_ms[steps], kernel launches inside the timed steps)."""
+        a = _f64(intr0).reshape(-1)
+        pz = _f64(poses0).reshape(-1)
+        ms = np.zeros(steps)
+        n = C.c_int64(0)
+        check(self.lib.ccrs_bench_lm_steps(self.h, _dp(a), _dp(pz), int(warmup), int(steps), int(reset_every),
+                                           int(flush_l2), _dp(ms), C.byref(n)))
+        return ms, int(n.value)
 
     def launch_count(self) -> int:
         return int(self.lib.ccrs_launch_count(self.h))

@@ -51,6 +51,10 @@ NcclApi& nccl() {
   return api;
 }
 
+// one process = one GPU = one communicator, shared by every handle of the process (created once: ncclCommInitRank
+// costs ~100 ms, far more than a whole calibration)
+struct GlobalComm { ncclComm_t comm = nullptr; int rank = 0, world = 1; } g_comm;
+
 thread_local char g_err[512] = "";
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -422,7 +426,6 @@ int ccrs_problem_destroy(ccrs_problem* p) {
   if (!p) return 0;
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
-  if (p->comm && nccl().ok) nccl().CommDestroy(p->comm);
   p->x.release(); p->y.release(); p->z.release(); p->u.release(); p->v.release();
   p->frame_offsets.release(); p->frame_problem.release(); p->problem_frame_offsets.release(); p->obs_frame.release();
   p->cur.release(); p->acc_to_blk.release();
@@ -641,15 +644,29 @@ int ccrs_comm_unique_id(void* unique_id_128) {
 }
 
 int ccrs_comm_init(ccrs_problem* p, const void* unique_id_128, int rank, int world_size) {
-  if (!p || !unique_id_128 || world_size < 1 || rank < 0 || rank >= world_size) return fail(CCRS_ERR_INVALID, "bad comm args");
+  if (!p) return fail(CCRS_ERR_INVALID, "null");
+  if (!unique_id_128) {  // attach the communicator this process already created
+    if (!g_comm.comm) return fail(CCRS_ERR_COMM, "no communicator yet: call ccrs_comm_init with a unique id first");
+    p->comm = g_comm.comm; p->rank = g_comm.rank; p->world = g_comm.world;
+    return 0;
+  }
+  if (world_size < 1 || rank < 0 || rank >= world_size) return fail(CCRS_ERR_INVALID, "bad comm args");
   NcclApi& n = nccl();
   if (!n.ok) return fail(CCRS_ERR_COMM, "libnccl.so.2 not loadable");
   CK(cudaSetDevice(p->device));
+  if (g_comm.comm) { n.CommDestroy(g_comm.comm); g_comm.comm = nullptr; }
   ncclUniqueId id;
   std::memcpy(&id, unique_id_128, 128);
-  int r = n.CommInitRank(&p->comm, world_size, id, rank);
+  int r = n.CommInitRank(&g_comm.comm, world_size, id, rank);
   if (r != 0) return fail(CCRS_ERR_COMM, "ncclCommInitRank: %s", n.GetErrorString ? n.GetErrorString(r) : "?");
-  p->rank = rank; p->world = world_size;
+  g_comm.rank = rank; g_comm.world = world_size;
+  p->comm = g_comm.comm; p->rank = rank; p->world = world_size;
+  return 0;
+}
+
+int ccrs_comm_finalize(void) {
+  if (g_comm.comm && nccl().ok) nccl().CommDestroy(g_comm.comm);
+  g_comm.comm = nullptr;
   return 0;
 }
 
@@ -786,6 +803,57 @@ int ccrs_measure_fp64_peak(int device_id, double* tflops) {
   cudaFree(out);
   *tflops = best;
   return 0;
+}
+
+struct ccrs_lm_state;
+ccrs_lm_state* ccrs_lm_state_create(const ccrs_backend* be, double* intr, const ccrs_options* opt, ccrs_summary* sum);
+int ccrs_lm_state_step(ccrs_lm_state* S, int* done);
+void ccrs_lm_state_destroy(ccrs_lm_state* S);
+
+int ccrs_bench_lm_steps(ccrs_problem* p, const double* intr0, const double* poses0, int warmup, int steps,
+                        int reset_every, int flush_l2, double* step_ms, int64_t* timed_launches) {
+  if (!p || !intr0 || !poses0 || !step_ms || steps <= 0 || warmup < 0 || reset_every <= 0) return fail(CCRS_ERR_INVALID, "bad args");
+  CK(cudaSetDevice(p->device));
+  const size_t flush_n = (size_t)64 << 20;  // 512 MB of doubles > 126 MB L2
+  if (flush_l2 && !p->l2_flush.p) CK(p->l2_flush.alloc(flush_n));
+  ccrs_options opt;
+  ccrs_default_options(&opt);
+  opt.max_iteration = reset_every + 1;
+  opt.min_abs_decrease = -1.0; opt.min_rel_decrease = -1.0; opt.min_error = -1.0;  // never stop: every step does full work
+  ccrs_summary sum;
+  ccrs_backend be = cuda_backend(p);
+  std::vector<double> intr((size_t)p->n_problems * p->D);
+  ccrs_lm_state* S = nullptr;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  int st = 0;
+  int64_t timed = 0;
+  for (int i = 0; i < warmup + steps; ++i) {
+    if (i % reset_every == 0) {  // back to the initial point: untimed (pose upload, first linearisation, Jacobi scaling)
+      if (S) ccrs_lm_state_destroy(S);
+      st = ccrs_set_poses(p, poses0);
+      if (st) break;
+      std::memcpy(intr.data(), intr0, intr.size() * sizeof(double));
+      S = ccrs_lm_state_create(&be, intr.data(), &opt, &sum);
+      if (!S) { st = fail(CCRS_ERR_CUDA, "lm_begin failed (%d)", sum.status); break; }
+    }
+    if (flush_l2) CK(launch_l2_flush(p->l2_flush.p, flush_n, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    const int64_t l0 = p->launches;
+    int done = 0;
+    CK(cudaEventRecord(e0, p->stream));
+    st = ccrs_lm_state_step(S, &done);
+    if (st) break;
+    CK(cudaEventRecord(e1, p->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (i >= warmup) { step_ms[i - warmup] = ms; timed += p->launches - l0; }
+  }
+  if (timed_launches) *timed_launches = timed;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (S) ccrs_lm_state_destroy(S);
+  return st;
 }
 
 int ccrs_time_linearize(ccrs_problem* p, const double* intr, int reps, int flush_l2, double* avg_ms) {

@@ -151,89 +151,139 @@ int ccrs_controller_gn(const ccrs_backend* be, double* intr, const double* lo, c
   return worst;
 }
 
-int ccrs_controller_lm(const ccrs_backend* be, double* intr, const double* lo, const double* hi,
-                       const unsigned char* fixed, const ccrs_options* opt_in, ccrs_summary* sum, double* err_hist) {
+// LM loop state, steppable so that the bench can time single iterations (ccrs_bench_lm_steps).
+struct ccrs_lm_state {
+  const ccrs_backend* be;
   ccrs_options opt;
-  if (opt_in) opt = *opt_in; else ccrs_default_options(&opt);
-  ccrs_summary local_sum;
-  if (!sum) sum = &local_sum;
-  std::memset(sum, 0, sizeof(*sum));
-  const int d = be->d, P = be->n_problems, NOUT = d * d + 3 * d + 1;
-  std::vector<double> out((size_t)P * NOUT), y((size_t)P * d, 0.0), scale((size_t)P * d, 1.0), colsq((size_t)P * d);
-  std::vector<double> u(P, 1.0 / opt.lm_initial_radius), v(P, kLmRejectFactor0), cur_err(P, 0.0), md_a(P, 0.0);
-  std::vector<double> trial((size_t)P * d), dx(d), stats((size_t)P * 2);
-  std::vector<unsigned char> active(P, 1), acc_mask(P, 0);
-  std::vector<int> stop(P, 0);
-  int worst = 0;
+  int d, P, NOUT, it;
+  double* intr;
+  const double *lo, *hi;
+  const unsigned char* fixed;
+  std::vector<double> out, y, scale, colsq, u, v, cur_err, md_a, trial, dx, stats;
+  std::vector<unsigned char> active, acc_mask;
+  std::vector<int> stop;
+  int worst;
+  ccrs_summary* sum;
+  double* err_hist;
+};
 
+static int lm_begin(ccrs_lm_state& S, const ccrs_backend* be, double* intr, const double* lo, const double* hi,
+                    const unsigned char* fixed, const ccrs_options* opt_in, ccrs_summary* sum, double* err_hist) {
+  S.be = be;
+  if (opt_in) S.opt = *opt_in; else ccrs_default_options(&S.opt);
+  S.sum = sum;
+  std::memset(sum, 0, sizeof(*sum));
+  S.err_hist = err_hist;
+  S.intr = intr; S.lo = lo; S.hi = hi; S.fixed = fixed;
+  const int d = S.d = be->d, P = S.P = be->n_problems;
+  S.NOUT = d * d + 3 * d + 1;
+  S.it = 0; S.worst = 0;
+  S.out.assign((size_t)P * S.NOUT, 0.0); S.y.assign((size_t)P * d, 0.0); S.scale.assign((size_t)P * d, 1.0);
+  S.colsq.assign((size_t)P * d, 0.0);
+  S.u.assign(P, 1.0 / S.opt.lm_initial_radius); S.v.assign(P, kLmRejectFactor0);
+  S.cur_err.assign(P, 0.0); S.md_a.assign(P, 0.0);
+  S.trial.assign((size_t)P * d, 0.0); S.dx.assign(d, 0.0); S.stats.assign((size_t)P * 2, 0.0);
+  S.active.assign(P, 1); S.acc_mask.assign(P, 0); S.stop.assign(P, 0);
   BE(be->linearize(be->ctx, intr, 0));
   // Jacobi scaling 1/(1+||J[:,c]||) from the first (loss-corrected) Jacobian
-  BE(be->compute_scale(be->ctx, 0, colsq.data()));
-  if (be->allreduce) BE(be->allreduce(be->ctx, colsq.data(), (int)colsq.size()));
-  for (size_t i = 0; i < scale.size(); ++i) scale[i] = 1.0 / (1.0 + std::sqrt(colsq[i]));
-  BE(be->set_intr_scale(be->ctx, scale.data()));
-
-  for (int it = 0; it < opt.max_iteration; ++it) {
-    BE(be->reduce(be->ctx, 0, u.data(), 1, opt.lm_min_diag, opt.lm_max_diag, out.data()));
-    if (be->allreduce) BE(be->allreduce(be->ctx, out.data(), (int)out.size()));
-    sum->iterations = it + 1;
-    int n_active = 0;
-    for (int p = 0; p < P; ++p) {
-      std::memcpy(&trial[(size_t)p * d], intr + (size_t)p * d, d * sizeof(double));
-      if (!active[p]) continue;
-      const Reduced r = view(&out[(size_t)p * NOUT], d);
-      if (it == 0) cur_err[p] = err_metric(r.sq_err);
-      double* yp = &y[(size_t)p * d];
-      const int st = solve_intrinsics(r, d, u[p], opt.lm_min_diag, opt.lm_max_diag, fixed, opt.fixed_mode, yp, &md_a[p]);
-      if (st != 0) { active[p] = 0; worst = st; continue; }
-      for (int i = 0; i < d; ++i) dx[i] = scale[(size_t)p * d + i] * yp[i];
-      update_intr(d, intr + (size_t)p * d, dx.data(), lo, hi, fixed, &trial[(size_t)p * d]);
-      ++n_active;
-    }
-    if (n_active == 0) break;
-    BE(be->backsub(be->ctx, y.data(), u.data(), P > 1 ? active.data() : nullptr, 0));
-    BE(be->trial_stats(be->ctx, trial.data(), opt.speculative, stats.data()));
-    if (be->allreduce) BE(be->allreduce(be->ctx, stats.data(), (int)stats.size()));
-    bool any_accept = false;
-    for (int p = 0; p < P; ++p) {
-      acc_mask[p] = 0;
-      if (!active[p]) continue;
-      const Reduced r = view(&out[(size_t)p * NOUT], d);
-      const double new_sq = stats[2 * p + 1];
-      const double rho = (r.sq_err - new_sq) / (md_a[p] + stats[2 * p]);
-      const double last_err = cur_err[p];
-      bool accepted = false;
-      if (rho > 0.0) {
-        accepted = true; acc_mask[p] = 1; any_accept = true;
-        std::memcpy(intr + (size_t)p * d, &trial[(size_t)p * d], d * sizeof(double));
-        const double t = 2.0 * rho - 1.0;
-        u[p] *= std::max(1.0 / 3.0, 1.0 - t * t * t);
-        v[p] = kLmRejectFactor0;
-        cur_err[p] = err_metric(new_sq);
-        if (p == 0) sum->n_accepted++;
-      } else {
-        u[p] *= v[p]; v[p] *= 2.0;
-        if (p == 0) sum->n_rejected++;
-      }
-      if (p == 0) { if (err_hist) err_hist[it] = cur_err[p]; sum->final_error = cur_err[p]; }
-      if (cur_err[p] < opt.min_error) { active[p] = 0; stop[p] = 1; }
-      else if (std::isnan(cur_err[p]) || std::isnan(rho)) { active[p] = 0; worst = CCRS_ERR_NUMERIC; }
-      else if (accepted) {  // stop tests compare successive ACCEPTED errors
-        if (std::fabs(last_err - cur_err[p]) < opt.min_abs_decrease) { active[p] = 0; stop[p] = 2; }
-        else if (std::fabs(last_err - cur_err[p]) / last_err < opt.min_rel_decrease) { active[p] = 0; stop[p] = 3; }
-      }
-    }
-    if (any_accept) {
-      BE(be->accept(be->ctx, acc_mask.data()));
-      if (!opt.speculative) BE(be->linearize(be->ctx, intr, 0));
-    }
-    bool any_active = false;
-    for (int p = 0; p < P; ++p) any_active |= (active[p] != 0);
-    if (!any_active) break;
-  }
-  sum->stop_reason = stop[0];
-  sum->status = worst;
-  return worst;
+  BE(be->compute_scale(be->ctx, 0, S.colsq.data()));
+  if (be->allreduce) BE(be->allreduce(be->ctx, S.colsq.data(), (int)S.colsq.size()));
+  for (size_t i = 0; i < S.scale.size(); ++i) S.scale[i] = 1.0 / (1.0 + std::sqrt(S.colsq[i]));
+  BE(be->set_intr_scale(be->ctx, S.scale.data()));
+  return 0;
 }
+
+// one LM iteration; *done = 1 when every problem has stopped
+static int lm_iterate(ccrs_lm_state& S, int* done) {
+  const ccrs_backend* be = S.be;
+  const ccrs_options& opt = S.opt;
+  ccrs_summary* sum = S.sum;
+  const int d = S.d, P = S.P, NOUT = S.NOUT, it = S.it;
+  *done = 0;
+  BE(be->reduce(be->ctx, 0, S.u.data(), 1, opt.lm_min_diag, opt.lm_max_diag, S.out.data()));
+  if (be->allreduce) BE(be->allreduce(be->ctx, S.out.data(), (int)S.out.size()));
+  sum->iterations = it + 1;
+  int n_active = 0;
+  for (int p = 0; p < P; ++p) {
+    std::memcpy(&S.trial[(size_t)p * d], S.intr + (size_t)p * d, d * sizeof(double));
+    if (!S.active[p]) continue;
+    const Reduced r = view(&S.out[(size_t)p * NOUT], d);
+    if (it == 0) S.cur_err[p] = err_metric(r.sq_err);
+    double* yp = &S.y[(size_t)p * d];
+    const int st = solve_intrinsics(r, d, S.u[p], opt.lm_min_diag, opt.lm_max_diag, S.fixed, opt.fixed_mode, yp, &S.md_a[p]);
+    if (st != 0) { S.active[p] = 0; S.worst = st; continue; }
+    for (int i = 0; i < d; ++i) S.dx[i] = S.scale[(size_t)p * d + i] * yp[i];
+    update_intr(d, S.intr + (size_t)p * d, S.dx.data(), S.lo, S.hi, S.fixed, &S.trial[(size_t)p * d]);
+    ++n_active;
+  }
+  if (n_active == 0) { *done = 1; return 0; }
+  BE(be->backsub(be->ctx, S.y.data(), S.u.data(), P > 1 ? S.active.data() : nullptr, 0));
+  BE(be->trial_stats(be->ctx, S.trial.data(), opt.speculative, S.stats.data()));
+  if (be->allreduce) BE(be->allreduce(be->ctx, S.stats.data(), (int)S.stats.size()));
+  bool any_accept = false;
+  for (int p = 0; p < P; ++p) {
+    S.acc_mask[p] = 0;
+    if (!S.active[p]) continue;
+    const Reduced r = view(&S.out[(size_t)p * NOUT], d);
+    const double new_sq = S.stats[2 * p + 1];
+    const double rho = (r.sq_err - new_sq) / (S.md_a[p] + S.stats[2 * p]);
+    const double last_err = S.cur_err[p];
+    bool accepted = false;
+    if (rho > 0.0) {
+      accepted = true; S.acc_mask[p] = 1; any_accept = true;
+      std::memcpy(S.intr + (size_t)p * d, &S.trial[(size_t)p * d], d * sizeof(double));
+      const double t = 2.0 * rho - 1.0;
+      S.u[p] *= std::max(1.0 / 3.0, 1.0 - t * t * t);
+      S.v[p] = kLmRejectFactor0;
+      S.cur_err[p] = err_metric(new_sq);
+      if (p == 0) sum->n_accepted++;
+    } else {
+      S.u[p] *= S.v[p]; S.v[p] *= 2.0;
+      if (p == 0) sum->n_rejected++;
+    }
+    if (p == 0) { if (S.err_hist) S.err_hist[it] = S.cur_err[p]; sum->final_error = S.cur_err[p]; }
+    if (S.cur_err[p] < opt.min_error) { S.active[p] = 0; S.stop[p] = 1; }
+    else if (std::isnan(S.cur_err[p]) || std::isnan(rho)) { S.active[p] = 0; S.worst = CCRS_ERR_NUMERIC; }
+    else if (accepted) {  // stop tests compare successive ACCEPTED errors
+      if (std::fabs(last_err - S.cur_err[p]) < opt.min_abs_decrease) { S.active[p] = 0; S.stop[p] = 2; }
+      else if (std::fabs(last_err - S.cur_err[p]) / last_err < opt.min_rel_decrease) { S.active[p] = 0; S.stop[p] = 3; }
+    }
+  }
+  if (any_accept) {
+    BE(be->accept(be->ctx, S.acc_mask.data()));
+    if (!opt.speculative) BE(be->linearize(be->ctx, S.intr, 0));
+  }
+  bool any_active = false;
+  for (int p = 0; p < P; ++p) any_active |= (S.active[p] != 0);
+  S.it = it + 1;
+  if (!any_active || S.it >= opt.max_iteration) *done = 1;
+  return 0;
+}
+
+int ccrs_controller_lm(const ccrs_backend* be, double* intr, const double* lo, const double* hi,
+                       const unsigned char* fixed, const ccrs_options* opt_in, ccrs_summary* sum, double* err_hist) {
+  ccrs_summary local_sum;
+  if (!sum) sum = &local_sum;
+  ccrs_lm_state S;
+  int st = lm_begin(S, be, intr, lo, hi, fixed, opt_in, sum, err_hist);
+  if (st) return st;
+  int done = S.opt.max_iteration <= 0;
+  while (!done) {
+    st = lm_iterate(S, &done);
+    if (st) return st;
+  }
+  sum->stop_reason = S.stop[0];
+  sum->status = S.worst;
+  return S.worst;
+}
+
+// Stepping interface for measurement (ccrs_bench_lm_steps): opaque state, one LM iteration per call.
+ccrs_lm_state* ccrs_lm_state_create(const ccrs_backend* be, double* intr, const ccrs_options* opt, ccrs_summary* sum) {
+  ccrs_lm_state* S = new ccrs_lm_state();
+  if (lm_begin(*S, be, intr, nullptr, nullptr, nullptr, opt, sum, nullptr) != 0) { delete S; return nullptr; }
+  return S;
+}
+int ccrs_lm_state_step(ccrs_lm_state* S, int* done) { return lm_iterate(*S, done); }
+void ccrs_lm_state_destroy(ccrs_lm_state* S) { delete S; }
 
 }  // extern "C"

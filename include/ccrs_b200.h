@@ -143,6 +143,9 @@ int ccrs_accept(ccrs_problem* p, const unsigned char* mask);
  * produced by ccrs_comm_unique_id on rank 0 and distributed by the host (torch.distributed / MPI). */
 int ccrs_comm_unique_id(void* unique_id_128);
 int ccrs_comm_init(ccrs_problem* p, const void* unique_id_128, int rank, int world_size);
+/* The communicator is process-wide (one process per GPU): ccrs_comm_init with unique_id_128 == NULL attaches
+ * the communicator an earlier call created to another handle. ccrs_comm_finalize destroys it. */
+int ccrs_comm_finalize(void);
 /* deterministic = 1: all-gather the per-rank partials and sum in rank order on every rank (default);
  * 0: ncclAllReduce(sum) as north_star names. */
 int ccrs_comm_set_deterministic(ccrs_problem* p, int deterministic);
@@ -229,6 +232,13 @@ int ccrs_model_bounds(int model, int width, int height, double* lo, double* hi);
 int ccrs_measure_fp64_peak(int device_id, double* tflops);
 /* Time `reps` back-to-back launches of K2 (linearise) with CUDA events on the handle's stream. */
 int ccrs_time_linearize(ccrs_problem* p, const double* intr, int reps, int flush_l2, double* avg_ms);
+/* `warmup` untimed + `steps` timed LM iterations with the stop tests disabled, each iteration bracketed by CUDA
+ * events on the handle's stream (step_ms[steps]). Every `reset_every` iterations the state returns to
+ * (intr0, poses0) outside the timed bracket, so every timed step is one of the first `reset_every` LM iterations of
+ * the problem. flush_l2 writes a 512 MB buffer before every iteration, also outside the bracket.
+ * timed_launches = kernels launched inside the timed iterations. */
+int ccrs_bench_lm_steps(ccrs_problem* p, const double* intr0, const double* poses0, int warmup, int steps,
+                        int reset_every, int flush_l2, double* step_ms, int64_t* timed_launches);
 /* Kernel launches issued by this handle since creation. */
 int64_t ccrs_launch_count(const ccrs_problem* p);
 
