@@ -9,7 +9,11 @@
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
+#include <atomic>
 #include <limits>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 using namespace ccrs;
@@ -69,21 +73,74 @@ int fail(int code, const char* fmt, ...) {
     if (_e != cudaSuccess) return fail(CCRS_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
 
+// Process-wide caching allocators: cudaMalloc / cudaHostAlloc / cudaFree cost 0.1-1 ms each and a calibration call
+// creates ~30 buffers, far more than the whole solve (a few hundred microseconds). Freed blocks are kept and reused.
+struct BlockPool {
+  bool host;
+  std::mutex mu;
+  std::multimap<size_t, void*> free_blocks;
+  std::unordered_map<void*, size_t> live;
+  explicit BlockPool(bool h) : host(h) {}
+  cudaError_t get(size_t bytes, void** out) {
+    bytes = std::max<size_t>((bytes + 255) / 256 * 256, 256);
+    {
+      std::lock_guard<std::mutex> g(mu);
+      auto it = free_blocks.lower_bound(bytes);
+      if (it != free_blocks.end() && it->first <= 2 * bytes + (1u << 20)) {
+        *out = it->second;
+        live[*out] = it->first;
+        free_blocks.erase(it);
+        return cudaSuccess;
+      }
+    }
+    cudaError_t e = host ? cudaHostAlloc(out, bytes, cudaHostAllocMapped | cudaHostAllocPortable) : cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {  // out of memory: drop the cache and retry once
+      trim();
+      e = host ? cudaHostAlloc(out, bytes, cudaHostAllocMapped | cudaHostAllocPortable) : cudaMalloc(out, bytes);
+    }
+    if (e == cudaSuccess) { std::lock_guard<std::mutex> g(mu); live[*out] = bytes; }
+    return e;
+  }
+  void put(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> g(mu);
+    auto it = live.find(p);
+    if (it == live.end()) return;
+    free_blocks.emplace(it->second, p);
+    live.erase(it);
+  }
+  void trim() {
+    std::lock_guard<std::mutex> g(mu);
+    for (auto& kv : free_blocks) { if (host) cudaFreeHost(kv.second); else cudaFree(kv.second); }
+    free_blocks.clear();
+  }
+};
+BlockPool& dev_pool(int device) {
+  static BlockPool* pools[64] = {nullptr};
+  static std::mutex mu;
+  std::lock_guard<std::mutex> g(mu);
+  if (!pools[device & 63]) pools[device & 63] = new BlockPool(false);
+  return *pools[device & 63];
+}
+BlockPool& host_pool() { static BlockPool pool(true); return pool; }
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  int dev = 0;
   cudaError_t alloc(size_t count) {
     n = count;
-    return cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+    cudaGetDevice(&dev);
+    return dev_pool(dev).get(std::max<size_t>(count, 1) * sizeof(T), (void**)&p);
   }
-  void release() { if (p) cudaFree(p); p = nullptr; }
+  void release() { if (p) dev_pool(dev).put(p); p = nullptr; }
 };
 template <class T>
-struct PinBuf {
+struct PinBuf {   // page-locked, mapped into the device address space (UVA: same pointer on host and device)
   T* p = nullptr;
-  cudaError_t alloc(size_t count) { return cudaMallocHost((void**)&p, std::max<size_t>(count, 1) * sizeof(T)); }
-  void release() { if (p) cudaFreeHost(p); p = nullptr; }
+  cudaError_t alloc(size_t count) { return host_pool().get(std::max<size_t>(count, 1) * sizeof(T), (void**)&p); }
+  void release() { if (p) host_pool().put(p); p = nullptr; }
 };
 }  // namespace
 
@@ -96,21 +153,28 @@ struct ccrs_problem {
   int device = 0;
   int n_sms = 148;
   cudaStream_t stream = nullptr;
-  int G = 1, FPC = 128, n_lin_ctas = 0;
+  int G = 1, FPC = 128, n_lin_ctas = 0, n_schur_ctas = 0;
   double huber = 1.0;
   int64_t launches = 0;
 
   DevBuf<double> x, y, z, u, v;
   DevBuf<int32_t> frame_offsets, frame_problem, problem_frame_offsets, obs_frame, cur, acc_to_blk;
   DevBuf<double> poses[2], blocks[2], frame_cost[2];
-  DevBuf<double> elim, frame_red, pose_scale, frame_md;
+  DevBuf<double> elim, frame_red, pose_scale, frame_md, cta_part;
   DevBuf<double> red_out, stat_out, gather, intr_dev, ya_dev, u_dev, scale_dev, l2_flush;
   DevBuf<unsigned char> mask_dev;
-  PinBuf<double> h_red, h_stat, h_small;
+  DevBuf<unsigned int> tickets;   // [0] K2 statistics, [1] K3 reduction
+  PinBuf<double> h_red, h_stat;   // mapped: single problem [NRED + 1] / [4] (last = sequence number); batch: plain D2H targets
   bool have_scale = false, have_obs_frame = false;
   std::vector<int32_t> h_frame_offsets, h_problem_frame_offsets;
-  // state of the last reduce(), needed by backsub
-  bool last_use_scale = false;
+  bool last_use_scale = false;    // state of the last reduce(), needed by the back-substitution
+  int cur_val = 0;                // single problem: which state buffer is current (host-tracked, passed by value)
+  double seq = 0.0;               // sequence number of the last published result
+  // back-substitution deferred into the prologue of the next K2 launch
+  bool pend = false;
+  int pend_in_place = 0;
+  bool pend_active = false;
+  double pend_ya[9] = {0}, pend_u = 0.0;
   // communicator
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1, deterministic = 1;
@@ -122,7 +186,8 @@ struct ccrs_problem {
     d.frame_problem = batch ? frame_problem.p : nullptr;
     d.problem_frame_offsets = problem_frame_offsets.p;
     d.obs_frame = obs_frame.p;
-    d.cur = cur.p;
+    d.cur = batch ? cur.p : nullptr;
+    d.cur_val = cur_val;
     for (int i = 0; i < 2; ++i) { d.poses[i] = poses[i].p; d.blocks[i] = blocks[i].p; d.frame_cost[i] = frame_cost[i].p; }
     d.n_frames = n_frames; d.n_problems = n_problems; d.Fs = Fs;
     d.huber_delta = huber;
@@ -163,54 +228,77 @@ int upload_problem(ccrs_problem* p, int n_problems, const int32_t* problem_frame
   p->h_frame_offsets.assign(frame_offsets, frame_offsets + n_frames + 1);
   if (problem_frame_offsets) p->h_problem_frame_offsets.assign(problem_frame_offsets, problem_frame_offsets + n_problems + 1);
   else p->h_problem_frame_offsets = {0, n_frames};
+  choose_slicing(p);
+  p->n_schur_ctas = (n_frames + 127) / 128;
   const size_t N = (size_t)p->n_obs, F = (size_t)n_frames, Fs = (size_t)p->Fs, P = (size_t)n_problems;
-  CK(p->x.alloc(N)); CK(p->y.alloc(N)); CK(p->z.alloc(N)); CK(p->u.alloc(N)); CK(p->v.alloc(N));
-  CK(p->frame_offsets.alloc(F + 1));
-  CK(p->problem_frame_offsets.alloc(P + 1));
-  CK(p->cur.alloc(P));
-  CK(p->acc_to_blk.alloc(p->NACC));
-  for (int i = 0; i < 2; ++i) {
-    CK(p->poses[i].alloc(F * 6));
-    CK(p->blocks[i].alloc((size_t)p->NBLK * Fs));
-    CK(p->frame_cost[i].alloc(Fs));
-    CK(cudaMemsetAsync(p->blocks[i].p, 0, (size_t)p->NBLK * Fs * sizeof(double), p->stream));  // structural zeros stay zero
-    CK(cudaMemsetAsync(p->poses[i].p, 0, F * 6 * sizeof(double), p->stream));
-  }
-  CK(p->elim.alloc((size_t)(6 * p->D + 18) * Fs));
-  const size_t n_schur_ctas = (F + 127) / 128;
-  CK(p->frame_red.alloc(std::max((size_t)p->NRED * Fs, n_schur_ctas * (size_t)p->NRED)));
-  CK(p->pose_scale.alloc(6 * Fs));
-  CK(p->frame_md.alloc(Fs));
-  CK(p->red_out.alloc(P * p->NRED));
-  CK(p->stat_out.alloc(P * 2));
-  CK(p->intr_dev.alloc(P * p->D)); CK(p->ya_dev.alloc(P * p->D)); CK(p->u_dev.alloc(P)); CK(p->scale_dev.alloc(P * p->D));
-  CK(p->mask_dev.alloc(P));
-  CK(p->h_red.alloc(P * p->NRED)); CK(p->h_stat.alloc(P * 2)); CK(p->h_small.alloc(P * (p->D + 2)));
-  CK(cudaMemsetAsync(p->cur.p, 0, P * sizeof(int32_t), p->stream));
-  CK(cudaMemsetAsync(p->u_dev.p, 0, P * sizeof(double), p->stream));
   cudaStream_t s = p->stream;
+  CK(p->x.alloc(N)); CK(p->y.alloc(N)); CK(p->z.alloc(N)); CK(p->u.alloc(N)); CK(p->v.alloc(N));
+  // start the big copies first so everything below overlaps with them
   CK(cudaMemcpyAsync(p->x.p, x, N * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(p->y.p, y, N * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(p->z.p, z, N * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(p->u.p, u, N * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(p->v.p, v, N * 8, cudaMemcpyHostToDevice, s));
+  CK(p->frame_offsets.alloc(F + 1));
+  CK(p->problem_frame_offsets.alloc(P + 1));
+  CK(p->cur.alloc(P));
+  CK(p->acc_to_blk.alloc(p->NACC));
+  CK(p->tickets.alloc(2));
+  CK(cudaMemsetAsync(p->tickets.p, 0, 2 * sizeof(unsigned int), s));
+  for (int i = 0; i < 2; ++i) {
+    CK(p->poses[i].alloc(F * 6));
+    CK(p->blocks[i].alloc((size_t)p->NBLK * Fs));
+    CK(p->frame_cost[i].alloc(Fs));
+    CK(cudaMemsetAsync(p->blocks[i].p, 0, (size_t)p->NBLK * Fs * sizeof(double), s));  // structural zeros stay zero
+    CK(cudaMemsetAsync(p->poses[i].p, 0, F * 6 * sizeof(double), s));
+  }
+  CK(p->elim.alloc((size_t)(6 * p->D + 18) * Fs));
+  CK(p->frame_red.alloc(std::max((size_t)p->NRED * Fs, (size_t)p->n_schur_ctas * p->NRED)));
+  CK(p->pose_scale.alloc(6 * Fs));
+  CK(p->frame_md.alloc(Fs));
+  CK(p->cta_part.alloc((size_t)2 * p->n_lin_ctas));
+  CK(p->red_out.alloc(P * p->NRED));
+  CK(p->stat_out.alloc(P * 2));
+  CK(p->intr_dev.alloc(P * p->D)); CK(p->ya_dev.alloc(P * p->D)); CK(p->u_dev.alloc(P)); CK(p->scale_dev.alloc(P * p->D));
+  CK(p->mask_dev.alloc(P));
+  CK(p->h_red.alloc(P * p->NRED + 1)); CK(p->h_stat.alloc(P * 2 + 2));
+  p->h_red.p[p->NRED] = -1.0; p->h_stat.p[2] = -1.0; p->h_stat.p[3] = -1.0;
+  CK(cudaMemsetAsync(p->cur.p, 0, P * sizeof(int32_t), s));
+  CK(cudaMemsetAsync(p->u_dev.p, 0, P * sizeof(double), s));
   CK(cudaMemcpyAsync(p->frame_offsets.p, frame_offsets, (F + 1) * 4, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(p->problem_frame_offsets.p, p->h_problem_frame_offsets.data(), (P + 1) * 4, cudaMemcpyHostToDevice, s));
   std::vector<int32_t> tbl(p->NACC);
   fill_acc_to_blk(p->model, p->one_focal, tbl.data());
   CK(cudaMemcpyAsync(p->acc_to_blk.p, tbl.data(), tbl.size() * 4, cudaMemcpyHostToDevice, s));
+  std::vector<int32_t> fp;
   if (p->batch) {
-    std::vector<int32_t> fp(F);
+    fp.resize(F);
     for (int b = 0; b < n_problems; ++b)
       for (int f = problem_frame_offsets[b]; f < problem_frame_offsets[b + 1]; ++f) fp[f] = b;
     CK(p->frame_problem.alloc(F));
     CK(cudaMemcpyAsync(p->frame_problem.p, fp.data(), F * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaStreamSynchronize(s));
   }
   CK(cudaStreamSynchronize(s));
-  choose_slicing(p);
   return 0;
 }
+
+// streams are cached per process too (creation costs ~10 us, destruction synchronises)
+std::mutex g_stream_mu;
+std::vector<std::pair<int, cudaStream_t>> g_streams;
+cudaError_t get_stream(int device, cudaStream_t* out) {
+  {
+    std::lock_guard<std::mutex> g(g_stream_mu);
+    for (size_t i = 0; i < g_streams.size(); ++i)
+      if (g_streams[i].first == device) { *out = g_streams[i].second; g_streams.erase(g_streams.begin() + i); return cudaSuccess; }
+  }
+  return cudaStreamCreateWithFlags(out, cudaStreamNonBlocking);
+}
+void put_stream(int device, cudaStream_t s) { std::lock_guard<std::mutex> g(g_stream_mu); g_streams.emplace_back(device, s); }
+
+std::atomic<unsigned long long> g_seq{0};
+double next_seq() { return (double)(++g_seq); }
+
+struct DevInfo { bool known = false; int major = 0, minor = 0, sms = 0; } g_dev_info[64];
 
 int create_common(ccrs_problem** out, int model, int width, int height, int xy_same_focal, int n_problems,
                   const int32_t* problem_frame_offsets, int n_frames, const int32_t* frame_offsets, const double* x,
@@ -226,18 +314,23 @@ int create_common(ccrs_problem** out, int model, int width, int height, int xy_s
     cudaGetLastError();
     return fail(CCRS_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
   }
-  if (device_id < 0 || device_id >= n_dev) return fail(CCRS_ERR_INVALID, "device %d out of range", device_id);
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device_id));
-  if (prop.major != 10) return fail(CCRS_ERR_NO_DEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only", device_id, prop.major, prop.minor);
+  if (device_id < 0 || device_id >= n_dev || device_id >= 64) return fail(CCRS_ERR_INVALID, "device %d out of range", device_id);
+  DevInfo& di = g_dev_info[device_id];
+  if (!di.known) {
+    CK(cudaDeviceGetAttribute(&di.major, cudaDevAttrComputeCapabilityMajor, device_id));
+    CK(cudaDeviceGetAttribute(&di.minor, cudaDevAttrComputeCapabilityMinor, device_id));
+    CK(cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, device_id));
+    di.known = true;
+  }
+  if (di.major != 10) return fail(CCRS_ERR_NO_DEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only", device_id, di.major, di.minor);
   CK(cudaSetDevice(device_id));
   ccrs_problem* p = new ccrs_problem();
   p->model = model; p->width = width; p->height = height; p->one_focal = xy_same_focal ? 1 : 0;
-  p->huber = huber_delta; p->device = device_id; p->batch = batch; p->n_sms = prop.multiProcessorCount;
+  p->huber = huber_delta; p->device = device_id; p->batch = batch; p->n_sms = di.sms;
   model_dims(model, p->one_focal, &p->D, &p->NA, &p->NBLK, &p->NACC);
   p->NRED = nred_of(p->D);
   p->NOUT = p->D * p->D + 3 * p->D + 1;
-  cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+  cudaError_t e = get_stream(device_id, &p->stream);
   if (e != cudaSuccess) { delete p; return fail(CCRS_ERR_CUDA, "stream: %s", cudaGetErrorString(e)); }
   int st = upload_problem(p, n_problems, problem_frame_offsets, n_frames, frame_offsets, x, y, z, u, v);
   if (st != 0) { ccrs_problem_destroy(p); return st; }
@@ -245,19 +338,40 @@ int create_common(ccrs_problem** out, int model, int width, int height, int xy_s
   return 0;
 }
 
-// sum `count` doubles across ranks on the device (stream-ordered); in == out allowed
-int exchange(ccrs_problem* p, double* buf, size_t count) {
-  if (!p->comm) return 0;
+// Spin on a sequence number the GPU writes to mapped host memory after its results (kernel-to-host latency of a
+// PCIe write instead of a D2H copy + stream synchronisation). Falls back to the stream status so a failed launch
+// cannot hang the host.
+int wait_seq(ccrs_problem* p, volatile double* flag, double seq) {
+  for (unsigned long spins = 1;; ++spins) {
+    if (*flag == seq) return 0;
+    if ((spins & 0x3fff) == 0) {
+      cudaError_t e = cudaStreamQuery(p->stream);
+      if (e == cudaSuccess) {
+        if (*flag == seq) return 0;
+        return fail(CCRS_ERR_CUDA, "stream drained but result %g was never published", seq);
+      }
+      if (e != cudaErrorNotReady) return fail(CCRS_ERR_CUDA, "stream error while waiting: %s", cudaGetErrorString(e));
+    }
+  }
+}
+
+// sum `count` doubles across ranks on the device (stream-ordered), in place; optionally publish to mapped host memory
+int exchange(ccrs_problem* p, double* buf, size_t count, volatile double* host_out, double seq) {
+  if (!p->comm) {
+    if (host_out) { CK(launch_sum_partials(buf, 1, (int)count, buf, host_out, seq, p->stream)); p->launches++; }
+    return 0;
+  }
   NcclApi& n = nccl();
   if (p->deterministic) {
     if (p->gather.n < count * p->world) { p->gather.release(); CK(p->gather.alloc(count * p->world)); }
     int r = n.AllGather(buf, p->gather.p, count, kNcclFloat64, p->comm, p->stream);
     if (r != 0) return fail(CCRS_ERR_COMM, "ncclAllGather: %s", n.GetErrorString ? n.GetErrorString(r) : "?");
-    CK(launch_sum_partials(p->gather.p, p->world, (int)count, buf, p->stream));  // rank order
+    CK(launch_sum_partials(p->gather.p, p->world, (int)count, buf, host_out, seq, p->stream));  // rank order
     p->launches++;
   } else {
     int r = n.AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, p->comm, p->stream);
     if (r != 0) return fail(CCRS_ERR_COMM, "ncclAllReduce: %s", n.GetErrorString ? n.GetErrorString(r) : "?");
+    if (host_out) { CK(launch_sum_partials(buf, 1, (int)count, buf, host_out, seq, p->stream)); p->launches++; }
   }
   return 0;
 }
@@ -268,11 +382,75 @@ int upload_intr(ccrs_problem* p, const double* intr) {
   return 0;
 }
 
-int do_linearize(ccrs_problem* p, const double* intr, int which, bool cost_only) {
+// standalone K4 (used by the public ccrs_backsub and to flush a deferred back-substitution)
+int launch_backsub_now(ccrs_problem* p, int in_place, bool want_md) {
+  if (!p->batch) {  // the single-problem hot path keeps y_a / u on the host (kernel arguments); upload them for K4
+    CK(cudaMemcpyAsync(p->ya_dev.p, p->pend_ya, (size_t)p->D * 8, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(p->u_dev.p, &p->pend_u, 8, cudaMemcpyHostToDevice, p->stream));
+  }
+  BacksubParams prm{};
+  prm.pb = p->dev();
+  prm.elim = p->elim.p;
+  prm.y_a = p->ya_dev.p;
+  prm.u_dev = p->u_dev.p;
+  prm.pose_scale = p->last_use_scale ? p->pose_scale.p : nullptr;
+  prm.frame_md = want_md ? p->frame_md.p : nullptr;
+  prm.in_place = in_place;
+  prm.active = p->pend_active ? p->mask_dev.p : nullptr;
+  CK(launch_backsub(p->D, prm, p->stream));
+  p->launches++;
+  return 0;
+}
+
+// record a back-substitution; it runs in the prologue of the next K2 launch (or on flush)
+int defer_backsub(ccrs_problem* p, const double* y_a, const double* u, const unsigned char* active, int in_place) {
+  const int P = p->n_problems, D = p->D;
+  if (p->pend) { p->pend = false; int st = launch_backsub_now(p, p->pend_in_place, false); if (st) return st; }
+  p->pend_active = false;
+  if (p->batch) {
+    CK(cudaMemcpyAsync(p->ya_dev.p, y_a, (size_t)P * D * 8, cudaMemcpyHostToDevice, p->stream));
+    if (u) CK(cudaMemcpyAsync(p->u_dev.p, u, (size_t)P * 8, cudaMemcpyHostToDevice, p->stream));
+    else CK(cudaMemsetAsync(p->u_dev.p, 0, (size_t)P * 8, p->stream));
+    if (active) {
+      CK(cudaMemcpyAsync(p->mask_dev.p, active, (size_t)P, cudaMemcpyHostToDevice, p->stream));
+      p->pend_active = true;
+    }
+  } else {
+    for (int i = 0; i < D; ++i) p->pend_ya[i] = y_a[i];
+    p->pend_u = u ? u[0] : 0.0;
+  }
+  p->pend = true;
+  p->pend_in_place = in_place;
+  return 0;
+}
+
+int flush_pending(ccrs_problem* p) {
+  if (!p->pend) return 0;
+  p->pend = false;
+  return launch_backsub_now(p, p->pend_in_place, false);
+}
+
+// K2 (or its cost-only variant K5). A deferred back-substitution that targets the same point is fused into the
+// prologue. Single problem: {model decrease, cost} are reduced in-kernel and published under sequence number *seq_out.
+int do_linearize(ccrs_problem* p, const double* intr, int which, bool cost_only, bool publish, double* seq_out) {
+  if (p->pend && (p->pend_in_place ? which != 0 : which != 1)) { int st = flush_pending(p); if (st) return st; }
   LinParams prm{};
   prm.pb = p->dev();
   prm.which = which; prm.G = p->G; prm.FPC = p->FPC;
   prm.acc_to_blk = p->acc_to_blk.p;
+  if (p->pend) {
+    prm.backsub = p->pend_in_place ? 2 : 1;
+    prm.elim = p->elim.p;
+    prm.pose_scale = p->last_use_scale ? p->pose_scale.p : nullptr;
+    prm.ya_dev = p->ya_dev.p; prm.u_dev = p->u_dev.p;
+    prm.active = p->pend_active ? p->mask_dev.p : nullptr;
+    prm.frame_md = p->frame_md.p;
+    for (int i = 0; i < p->D; ++i) prm.y_a[i] = p->pend_ya[i];
+    prm.u = p->pend_u;
+    p->pend = false;
+  } else if (p->batch) {
+    CK(cudaMemsetAsync(p->frame_md.p, 0, (size_t)p->Fs * 8, p->stream));  // no step taken: model decrease 0
+  }
   if (p->batch) {
     int st = upload_intr(p, intr);
     if (st) return st;
@@ -280,9 +458,41 @@ int do_linearize(ccrs_problem* p, const double* intr, int which, bool cost_only)
   } else {
     if (p->one_focal) { prm.intr[0] = intr[0]; prm.intr[1] = intr[0]; for (int i = 1; i < p->D; ++i) prm.intr[i + 1] = intr[i]; }
     else for (int i = 0; i < p->D; ++i) prm.intr[i] = intr[i];
+    prm.cta_part = p->cta_part.p;
+    prm.ticket = p->tickets.p;
+    prm.stat_dev = p->stat_out.p;
+    p->seq = next_seq();
+    prm.seq = p->seq;
+    prm.host_stat = (publish && !p->comm) ? p->h_stat.p : nullptr;
+    if (seq_out) *seq_out = p->seq;
   }
   CK(launch_linearize(p->model, p->one_focal, p->batch, cost_only, prm, p->n_lin_ctas, p->stream));
   p->launches++;
+  if (!p->batch && publish && p->comm) {
+    int st = exchange(p, p->stat_out.p, 2, p->h_stat.p, p->seq);   // h_stat[0..1] = sums, h_stat[2] = seq
+    if (st) return st;
+  }
+  return 0;
+}
+
+// {model decrease, cost} of the last K2 launch. mode: see launch_trial_stats (batch path only).
+int fetch_stats(ccrs_problem* p, int batch_mode, double seq, double* out /* [P][2] */) {
+  const int P = p->n_problems;
+  if (!p->batch) {
+    // without a communicator the kernel publishes {md, cost, 0} then seq at [3]; with one, sum_partials publishes
+    // {md, cost} then seq at [2]
+    int st = wait_seq(p, p->comm ? p->h_stat.p + 2 : p->h_stat.p + 3, seq);
+    if (st) return st;
+    out[0] = p->h_stat.p[0]; out[1] = p->h_stat.p[1];
+    return 0;
+  }
+  CK(launch_trial_stats(p->dev(), p->NBLK - 1, batch_mode, p->frame_md.p, p->stat_out.p, p->stream));
+  p->launches++;
+  int st = exchange(p, p->stat_out.p, (size_t)P * 2, nullptr, 0.0);
+  if (st) return st;
+  CK(cudaMemcpyAsync(p->h_stat.p, p->stat_out.p, (size_t)P * 2 * 8, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  std::memcpy(out, p->h_stat.p, (size_t)P * 2 * 8);
   return 0;
 }
 
@@ -296,31 +506,43 @@ int reduce_frames(ccrs_problem* p, const double* in, int NV, double* out_dev) {
 int do_reduce(ccrs_problem* p, int which, const double* u, int use_scale, double min_diag, double max_diag, double* out) {
   const int D = p->D, P = p->n_problems;
   if (use_scale && !p->have_scale) return fail(CCRS_ERR_INVALID, "use_scale without ccrs_compute_scale/ccrs_set_intr_scale");
-  if (u) CK(cudaMemcpyAsync(p->u_dev.p, u, (size_t)P * 8, cudaMemcpyHostToDevice, p->stream));
-  else CK(cudaMemsetAsync(p->u_dev.p, 0, (size_t)P * 8, p->stream));
+  int st = flush_pending(p);
+  if (st) return st;
   SchurParams prm{};
   prm.pb = p->dev();
   prm.which = which;
-  prm.u_dev = p->u_dev.p;
   prm.intr_scale = use_scale ? p->scale_dev.p : nullptr;
   prm.pose_scale = use_scale ? p->pose_scale.p : nullptr;
   prm.min_diag = min_diag; prm.max_diag = max_diag;
   prm.elim = p->elim.p;
   prm.frame_red = p->frame_red.p;
   p->last_use_scale = use_scale != 0;
-  CK(launch_schur(D, prm, p->stream));
-  p->launches++;
   if (p->batch) {
-    int st = reduce_frames(p, p->frame_red.p, p->NRED, p->red_out.p);
-    if (st) return st;
-  } else {
-    CK(launch_sum_partials(p->frame_red.p, (p->n_frames + 127) / 128, p->NRED, p->red_out.p, p->stream));
+    if (u) CK(cudaMemcpyAsync(p->u_dev.p, u, (size_t)P * 8, cudaMemcpyHostToDevice, p->stream));
+    else CK(cudaMemsetAsync(p->u_dev.p, 0, (size_t)P * 8, p->stream));
+    prm.u_dev = p->u_dev.p;
+    CK(launch_schur(D, prm, p->stream));
     p->launches++;
+    st = reduce_frames(p, p->frame_red.p, p->NRED, p->red_out.p);
+    if (st) return st;
+    st = exchange(p, p->red_out.p, (size_t)P * p->NRED, nullptr, 0.0);
+    if (st) return st;
+    CK(cudaMemcpyAsync(p->h_red.p, p->red_out.p, (size_t)P * p->NRED * 8, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+  } else {
+    prm.u_dev = nullptr;
+    prm.u_val = u ? u[0] : 0.0;
+    prm.ticket = p->tickets.p + 1;
+    prm.red_out = p->red_out.p;
+    p->seq = next_seq();
+    prm.seq = p->seq;
+    prm.host_red = p->comm ? nullptr : p->h_red.p;
+    CK(launch_schur(D, prm, p->stream));
+    p->launches++;
+    if (p->comm) { st = exchange(p, p->red_out.p, (size_t)p->NRED, p->h_red.p, p->seq); if (st) return st; }
+    st = wait_seq(p, p->h_red.p + p->NRED, p->seq);
+    if (st) return st;
   }
-  int st = exchange(p, p->red_out.p, (size_t)P * p->NRED);
-  if (st) return st;
-  CK(cudaMemcpyAsync(p->h_red.p, p->red_out.p, (size_t)P * p->NRED * 8, cudaMemcpyDeviceToHost, p->stream));
-  CK(cudaStreamSynchronize(p->stream));
   // unpack: packed upper S -> full row-major
   const int NS = D * (D + 1) / 2;
   for (int q = 0; q < P; ++q) {
@@ -334,53 +556,24 @@ int do_reduce(ccrs_problem* p, int which, const double* u, int use_scale, double
   return 0;
 }
 
-int do_backsub(ccrs_problem* p, const double* y_a, const double* u, const unsigned char* active, int in_place, bool want_md) {
-  const int P = p->n_problems, D = p->D;
-  CK(cudaMemcpyAsync(p->ya_dev.p, y_a, (size_t)P * D * 8, cudaMemcpyHostToDevice, p->stream));
-  if (u) CK(cudaMemcpyAsync(p->u_dev.p, u, (size_t)P * 8, cudaMemcpyHostToDevice, p->stream));
-  else CK(cudaMemsetAsync(p->u_dev.p, 0, (size_t)P * 8, p->stream));
-  BacksubParams prm{};
-  prm.pb = p->dev();
-  prm.elim = p->elim.p;
-  prm.y_a = p->ya_dev.p;
-  prm.u_dev = p->u_dev.p;
-  prm.pose_scale = p->last_use_scale ? p->pose_scale.p : nullptr;
-  prm.frame_md = want_md ? p->frame_md.p : nullptr;
-  prm.in_place = in_place;
-  prm.active = nullptr;
-  if (active) {
-    CK(cudaMemcpyAsync(p->mask_dev.p, active, (size_t)P, cudaMemcpyHostToDevice, p->stream));
-    prm.active = p->mask_dev.p;
-  }
-  CK(launch_backsub(D, prm, p->stream));
-  p->launches++;
-  return 0;
-}
-
 // ---- CUDA implementation of the controller's backend table ------------------------------------------------------
-int be_linearize(void* ctx, const double* intr, int which) { return do_linearize((ccrs_problem*)ctx, intr, which, false); }
+int be_linearize(void* ctx, const double* intr, int which) {
+  return do_linearize((ccrs_problem*)ctx, intr, which, false, false, nullptr);
+}
 int be_compute_scale(void* ctx, int which, double* col_sq) { return ccrs_compute_scale((ccrs_problem*)ctx, which, col_sq); }
 int be_set_intr_scale(void* ctx, const double* s) { return ccrs_set_intr_scale((ccrs_problem*)ctx, s); }
 int be_reduce(void* ctx, int which, const double* u, int use_scale, double mn, double mx, double* out) {
   return do_reduce((ccrs_problem*)ctx, which, u, use_scale, mn, mx, out);
 }
 int be_backsub(void* ctx, const double* y_a, const double* u, const unsigned char* active, int in_place) {
-  return do_backsub((ccrs_problem*)ctx, y_a, u, active, in_place, !in_place);
+  return defer_backsub((ccrs_problem*)ctx, y_a, u, active, in_place);   // fused into the next K2 launch
 }
 int be_trial_stats(void* ctx, const double* intr_trial, int speculative, double* out) {
   ccrs_problem* p = (ccrs_problem*)ctx;
-  const int P = p->n_problems;
-  int st = do_linearize(p, intr_trial, 1, !speculative);
+  double seq = 0.0;
+  int st = do_linearize(p, intr_trial, 1, !speculative, true, &seq);
   if (st) return st;
-  // stat_out[q] = {model_dec pose part, sq_err at the trial point}, reduced per problem in a fixed order
-  CK(launch_trial_stats(p->dev(), p->NBLK - 1, speculative, p->frame_md.p, p->stat_out.p, p->stream));
-  p->launches++;
-  st = exchange(p, p->stat_out.p, (size_t)P * 2);
-  if (st) return st;
-  CK(cudaMemcpyAsync(p->h_stat.p, p->stat_out.p, (size_t)P * 2 * 8, cudaMemcpyDeviceToHost, p->stream));
-  CK(cudaStreamSynchronize(p->stream));
-  std::memcpy(out, p->h_stat.p, (size_t)P * 2 * 8);
-  return 0;
+  return fetch_stats(p, speculative ? 1 : 0, seq, out);
 }
 int be_accept(void* ctx, const unsigned char* mask) { return ccrs_accept((ccrs_problem*)ctx, mask); }
 
@@ -428,14 +621,28 @@ int ccrs_problem_destroy(ccrs_problem* p) {
   if (p->stream) cudaStreamSynchronize(p->stream);
   p->x.release(); p->y.release(); p->z.release(); p->u.release(); p->v.release();
   p->frame_offsets.release(); p->frame_problem.release(); p->problem_frame_offsets.release(); p->obs_frame.release();
-  p->cur.release(); p->acc_to_blk.release();
+  p->cur.release(); p->acc_to_blk.release(); p->tickets.release();
   for (int i = 0; i < 2; ++i) { p->poses[i].release(); p->blocks[i].release(); p->frame_cost[i].release(); }
-  p->elim.release(); p->frame_red.release(); p->pose_scale.release(); p->frame_md.release();
+  p->elim.release(); p->frame_red.release(); p->pose_scale.release(); p->frame_md.release(); p->cta_part.release();
   p->red_out.release(); p->stat_out.release(); p->gather.release(); p->intr_dev.release(); p->ya_dev.release();
   p->u_dev.release(); p->scale_dev.release(); p->l2_flush.release(); p->mask_dev.release();
-  p->h_red.release(); p->h_stat.release(); p->h_small.release();
-  if (p->stream) cudaStreamDestroy(p->stream);
+  p->h_red.release(); p->h_stat.release();
+  if (p->stream) put_stream(p->device, p->stream);
   delete p;
+  return 0;
+}
+
+int ccrs_release_cached_memory(void) {
+  for (int d = 0; d < 64; ++d) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || d >= n) break;
+    cudaSetDevice(d);
+    dev_pool(d).trim();
+  }
+  host_pool().trim();
+  std::lock_guard<std::mutex> g(g_stream_mu);
+  for (auto& s : g_streams) { cudaSetDevice(s.first); cudaStreamDestroy(s.second); }
+  g_streams.clear();
   return 0;
 }
 
@@ -449,8 +656,10 @@ int64_t ccrs_launch_count(const ccrs_problem* p) { return p ? p->launches : -1; 
 int ccrs_set_poses(ccrs_problem* p, const double* poses) {
   if (!p || !poses) return fail(CCRS_ERR_INVALID, "null");
   CK(cudaSetDevice(p->device));
-  // "current" may differ per problem after accepts; resetting poses also resets the buffer selector
-  CK(cudaMemsetAsync(p->cur.p, 0, (size_t)p->n_problems * sizeof(int32_t), p->stream));
+  // resetting the poses also resets the buffer selector and drops any deferred step
+  p->pend = false;
+  p->cur_val = 0;
+  if (p->batch) CK(cudaMemsetAsync(p->cur.p, 0, (size_t)p->n_problems * sizeof(int32_t), p->stream));
   CK(cudaMemcpyAsync(p->poses[0].p, poses, (size_t)p->n_frames * 6 * 8, cudaMemcpyHostToDevice, p->stream));
   CK(cudaStreamSynchronize(p->stream));
   return 0;
@@ -459,6 +668,13 @@ int ccrs_set_poses(ccrs_problem* p, const double* poses) {
 int ccrs_get_poses(ccrs_problem* p, double* poses) {
   if (!p || !poses) return fail(CCRS_ERR_INVALID, "null");
   CK(cudaSetDevice(p->device));
+  int st = flush_pending(p);
+  if (st) return st;
+  if (!p->batch) {
+    CK(cudaMemcpyAsync(poses, p->poses[p->cur_val].p, (size_t)p->n_frames * 48, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+  }
   std::vector<int32_t> cur(p->n_problems);
   std::vector<double> b0((size_t)p->n_frames * 6), b1;
   CK(cudaMemcpyAsync(cur.data(), p->cur.p, cur.size() * 4, cudaMemcpyDeviceToHost, p->stream));
@@ -483,6 +699,8 @@ int ccrs_eval_rj(ccrs_problem* p, const double* intr, const double* poses, int a
   if (!p || !intr || !r) return fail(CCRS_ERR_INVALID, "null");
   if (p->batch) return fail(CCRS_ERR_INVALID, "ccrs_eval_rj is for single-problem handles");
   CK(cudaSetDevice(p->device));
+  int st = flush_pending(p);
+  if (st) return st;
   const size_t N = (size_t)p->n_obs;
   if (!p->have_obs_frame) {
     std::vector<int32_t> of(N);
@@ -497,18 +715,13 @@ int ccrs_eval_rj(ccrs_problem* p, const double* intr, const double* poses, int a
   DevBuf<double> d_r, d_J, d_pose;
   CK(d_r.alloc(2 * N));
   if (J) CK(d_J.alloc(2 * N * n));
-  int st = upload_intr(p, intr);
+  st = upload_intr(p, intr);
   if (st) return st;
-  const double* pose_ptr = nullptr;
+  const double* pose_ptr = p->poses[p->cur_val].p;
   if (poses) {
     CK(d_pose.alloc((size_t)p->n_frames * 6));
     CK(cudaMemcpyAsync(d_pose.p, poses, (size_t)p->n_frames * 48, cudaMemcpyHostToDevice, p->stream));
     pose_ptr = d_pose.p;
-  } else {
-    int32_t cur = 0;
-    CK(cudaMemcpyAsync(&cur, p->cur.p, 4, cudaMemcpyDeviceToHost, p->stream));
-    CK(cudaStreamSynchronize(p->stream));
-    pose_ptr = p->poses[cur].p;
   }
   CK(launch_eval_rj(p->model, p->one_focal, p->dev(), p->intr_dev.p, pose_ptr, apply_loss, d_r.p, J ? d_J.p : nullptr,
                     p->n_obs, p->stream));
@@ -523,16 +736,14 @@ int ccrs_eval_rj(ccrs_problem* p, const double* intr, const double* poses, int a
 int ccrs_linearize(ccrs_problem* p, const double* intr, int which, double* sq_err) {
   if (!p || !intr) return fail(CCRS_ERR_INVALID, "null");
   CK(cudaSetDevice(p->device));
-  int st = do_linearize(p, intr, which, false);
+  double seq = 0.0;
+  int st = do_linearize(p, intr, which ? 1 : 0, false, sq_err != nullptr, &seq);
   if (st) return st;
   if (sq_err) {
-    CK(launch_trial_stats(p->dev(), p->NBLK - 1, which ? 1 : 2, nullptr, p->stat_out.p, p->stream));
-    p->launches++;
-    st = exchange(p, p->stat_out.p, (size_t)p->n_problems * 2);
+    std::vector<double> stats((size_t)p->n_problems * 2);
+    st = fetch_stats(p, which ? 1 : 2, seq, stats.data());
     if (st) return st;
-    CK(cudaMemcpyAsync(p->h_stat.p, p->stat_out.p, (size_t)p->n_problems * 16, cudaMemcpyDeviceToHost, p->stream));
-    CK(cudaStreamSynchronize(p->stream));
-    for (int q = 0; q < p->n_problems; ++q) sq_err[q] = p->h_stat.p[2 * q + 1];
+    for (int q = 0; q < p->n_problems; ++q) sq_err[q] = stats[2 * q + 1];
   }
   return 0;
 }
@@ -542,8 +753,8 @@ int ccrs_get_frame_blocks(ccrs_problem* p, int which, double* blocks) {
   CK(cudaSetDevice(p->device));
   const size_t n = (size_t)p->NBLK * p->Fs;
   std::vector<double> b[2];
-  std::vector<int32_t> cur(p->n_problems);
-  CK(cudaMemcpyAsync(cur.data(), p->cur.p, cur.size() * 4, cudaMemcpyDeviceToHost, p->stream));
+  std::vector<int32_t> cur(p->n_problems, p->cur_val);
+  if (p->batch) CK(cudaMemcpyAsync(cur.data(), p->cur.p, cur.size() * 4, cudaMemcpyDeviceToHost, p->stream));
   for (int i = 0; i < 2; ++i) { b[i].resize(n); CK(cudaMemcpyAsync(b[i].data(), p->blocks[i].p, n * 8, cudaMemcpyDeviceToHost, p->stream)); }
   CK(cudaStreamSynchronize(p->stream));
   for (int q = 0; q < p->n_problems; ++q) {
@@ -562,11 +773,12 @@ int ccrs_compute_scale(ccrs_problem* p, int which, double* col_sq) {
   p->launches++;
   int st = reduce_frames(p, p->frame_red.p, p->D, p->red_out.p);
   if (st) return st;
-  st = exchange(p, p->red_out.p, (size_t)p->n_problems * p->D);
+  st = exchange(p, p->red_out.p, (size_t)p->n_problems * p->D, nullptr, 0.0);
   if (st) return st;
-  CK(cudaMemcpyAsync(p->h_red.p, p->red_out.p, (size_t)p->n_problems * p->D * 8, cudaMemcpyDeviceToHost, p->stream));
+  std::vector<double> tmp((size_t)p->n_problems * p->D);
+  CK(cudaMemcpyAsync(tmp.data(), p->red_out.p, tmp.size() * 8, cudaMemcpyDeviceToHost, p->stream));
   CK(cudaStreamSynchronize(p->stream));
-  std::memcpy(col_sq, p->h_red.p, (size_t)p->n_problems * p->D * 8);
+  std::memcpy(col_sq, tmp.data(), tmp.size() * 8);
   return 0;
 }
 
@@ -575,7 +787,6 @@ int ccrs_set_intr_scale(ccrs_problem* p, const double* intr_scale) {
   CK(cudaSetDevice(p->device));
   if (!intr_scale) { p->have_scale = false; return 0; }
   CK(cudaMemcpyAsync(p->scale_dev.p, intr_scale, (size_t)p->n_problems * p->D * 8, cudaMemcpyHostToDevice, p->stream));
-  CK(cudaStreamSynchronize(p->stream));
   p->have_scale = true;
   return 0;
 }
@@ -589,16 +800,20 @@ int ccrs_reduce(ccrs_problem* p, int which, const double* u, int use_scale, doub
 int ccrs_backsub(ccrs_problem* p, const double* y_a, const double* u, int in_place, double* model_dec) {
   if (!p || !y_a) return fail(CCRS_ERR_INVALID, "null");
   CK(cudaSetDevice(p->device));
-  int st = do_backsub(p, y_a, u, nullptr, in_place, model_dec != nullptr);
+  int st = defer_backsub(p, y_a, u, nullptr, in_place);
+  if (st) return st;
+  p->pend = false;
+  st = launch_backsub_now(p, in_place, model_dec != nullptr);
   if (st) return st;
   if (model_dec) {
     CK(launch_trial_stats(p->dev(), p->NBLK - 1, 3, p->frame_md.p, p->stat_out.p, p->stream));
     p->launches++;
-    st = exchange(p, p->stat_out.p, (size_t)p->n_problems * 2);
+    st = exchange(p, p->stat_out.p, (size_t)p->n_problems * 2, nullptr, 0.0);
     if (st) return st;
-    CK(cudaMemcpyAsync(p->h_stat.p, p->stat_out.p, (size_t)p->n_problems * 16, cudaMemcpyDeviceToHost, p->stream));
+    std::vector<double> tmp((size_t)p->n_problems * 2);
+    CK(cudaMemcpyAsync(tmp.data(), p->stat_out.p, tmp.size() * 8, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
-    for (int q = 0; q < p->n_problems; ++q) model_dec[q] = p->h_stat.p[2 * q];
+    for (int q = 0; q < p->n_problems; ++q) model_dec[q] = tmp[2 * q];
   } else {
     CK(cudaStreamSynchronize(p->stream));
   }
@@ -608,21 +823,25 @@ int ccrs_backsub(ccrs_problem* p, const double* y_a, const double* u, int in_pla
 int ccrs_eval_cost(ccrs_problem* p, const double* intr, int which, double* sq_err) {
   if (!p || !intr || !sq_err) return fail(CCRS_ERR_INVALID, "null");
   CK(cudaSetDevice(p->device));
-  int st = do_linearize(p, intr, which, true);
+  double seq = 0.0;
+  int st = do_linearize(p, intr, which ? 1 : 0, true, true, &seq);
   if (st) return st;
-  CK(launch_trial_stats(p->dev(), p->NBLK - 1, which ? 0 : 4, nullptr, p->stat_out.p, p->stream));
-  p->launches++;
-  st = exchange(p, p->stat_out.p, (size_t)p->n_problems * 2);
+  std::vector<double> stats((size_t)p->n_problems * 2);
+  st = fetch_stats(p, which ? 0 : 4, seq, stats.data());
   if (st) return st;
-  CK(cudaMemcpyAsync(p->h_stat.p, p->stat_out.p, (size_t)p->n_problems * 16, cudaMemcpyDeviceToHost, p->stream));
-  CK(cudaStreamSynchronize(p->stream));
-  for (int q = 0; q < p->n_problems; ++q) sq_err[q] = p->h_stat.p[2 * q + 1];
+  for (int q = 0; q < p->n_problems; ++q) sq_err[q] = stats[2 * q + 1];
   return 0;
 }
 
 int ccrs_accept(ccrs_problem* p, const unsigned char* mask) {
   if (!p) return fail(CCRS_ERR_INVALID, "null");
   CK(cudaSetDevice(p->device));
+  int st = flush_pending(p);
+  if (st) return st;
+  if (!p->batch) {
+    if (!mask || mask[0]) p->cur_val ^= 1;
+    return 0;
+  }
   const unsigned char* md = nullptr;
   if (mask) {
     CK(cudaMemcpyAsync(p->mask_dev.p, mask, (size_t)p->n_problems, cudaMemcpyHostToDevice, p->stream));
@@ -864,13 +1083,13 @@ int ccrs_time_linearize(ccrs_problem* p, const double* intr, int reps, int flush
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   double total = 0.0;
-  for (int w = 0; w < 3; ++w) { int st = do_linearize(p, intr, 0, false); if (st) return st; }
+  for (int w = 0; w < 3; ++w) { int st = do_linearize(p, intr, 0, false, false, nullptr); if (st) return st; }
   CK(cudaStreamSynchronize(p->stream));
   if (flush_l2) {
     for (int r = 0; r < reps; ++r) {
       CK(launch_l2_flush(p->l2_flush.p, flush_n, p->stream));
       CK(cudaEventRecord(e0, p->stream));
-      int st = do_linearize(p, intr, 0, false);
+      int st = do_linearize(p, intr, 0, false, false, nullptr);
       if (st) return st;
       CK(cudaEventRecord(e1, p->stream));
       CK(cudaEventSynchronize(e1));
@@ -880,7 +1099,7 @@ int ccrs_time_linearize(ccrs_problem* p, const double* intr, int reps, int flush
     }
   } else {
     CK(cudaEventRecord(e0, p->stream));
-    for (int r = 0; r < reps; ++r) { int st = do_linearize(p, intr, 0, false); if (st) return st; }
+    for (int r = 0; r < reps; ++r) { int st = do_linearize(p, intr, 0, false, false, nullptr); if (st) return st; }
     CK(cudaEventRecord(e1, p->stream));
     CK(cudaEventSynchronize(e1));
     float ms = 0.f;

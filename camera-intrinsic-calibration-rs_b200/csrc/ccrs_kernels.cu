@@ -63,6 +63,15 @@ struct Cfg {
   static constexpr int NACC = nacc();
 };
 
+CCRS_D int cur_of(const ProblemDev& pb, int prob) { return pb.cur ? pb.cur[prob] : pb.cur_val; }
+
+// publish n doubles + a sequence number to mapped host memory (the host spins on the sequence number)
+CCRS_D void publish_host(volatile double* dst, const double* src, int n, double seq) {
+  for (int i = 0; i < n; ++i) dst[i] = src[i];
+  __threadfence_system();
+  dst[n] = seq;
+}
+
 // One observation: weighted rows au, av of [J | r] in the LOCAL rotation basis (d/dphi, not d/drvec).
 // Returns the corrected squared residual. Structurally-zero entries of au/av are left untouched.
 template <int MODEL, bool OF, bool WITH_J>
@@ -126,12 +135,46 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   double* s_intr = s_fc + FPC * kFrameConst;             // [FPC][kMaxFull]   (BATCH only)
   double* s_red = s_intr + (BATCH ? FPC * kMaxFull : 0); // [kRedChunk][kLinThreads]
 
+  double* s_stat = s_red + (COST_ONLY ? kLinThreads : kRedChunk * kLinThreads);  // [2][FPC] per-frame md, cost
+
   if (t < nf) {
     const int f = f0 + t;
     const int prob = BATCH ? pb.frame_problem[f] : 0;
-    const int buf = pb.cur[prob] ^ prm.which;
+    const int cur = cur_of(pb, prob);
+    double rt[6];
+    double md = 0.0;
+    if (prm.backsub) {
+      // fused K4: y_p = cg - X y_a ; pose += D_p y_p ; model decrease y_p^T g'_p + u * sum dd_i y_p,i^2
+      const double* src = pb.poses[cur] + 6 * (size_t)f;
+      double* dst = pb.poses[prm.backsub == 2 ? cur : (cur ^ 1)] + 6 * (size_t)f;
+      const bool moves = !(BATCH && prm.active && !prm.active[prob]);
+      const double* ya = BATCH ? prm.ya_dev + (size_t)prob * C::D : prm.y_a;
+      const double u = BATCH ? (prm.u_dev ? prm.u_dev[prob] : 0.0) : prm.u;
+      const double* el = prm.elim + f;
+      const size_t Fs = pb.Fs;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        double v = src[i];
+        if (moves) {
+          double yp = el[(size_t)(6 * C::D + i) * Fs];
+#pragma unroll
+          for (int a = 0; a < C::D; ++a) yp -= el[(size_t)(i * C::D + a) * Fs] * ya[a];
+          const double sp = prm.pose_scale ? prm.pose_scale[(size_t)i * Fs + f] : 1.0;
+          v += sp * yp;
+          md += yp * el[(size_t)(6 * C::D + 6 + i) * Fs] + u * el[(size_t)(6 * C::D + 12 + i) * Fs] * yp * yp;
+        }
+        rt[i] = v;
+        dst[i] = v;
+      }
+      if (BATCH && prm.frame_md) prm.frame_md[f] = md;
+    } else {
+      const double* src = pb.poses[cur ^ prm.which] + 6 * (size_t)f;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) rt[i] = src[i];
+    }
+    s_stat[t] = md;
     FramePose fp;
-    pose_from_rvec_tvec(pb.poses[buf] + 6 * (size_t)f, fp);
+    pose_from_rvec_tvec(rt, fp);
     double* o = s_fc + t * kFrameConst;
 #pragma unroll
     for (int i = 0; i < 9; ++i) o[i] = fp.R[i];
@@ -222,7 +265,8 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
       for (int j = 0; j < G; ++j) s += s_red[t * G + j];
       const int f = f0 + t;
       const int prob = BATCH ? pb.frame_problem[f] : 0;
-      pb.frame_cost[pb.cur[prob] ^ prm.which][f] = s;
+      pb.frame_cost[cur_of(pb, prob) ^ prm.which][f] = s;
+      s_stat[FPC + t] = s;
     }
   } else {
     constexpr int NCH = (C::NACC + kRedChunk - 1) / kRedChunk;
@@ -244,10 +288,44 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
         for (int j = 0; j < G; ++j) s += src[j];
         const int f = f0 + ff;
         const int prob = BATCH ? pb.frame_problem[f] : 0;
-        double* out = pb.blocks[pb.cur[prob] ^ prm.which];
+        double* out = pb.blocks[cur_of(pb, prob) ^ prm.which];
         out[(size_t)prm.acc_to_blk[ch * kRedChunk + e] * pb.Fs + f] = s;
+        if (ch * kRedChunk + e == C::NACC - 1) s_stat[FPC + ff] = s;   // (r,r) entry = the frame's corrected cost
       }
     });
+  }
+
+  // ---- fused statistics (single problem): {model decrease, cost} summed over frames in a fixed order ----
+  if constexpr (!BATCH) {
+    __shared__ int s_last;
+    __syncthreads();
+    if (t == 0) {
+      double md = 0.0, cost = 0.0;
+      for (int i = 0; i < nf; ++i) { md += s_stat[i]; cost += s_stat[FPC + i]; }
+      prm.cta_part[2 * blockIdx.x] = md;
+      prm.cta_part[2 * blockIdx.x + 1] = cost;
+      __threadfence();
+      s_last = (atomicAdd(prm.ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {  // last CTA to finish: sum the CTA partials in CTA order (64 strided lanes x 2 values, fixed tree)
+      __threadfence();
+      double* sh = s_red;
+      const int v = t & 1, lane2 = t >> 1;   // 64 lanes per value
+      double a = 0.0;
+      for (int b = lane2; b < (int)gridDim.x; b += kLinThreads / 2) a += __ldcg(prm.cta_part + 2 * b + v);
+      sh[t] = a;
+      __syncthreads();
+      for (int w = kLinThreads / 2; w >= 2; w >>= 1) {
+        if (t < w) sh[t] += sh[t + w];
+        __syncthreads();
+      }
+      if (t == 0) {
+        prm.stat_dev[0] = sh[0]; prm.stat_dev[1] = sh[1];
+        *prm.ticket = 0u;
+        if (prm.host_stat) { double tmp[3] = {sh[0], sh[1], 0.0}; publish_host(prm.host_stat, tmp, 3, prm.seq); }
+      }
+    }
   }
 }
 
@@ -311,10 +389,10 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(const __grid_constant__
   int bad = 0;
   if (valid) {
     const int prob = BATCH ? pb.frame_problem[f] : 0;
-    const double* blk = pb.blocks[pb.cur[prob] ^ prm.which] + f;
+    const double* blk = pb.blocks[cur_of(pb, prob) ^ prm.which] + f;
     const size_t Fs = pb.Fs;
     auto H = [&](int i, int j) { return blk[(size_t)tri_idx(NA, i, j) * Fs]; };
-    const double u = prm.u_dev ? prm.u_dev[prob] : 0.0;
+    const double u = prm.u_dev ? prm.u_dev[prob] : prm.u_val;
     double sa[D], sp[6];
 #pragma unroll
     for (int a = 0; a < D; ++a) sa[a] = prm.intr_scale ? prm.intr_scale[prob * D + a] : 1.0;
@@ -429,6 +507,7 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(const __grid_constant__
     }
   } else {
     constexpr int LD = kSchurThreads + 1;
+    __shared__ int s_last;
 #pragma unroll
     for (int i = 0; i < NRED; ++i) s_red[i * LD + threadIdx.x] = red[i];
     __syncthreads();
@@ -438,16 +517,49 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(const __grid_constant__
       for (int j = 0; j < kSchurThreads; ++j) s += src[j];
       partials[(size_t)blockIdx.x * NRED + threadIdx.x] = s;
     }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(prm.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {  // last CTA: sum the CTA partials in CTA order; two interleaved halves per value, fixed combine
+      __threadfence();
+      static_assert(2 * NRED <= 2 * kSchurThreads, "NRED too large");
+      const int nb = gridDim.x;
+      for (int idx = threadIdx.x; idx < 2 * NRED; idx += kSchurThreads) {
+        const int v = idx >> 1, h = idx & 1;
+        double a = 0.0;
+        for (int b = h; b < nb; b += 2) a += __ldcg(partials + (size_t)b * NRED + v);
+        s_red[idx] = a;
+      }
+      __syncthreads();
+      if (threadIdx.x < NRED) {
+        const double tot = s_red[2 * threadIdx.x] + s_red[2 * threadIdx.x + 1];
+        prm.red_out[threadIdx.x] = tot;
+        if (prm.host_red) { prm.host_red[threadIdx.x] = tot; __threadfence_system(); }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        *prm.ticket = 0u;
+        if (prm.host_red) { __threadfence_system(); prm.host_red[NRED] = prm.seq; }
+      }
+    }
   }
 }
 
-// out[v] = sum_b partials[b][v], b ascending (fixed order)
-__global__ void k_sum_partials(const double* __restrict__ partials, int n_part, int NV, double* __restrict__ out) {
+// out[v] = sum_b partials[b][v], b ascending (fixed order); optionally published to mapped host memory
+__global__ void k_sum_partials(const double* __restrict__ partials, int n_part, int NV, double* __restrict__ out,
+                               volatile double* host_out, double seq) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= NV) return;
-  double s = 0.0;
-  for (int b = 0; b < n_part; ++b) s += partials[(size_t)b * NV + v];
-  out[v] = s;
+  if (v < NV) {
+    double s = 0.0;
+    for (int b = 0; b < n_part; ++b) s += partials[(size_t)b * NV + v];
+    out[v] = s;
+    if (host_out) { host_out[v] = s; __threadfence_system(); }
+  }
+  if (host_out) {  // single CTA when publishing (NV <= blockDim.x)
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence_system(); host_out[NV] = seq; }
+  }
 }
 
 // out[seg][v] = sum_{f in segment} in[v][f]; one CTA per segment; fixed strided order + fixed tree
@@ -485,7 +597,7 @@ __global__ void __launch_bounds__(128) k_backsub(const __grid_constant__ Backsub
   const double* el = prm.elim + f;
   const double* ya = prm.y_a + (size_t)prob * D;
   const double u = prm.u_dev ? prm.u_dev[prob] : 0.0;
-  const int cur = pb.cur[prob];
+  const int cur = cur_of(pb, prob);
   const double* src = pb.poses[cur] + 6 * (size_t)f;
   double* dst = pb.poses[prm.in_place ? cur : (cur ^ 1)] + 6 * (size_t)f;
   double md = 0.0;
@@ -514,7 +626,7 @@ __global__ void __launch_bounds__(128) k_compute_scale(ProblemDev pb, int which,
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= pb.n_frames) return;
   const int prob = BATCH ? pb.frame_problem[f] : 0;
-  const double* blk = pb.blocks[pb.cur[prob] ^ which] + f;
+  const double* blk = pb.blocks[cur_of(pb, prob) ^ which] + f;
   const size_t Fs = pb.Fs;
   for (int i = 0; i < 6; ++i) pose_scale[(size_t)i * Fs + f] = 1.0 / (1.0 + sqrt(blk[(size_t)tri_idx(NA, D + i, D + i) * Fs]));
   for (int a = 0; a < D; ++a) frame_colsq[(size_t)a * Fs + f] = blk[(size_t)tri_idx(NA, a, a) * Fs];
@@ -527,7 +639,7 @@ __global__ void __launch_bounds__(kSegThreads) k_trial_stats(ProblemDev pb, int 
   __shared__ double sh0[kSegThreads], sh1[kSegThreads];
   const int q = blockIdx.x;
   const int b = pb.problem_frame_offsets[q], e = pb.problem_frame_offsets[q + 1];
-  const int cur = pb.cur[q];
+  const int cur = cur_of(pb, q);
   const double* cost = nullptr;
   if (mode == 0) cost = pb.frame_cost[cur ^ 1];
   else if (mode == 4) cost = pb.frame_cost[cur];
@@ -608,6 +720,7 @@ void fill_acc_to_blk(int model, int one_focal, int32_t* table) {
 static size_t lin_smem_bytes(int FPC, bool batch, bool cost_only) {
   size_t d = (size_t)FPC * kFrameConst + (batch ? (size_t)FPC * kMaxFull : 0);
   d += cost_only ? kLinThreads : (size_t)kRedChunk * kLinThreads;
+  d += 2 * (size_t)FPC;  // per-frame {md, cost}
   return d * sizeof(double);
 }
 
@@ -681,8 +794,14 @@ cudaError_t launch_schur(int D, const SchurParams& prm, cudaStream_t s) {
   });
 }
 
-cudaError_t launch_sum_partials(const double* partials, int n_part, int NV, double* out, cudaStream_t s) {
-  k_sum_partials<<<(NV + 127) / 128, 128, 0, s>>>(partials, n_part, NV, out);
+cudaError_t launch_sum_partials(const double* partials, int n_part, int NV, double* out, volatile double* host_out,
+                                double seq, cudaStream_t s) {
+  if (host_out) {
+    if (NV > 1024) return cudaErrorInvalidValue;
+    k_sum_partials<<<1, (NV + 31) / 32 * 32, 0, s>>>(partials, n_part, NV, out, host_out, seq);
+  } else {
+    k_sum_partials<<<(NV + 127) / 128, 128, 0, s>>>(partials, n_part, NV, out, nullptr, 0.0);
+  }
   return cudaGetLastError();
 }
 

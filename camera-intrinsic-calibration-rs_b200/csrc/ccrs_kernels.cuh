@@ -17,7 +17,8 @@ struct ProblemDev {
   const int32_t* frame_problem;            // [F] problem of each frame (batch) — nullptr for a single problem
   const int32_t* problem_frame_offsets;    // [n_problems+1]
   const int32_t* obs_frame;                // [N] frame of each observation (K1 only)
-  const int32_t* cur;                      // [n_problems] which of the two state buffers is "current"
+  const int32_t* cur;                      // [n_problems] which of the two state buffers is "current" (batch)
+  int cur_val;                             // ... single problem: tracked by the host, passed by value (cur == nullptr)
   double* poses[2];                        // [F][6]
   double* blocks[2];                       // [NBLK][Fs] SoA packed frame blocks
   double* frame_cost[2];                   // [Fs] per-frame sum of corrected r^2 (cost-only pass)
@@ -33,6 +34,22 @@ struct LinParams {
   int which;                // 0 = current point, 1 = trial point
   int G;                    // lanes per frame
   int FPC;                  // frames per CTA = kLinThreads / G
+  // ---- fused K4 (pose back-substitution) in the prologue: 0 none, 1 trial = current + step, 2 in place (GN)
+  int backsub;
+  const double* elim;       // [(6D+18)][Fs] from K3
+  const double* pose_scale; // [6][Fs] or nullptr
+  double y_a[9];            // single problem: scaled intrinsic solution by value
+  double u;                 // single problem: damping used by K3
+  const double* ya_dev;     // batch: [n_problems][D]
+  const double* u_dev;      // batch: [n_problems]
+  const unsigned char* active;  // batch: problems whose poses may move (nullable)
+  double* frame_md;         // [Fs] per-frame model-decrease part (batch reduces it per problem)
+  // ---- fused statistics (single problem): per-CTA partial {md, cost}, final sum by the last CTA in CTA order
+  double* cta_part;         // [n_ctas][2]
+  unsigned int* ticket;
+  double* stat_dev;         // [2] = {md, cost}
+  volatile double* host_stat;  // mapped pinned [4] = {md, cost, -, seq}; nullptr when a cross-rank exchange follows
+  double seq;
 };
 
 struct SchurParams {
@@ -41,9 +58,15 @@ struct SchurParams {
   const double* u_dev;          // [n_problems] damping
   const double* intr_scale;     // [n_problems][D] or nullptr
   const double* pose_scale;     // [6][Fs] or nullptr
+  double u_val;                 // single problem: damping by value (u_dev == nullptr)
   double min_diag, max_diag;
   double* elim;                 // [(6D+18)][Fs]: X (6xD), cg (6), g'_p (6), Dd (6)
-  double* frame_red;            // [NRED][Fs] per-frame contributions to the reduced system
+  double* frame_red;            // batch: [NRED][Fs] per-frame contributions; single: [n_ctas][NRED] CTA partials
+  // single problem: the last CTA sums the CTA partials in CTA order
+  unsigned int* ticket;
+  double* red_out;              // [NRED] device
+  volatile double* host_red;    // mapped pinned [NRED+1] (last = seq); nullptr when a cross-rank exchange follows
+  double seq;
 };
 
 struct BacksubParams {
@@ -74,7 +97,9 @@ cudaError_t launch_compute_scale(int D, const ProblemDev& pb, int which, double*
 // out[n_seg][NV] = sum over frames of in[v][f], f in [seg_off[s], seg_off[s+1]) in a fixed order.
 cudaError_t launch_segreduce(const double* in, int NV, int Fs, const int32_t* seg_off, int n_seg, double* out,
                              cudaStream_t s);
-cudaError_t launch_sum_partials(const double* partials, int n_part, int NV, double* out, cudaStream_t s);
+// out[v] = sum_b partials[b][v] (b ascending); optionally published to mapped host memory followed by seq
+cudaError_t launch_sum_partials(const double* partials, int n_part, int NV, double* out, volatile double* host_out,
+                                double seq, cudaStream_t s);
 // stat_out[n_problems][2] = { sum_f frame_md[f] (0 if null), sum_f cost_f } with cost_f taken from
 // mode 0: frame_cost[trial]  1: (r,r) entry of blocks[trial]  2: (r,r) of blocks[current]  3: none  4: frame_cost[current]
 cudaError_t launch_trial_stats(const ProblemDev& pb, int rr_idx, int mode, const double* frame_md, double* stat_out,

@@ -79,6 +79,9 @@ int ccrs_batch_create(ccrs_problem** out, int model, int width, int height, int 
                       double huber_delta, int device_id);
 
 int ccrs_problem_destroy(ccrs_problem* p);
+/* Device / pinned buffers and streams of destroyed handles are cached process-wide (cudaMalloc/cudaFree cost more
+ * than a whole solve); this returns them to the driver. */
+int ccrs_release_cached_memory(void);
 
 /* Sizes. d = optimised intrinsics per problem; nblk = (d+7)(d+8)/2 packed entries per frame block. */
 int ccrs_problem_dim(const ccrs_problem* p);
