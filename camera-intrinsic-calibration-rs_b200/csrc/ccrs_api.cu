@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <atomic>
@@ -154,6 +155,7 @@ struct ccrs_problem {
   int n_sms = 148;
   cudaStream_t stream = nullptr;
   int G = 1, FPC = 128, n_lin_ctas = 0, n_schur_ctas = 0;
+  int k2_variant = 0;             // 0 = k_linearize (2 CTAs x 128 threads / SM), 1 = k_linearize_pc (warp-specialised)
   double huber = 1.0;
   int64_t launches = 0;
 
@@ -199,7 +201,7 @@ namespace {
 
 // Lanes per frame G: the G that minimises (waves of CTAs) x (observations per lane) for this device.
 void choose_slicing(ccrs_problem* p) {
-  const int slots = p->n_sms * kLinCtasPerSm;  // resident CTAs
+  const int slots = p->n_sms * (p->k2_variant == 1 ? 1 : kLinCtasPerSm);  // resident CTAs (128 streams each)
   int max_cnt = 1;
   for (int f = 0; f < p->n_frames; ++f) max_cnt = std::max(max_cnt, p->h_frame_offsets[f + 1] - p->h_frame_offsets[f]);
   double best = 1e300;
@@ -210,9 +212,12 @@ void choose_slicing(ccrs_problem* p) {
     const int waves = (ctas + slots - 1) / slots;
     const int per_lane = (max_cnt + G - 1) / G;
     // cost model: per-lane observations dominate; a small per-slice constant covers the basis change + reduction
-    const double cost = (double)waves * (per_lane + 2.0);
+    // cost model: per-lane observations dominate; a per-CTA constant covers prologue (pose maths), pipeline fill,
+    // basis change and the shared-memory reduction (measured: ~12 iterations' worth)
+    const double cost = (double)waves * (per_lane + 12.0);
     if (cost < best - 1e-12) { best = cost; bestG = G; }
   }
+  if (const char* e = getenv("CCRS_FORCE_G")) { const int g = atoi(e); if (g >= 1 && g <= kLinThreads) bestG = g; }
   p->G = bestG;
   p->FPC = kLinThreads / bestG;
   p->n_lin_ctas = (p->n_frames + p->FPC - 1) / p->FPC;
@@ -327,6 +332,7 @@ int create_common(ccrs_problem** out, int model, int width, int height, int xy_s
   ccrs_problem* p = new ccrs_problem();
   p->model = model; p->width = width; p->height = height; p->one_focal = xy_same_focal ? 1 : 0;
   p->huber = huber_delta; p->device = device_id; p->batch = batch; p->n_sms = di.sms;
+  if (const char* e = getenv("CCRS_K2_VARIANT")) p->k2_variant = atoi(e);
   model_dims(model, p->one_focal, &p->D, &p->NA, &p->NBLK, &p->NACC);
   p->NRED = nred_of(p->D);
   p->NOUT = p->D * p->D + 3 * p->D + 1;
@@ -466,7 +472,8 @@ int do_linearize(ccrs_problem* p, const double* intr, int which, bool cost_only,
     prm.host_stat = (publish && !p->comm) ? p->h_stat.p : nullptr;
     if (seq_out) *seq_out = p->seq;
   }
-  CK(launch_linearize(p->model, p->one_focal, p->batch, cost_only, prm, p->n_lin_ctas, p->stream));
+  if (p->k2_variant == 1 && !cost_only) CK(launch_linearize_pc(p->model, p->one_focal, p->batch, prm, p->n_lin_ctas, p->stream));
+  else CK(launch_linearize(p->model, p->one_focal, p->batch, cost_only, prm, p->n_lin_ctas, p->stream));
   p->launches++;
   if (!p->batch && publish && p->comm) {
     int st = exchange(p, p->stat_out.p, 2, p->h_stat.p, p->seq);   // h_stat[0..1] = sums, h_stat[2] = seq

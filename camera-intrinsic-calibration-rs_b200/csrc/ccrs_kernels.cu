@@ -330,6 +330,320 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2, warp-specialised variant ("PC": producers / consumers). One CTA of 384 threads per SM:
+//   warps 0-3  consumers  (one per SM sub-partition): own the NACC FP64 accumulators of 32 observation streams each
+//                         and do nothing but LDS + independent DFMAs — a steady stream that keeps the FP64 pipe busy;
+//   warps 4-11 producers  (two per sub-partition): evaluate pose transform, camera model, analytic Jacobian factors
+//                         and the Huber weight (long dependent chains: rsqrt, reciprocal) for the same streams, one
+//                         iteration ahead, and hand NV = 14 + 2 ND factors per observation over through a shared
+//                         memory ring guarded by mbarriers (full/empty per slot and consumer warp).
+// setmaxnreg moves registers from the producers (128) to the consumers (240), so the whole packed Gram block of a
+// stream stays in registers while 12 warps are resident instead of 8. Same stream decomposition, same summation
+// order and same outputs as k_linearize.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPcThreads = 384;
+constexpr int kPcStreams = 128;
+constexpr int kPcSlots = 4;
+
+CCRS_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+CCRS_D void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+CCRS_D void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+CCRS_D void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+
+template <int MODEL, bool OF>
+struct PcCfg {
+  using C = Cfg<MODEL, OF>;
+  static constexpr int NV = 14 + 2 * C::ND;   // w*mx, w*my, w, dk_u[ND], dk_v[ND], du[3], dv[3], q[3], w*ru, w*rv
+  static constexpr int I_DKU = 3, I_DKV = 3 + C::ND, I_DU = 3 + 2 * C::ND, I_DV = I_DU + 3, I_Q = I_DU + 6, I_R = I_DU + 9;
+};
+
+template <int MODEL, bool OF, bool BATCH>
+__global__ void __launch_bounds__(kPcThreads, 1) k_linearize_pc(const __grid_constant__ LinParams prm) {
+  using C = Cfg<MODEL, OF>;
+  using P = PcCfg<MODEL, OF>;
+  extern __shared__ double smem[];
+  const ProblemDev& pb = prm.pb;
+  const int t = threadIdx.x;
+  const int G = prm.G, FPC = prm.FPC;
+  const int f0 = blockIdx.x * FPC;
+  const int nf = min(FPC, pb.n_frames - f0);
+  // shared memory carve-up
+  double* s_fc = smem;                                          // [FPC][kFrameConst]
+  double* s_intr = s_fc + FPC * kFrameConst;                    // [FPC][kMaxFull] (BATCH)
+  double* s_stat = s_intr + (BATCH ? FPC * kMaxFull : 0);       // [2][FPC]
+  unsigned long long* s_bar = (unsigned long long*)(s_stat + 2 * FPC);   // full[kPcSlots][4], empty[kPcSlots][4]
+  int* s_misc = (int*)(s_bar + 2 * kPcSlots * 4);               // [0] n_iter, [1] last-CTA flag
+  double* s_ring = (double*)(s_misc + 4);                       // [kPcSlots][NV][128]; later [NACC][128]
+
+  if (t == 0) {
+    s_misc[0] = 0;
+    for (int i = 0; i < 2 * kPcSlots * 4; ++i) mbar_init(s_bar + i, 32);
+  }
+  __syncthreads();
+  if (t < nf) {
+    const int f = f0 + t;
+    const int prob = BATCH ? pb.frame_problem[f] : 0;
+    const int cur = cur_of(pb, prob);
+    double rt[6];
+    double md = 0.0;
+    if (prm.backsub) {
+      const double* src = pb.poses[cur] + 6 * (size_t)f;
+      double* dst = pb.poses[prm.backsub == 2 ? cur : (cur ^ 1)] + 6 * (size_t)f;
+      const bool moves = !(BATCH && prm.active && !prm.active[prob]);
+      const double* ya = BATCH ? prm.ya_dev + (size_t)prob * C::D : prm.y_a;
+      const double u = BATCH ? (prm.u_dev ? prm.u_dev[prob] : 0.0) : prm.u;
+      const double* el = prm.elim + f;
+      const size_t Fs = pb.Fs;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        double v = src[i];
+        if (moves) {
+          double yp = el[(size_t)(6 * C::D + i) * Fs];
+#pragma unroll
+          for (int a = 0; a < C::D; ++a) yp -= el[(size_t)(i * C::D + a) * Fs] * ya[a];
+          const double sp = prm.pose_scale ? prm.pose_scale[(size_t)i * Fs + f] : 1.0;
+          v += sp * yp;
+          md += yp * el[(size_t)(6 * C::D + 6 + i) * Fs] + u * el[(size_t)(6 * C::D + 12 + i) * Fs] * yp * yp;
+        }
+        rt[i] = v;
+        dst[i] = v;
+      }
+      if (BATCH && prm.frame_md) prm.frame_md[f] = md;
+    } else {
+      const double* src = pb.poses[cur ^ prm.which] + 6 * (size_t)f;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) rt[i] = src[i];
+    }
+    s_stat[t] = md;
+    FramePose fp;
+    pose_from_rvec_tvec(rt, fp);
+    double* o = s_fc + t * kFrameConst;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) o[i] = fp.R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o[9 + i] = fp.t[i];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) o[12 + i] = fp.Jl[i];
+    if constexpr (BATCH) {
+      const double* a = prm.intr_dev + (size_t)prob * C::D;
+      double* si = s_intr + t * kMaxFull;
+      if constexpr (OF) { si[0] = a[0]; si[1] = a[0]; for (int i = 1; i < C::D; ++i) si[i + 1] = a[i]; }
+      else { for (int i = 0; i < C::D; ++i) si[i] = a[i]; }
+    }
+    const int cnt = pb.frame_offsets[f + 1] - pb.frame_offsets[f];
+    atomicMax(&s_misc[0], (cnt + G - 1) / G);
+  }
+  __syncthreads();
+  const int n_iter = s_misc[0];
+  const int warp = t >> 5;
+
+  if (warp >= 4) {
+    // =============================== producers ===============================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 128;\n");
+    const int pt = t - kPcStreams;
+    const int pg = pt / kPcStreams;            // producer group 0/1: even / odd iterations
+    const int sidx = pt - pg * kPcStreams;     // stream
+    const int cw = sidx >> 5;                  // consumer warp served
+    const int fl = sidx / G;
+    const int lane = sidx - fl * G;
+    const bool active = fl < nf;
+    const double* ip = BATCH ? (s_intr + (active ? fl : 0) * kMaxFull) : prm.intr;
+    const double* fc = s_fc + (active ? fl : 0) * kFrameConst;
+    const int f = f0 + (active ? fl : 0);
+    const int beg = pb.frame_offsets[f] + lane;
+    const int end = active ? pb.frame_offsets[f + 1] : beg;  // inactive stream: empty range
+    unsigned long long* full = s_bar;
+    unsigned long long* empty = s_bar + kPcSlots * 4;
+    // software prefetch of the next observation of this stream handled by this group
+    int k = beg + pg * G;
+    double px = 0, py = 0, pz = 0, ou = 0, ov = 0;
+    bool have = k < end;
+    if (have) { px = pb.x[k]; py = pb.y[k]; pz = pb.z[k]; ou = pb.u[k]; ov = pb.v[k]; }
+    for (int it = pg; it < n_iter; it += 2) {
+      const int slot = it % kPcSlots;
+      const unsigned round = (unsigned)(it / kPcSlots);
+      // current observation (already loaded) and prefetch of the next one
+      const double cpx = px, cpy = py, cpz = pz, cou = ou, cov = ov;
+      const bool cur_have = have;
+      k += 2 * G;
+      have = k < end;
+      if (have) { px = pb.x[k]; py = pb.y[k]; pz = pb.z[k]; ou = pb.u[k]; ov = pb.v[k]; }
+      double val[P::NV];
+      if (cur_have) {
+        const double fx = ip[0], fy = OF ? ip[0] : ip[1], cx = ip[2], cy = ip[3];
+        const double qx = fma(fc[0], cpx, fma(fc[1], cpy, fc[2] * cpz));
+        const double qy = fma(fc[3], cpx, fma(fc[4], cpy, fc[5] * cpz));
+        const double qz = fma(fc[6], cpx, fma(fc[7], cpy, fc[8] * cpz));
+        double m[2], dP[2][3], dk[2][kMaxNd];
+        model_eval<MODEL, true>(ip + 4, qx + fc[9], qy + fc[10], qz + fc[11], m, dP, dk);
+        const double ru = fma(fx, m[0], cx) - cou;
+        const double rv = fma(fy, m[1], cy) - cov;
+        const double w = huber_weight(ru * ru + rv * rv, pb.huber_delta);
+        const double wfx = w * fx, wfy = w * fy;
+        val[0] = w * m[0]; val[1] = w * m[1]; val[2] = w;
+#pragma unroll
+        for (int j = 0; j < C::ND; ++j) { val[P::I_DKU + j] = wfx * dk[0][j]; val[P::I_DKV + j] = wfy * dk[1][j]; }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { val[P::I_DU + j] = wfx * dP[0][j]; val[P::I_DV + j] = wfy * dP[1][j]; }
+        val[P::I_Q] = qx; val[P::I_Q + 1] = qy; val[P::I_Q + 2] = qz;
+        val[P::I_R] = w * ru; val[P::I_R + 1] = w * rv;
+      } else {
+#pragma unroll
+        for (int j = 0; j < P::NV; ++j) val[j] = 0.0;   // contributes exact zeros
+      }
+      mbar_wait(empty + slot * 4 + cw, (round & 1u) ^ 1u);
+      double* dst = s_ring + (size_t)slot * P::NV * kPcStreams + sidx;
+#pragma unroll
+      for (int j = 0; j < P::NV; ++j) dst[j * kPcStreams] = val[j];
+      mbar_arrive(full + slot * 4 + cw);
+    }
+  } else {
+    // =============================== consumers ===============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 240;\n");
+    const int sidx = t;
+    const int cw = warp;
+    const int fl = sidx / G;
+    const bool active = fl < nf;
+    const double* fc = s_fc + (active ? fl : 0) * kFrameConst;
+    unsigned long long* full = s_bar;
+    unsigned long long* empty = s_bar + kPcSlots * 4;
+    double acc[C::NACC];
+#pragma unroll
+    for (int i = 0; i < C::NACC; ++i) acc[i] = 0.0;
+    for (int it = 0; it < n_iter; ++it) {
+      const int slot = it % kPcSlots;
+      const unsigned round = (unsigned)(it / kPcSlots);
+      mbar_wait(full + slot * 4 + cw, round & 1u);
+      const double* src = s_ring + (size_t)slot * P::NV * kPcStreams + sidx;
+      double val[P::NV];
+#pragma unroll
+      for (int j = 0; j < P::NV; ++j) val[j] = src[j * kPcStreams];
+      mbar_arrive(empty + slot * 4 + cw);
+      double au[C::NA], av[C::NA];
+      if constexpr (OF) { au[0] = val[0]; av[0] = val[1]; au[1] = val[2]; av[2] = val[2]; }
+      else { au[0] = val[0]; av[1] = val[1]; au[2] = val[2]; av[3] = val[2]; }
+#pragma unroll
+      for (int j = 0; j < C::ND; ++j) { au[C::KOFF + j] = val[P::I_DKU + j]; av[C::KOFF + j] = val[P::I_DKV + j]; }
+      const double qx = val[P::I_Q], qy = val[P::I_Q + 1], qz = val[P::I_Q + 2];
+      const double du0 = val[P::I_DU], du1 = val[P::I_DU + 1], du2 = val[P::I_DU + 2];
+      const double dv0 = val[P::I_DV], dv1 = val[P::I_DV + 1], dv2 = val[P::I_DV + 2];
+      au[C::D + 0] = qy * du2 - qz * du1; au[C::D + 1] = qz * du0 - qx * du2; au[C::D + 2] = qx * du1 - qy * du0;
+      av[C::D + 0] = qy * dv2 - qz * dv1; av[C::D + 1] = qz * dv0 - qx * dv2; av[C::D + 2] = qx * dv1 - qy * dv0;
+      au[C::D + 3] = du0; au[C::D + 4] = du1; au[C::D + 5] = du2;
+      av[C::D + 3] = dv0; av[C::D + 4] = dv1; av[C::D + 5] = dv2;
+      au[C::N] = val[P::I_R]; av[C::N] = val[P::I_R + 1];
+      static_for<0, C::NA>([&](auto I) {
+        static_for<decltype(I)::value, C::NA>([&](auto J) {
+          constexpr int i = decltype(I)::value, j = decltype(J)::value;
+          constexpr int kk = C::kidx(i, j);
+          if constexpr (kk >= 0) {
+            if constexpr (C::hasu(i, j)) acc[kk] = fma(au[i], au[j], acc[kk]);
+            if constexpr (C::hasv(i, j)) acc[kk] = fma(av[i], av[j], acc[kk]);
+          }
+        });
+      });
+    }
+    // basis change phi -> rvec (same as k_linearize)
+    {
+      const double* Jl = fc + 12;
+      static_for<0, C::NA>([&](auto Cc) {
+        constexpr int c = decltype(Cc)::value;
+        if constexpr (c < C::D || c >= C::D + 3) {
+          constexpr int k0 = c < C::D ? C::kidx(c, C::D + 0) : C::kidx(C::D + 0, c);
+          constexpr int k1 = c < C::D ? C::kidx(c, C::D + 1) : C::kidx(C::D + 1, c);
+          constexpr int k2 = c < C::D ? C::kidx(c, C::D + 2) : C::kidx(C::D + 2, c);
+          const double h0 = acc[k0], h1 = acc[k1], h2 = acc[k2];
+          acc[k0] = fma(Jl[0], h0, fma(Jl[3], h1, Jl[6] * h2));
+          acc[k1] = fma(Jl[1], h0, fma(Jl[4], h1, Jl[7] * h2));
+          acc[k2] = fma(Jl[2], h0, fma(Jl[5], h1, Jl[8] * h2));
+        }
+      });
+      constexpr int p = C::D;
+      const double h00 = acc[C::kidx(p, p)], h01 = acc[C::kidx(p, p + 1)], h02 = acc[C::kidx(p, p + 2)];
+      const double h11 = acc[C::kidx(p + 1, p + 1)], h12 = acc[C::kidx(p + 1, p + 2)], h22 = acc[C::kidx(p + 2, p + 2)];
+      double tmp[3][3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        tmp[0][c] = fma(h00, Jl[c], fma(h01, Jl[3 + c], h02 * Jl[6 + c]));
+        tmp[1][c] = fma(h01, Jl[c], fma(h11, Jl[3 + c], h12 * Jl[6 + c]));
+        tmp[2][c] = fma(h02, Jl[c], fma(h12, Jl[3 + c], h22 * Jl[6 + c]));
+      }
+      auto g = [&](int a, int b) { return fma(Jl[a], tmp[0][b], fma(Jl[3 + a], tmp[1][b], Jl[6 + a] * tmp[2][b])); };
+      acc[C::kidx(p, p)] = g(0, 0); acc[C::kidx(p, p + 1)] = g(0, 1); acc[C::kidx(p, p + 2)] = g(0, 2);
+      acc[C::kidx(p + 1, p + 1)] = g(1, 1); acc[C::kidx(p + 1, p + 2)] = g(1, 2); acc[C::kidx(p + 2, p + 2)] = g(2, 2);
+    }
+    // all consumers are past the ring before it is overwritten by the accumulator dump
+    asm volatile("bar.sync 1, 128;\n" ::: "memory");
+    static_for<0, C::NACC>([&](auto E) {
+      constexpr int e = decltype(E)::value;
+      s_ring[e * kPcStreams + sidx] = acc[e];
+    });
+  }
+  __syncthreads();
+
+  // ---- all 384 threads: sum the G slices of each frame in lane order, store SoA; frame cost = (r,r) entry ----
+  for (int o = t; o < C::NACC * nf; o += kPcThreads) {
+    const int e = o / nf, ff = o - e * nf;
+    const double* src = s_ring + e * kPcStreams + ff * G;
+    double s = 0.0;
+    for (int j = 0; j < G; ++j) s += src[j];
+    const int f = f0 + ff;
+    const int prob = BATCH ? pb.frame_problem[f] : 0;
+    double* out = pb.blocks[cur_of(pb, prob) ^ prm.which];
+    out[(size_t)prm.acc_to_blk[e] * pb.Fs + f] = s;
+    if (e == C::NACC - 1) s_stat[FPC + ff] = s;
+  }
+  if constexpr (!BATCH) {
+    __syncthreads();
+    if (t == 0) {
+      double md = 0.0, cost = 0.0;
+      for (int i = 0; i < nf; ++i) { md += s_stat[i]; cost += s_stat[FPC + i]; }
+      prm.cta_part[2 * blockIdx.x] = md;
+      prm.cta_part[2 * blockIdx.x + 1] = cost;
+      __threadfence();
+      s_misc[1] = (atomicAdd(prm.ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_misc[1]) {
+      __threadfence();
+      double* sh = s_ring;   // the accumulator dump has been consumed
+      __syncthreads();
+      if (t < 128) {
+        const int v = t & 1, lane2 = t >> 1;
+        double a = 0.0;
+        for (int b = lane2; b < (int)gridDim.x; b += 64) a += __ldcg(prm.cta_part + 2 * b + v);
+        sh[t] = a;
+      }
+      __syncthreads();
+      for (int w = 64; w >= 2; w >>= 1) {
+        if (t < w) sh[t] += sh[t + w];
+        __syncthreads();
+      }
+      if (t == 0) {
+        prm.stat_dev[0] = sh[0]; prm.stat_dev[1] = sh[1];
+        *prm.ticket = 0u;
+        if (prm.host_stat) { double tmp[3] = {sh[0], sh[1], 0.0}; publish_host(prm.host_stat, tmp, 3, prm.seq); }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1 parity hook: one thread per observation, r and J materialised (HBM-bound: 248 B/obs for EUCM).
 // ------------------------------------------------------------------------------------------------
 template <int MODEL, bool OF>
@@ -745,6 +1059,37 @@ cudaError_t launch_linearize(int model, int one_focal, bool batch, bool cost_onl
     constexpr bool of = decltype(OF)::value;
     if (batch) return cost_only ? launch_lin_t<m, of, true, true>(prm, n_ctas, s) : launch_lin_t<m, of, true, false>(prm, n_ctas, s);
     return cost_only ? launch_lin_t<m, of, false, true>(prm, n_ctas, s) : launch_lin_t<m, of, false, false>(prm, n_ctas, s);
+  });
+}
+
+static size_t pc_smem_bytes(int FPC, bool batch, int NV, int NACC) {
+  size_t d = (size_t)FPC * kFrameConst + (batch ? (size_t)FPC * kMaxFull : 0) + 2 * (size_t)FPC;
+  d += 2 * kPcSlots * 4;  // mbarriers (8 B each)
+  d += 2;                 // s_misc (4 ints)
+  const size_t ring = (size_t)kPcSlots * NV * kPcStreams, dump = (size_t)NACC * kPcStreams;
+  d += ring > dump ? ring : dump;
+  return d * sizeof(double);
+}
+
+template <int MODEL, bool OF, bool BATCH>
+static cudaError_t launch_pc_t(const LinParams& prm, int n_ctas, cudaStream_t s) {
+  auto kern = k_linearize_pc<MODEL, OF, BATCH>;
+  const size_t smem = pc_smem_bytes(prm.FPC, BATCH, PcCfg<MODEL, OF>::NV, Cfg<MODEL, OF>::NACC);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<n_ctas, kPcThreads, smem, s>>>(prm);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_linearize_pc(int model, int one_focal, bool batch, const LinParams& prm, int n_ctas, cudaStream_t s) {
+  return dispatch_model(model, one_focal, [&](auto M, auto OF) {
+    constexpr int m = decltype(M)::value;
+    constexpr bool of = decltype(OF)::value;
+    return batch ? launch_pc_t<m, of, true>(prm, n_ctas, s) : launch_pc_t<m, of, false>(prm, n_ctas, s);
   });
 }
 

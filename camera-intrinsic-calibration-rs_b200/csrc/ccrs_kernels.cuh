@@ -88,6 +88,8 @@ void fill_acc_to_blk(int model, int one_focal, int32_t* table);
 
 cudaError_t launch_linearize(int model, int one_focal, bool batch, bool cost_only, const LinParams& prm, int n_ctas,
                              cudaStream_t s);
+// warp-specialised K2 (384 threads, one CTA per SM); same LinParams, same outputs
+cudaError_t launch_linearize_pc(int model, int one_focal, bool batch, const LinParams& prm, int n_ctas, cudaStream_t s);
 cudaError_t launch_eval_rj(int model, int one_focal, const ProblemDev& pb, const double* intr_dev, const double* poses,
                            int apply_loss, double* r, double* J, int64_t n_obs, cudaStream_t s);
 cudaError_t launch_schur(int D, const SchurParams& prm, cudaStream_t s);
