@@ -20,7 +20,8 @@ SYMBOLS = [
     "ccrs_compute_scale", "ccrs_set_intr_scale", "ccrs_reduce", "ccrs_backsub", "ccrs_eval_cost", "ccrs_accept",
     "ccrs_comm_unique_id", "ccrs_comm_init", "ccrs_comm_finalize", "ccrs_comm_set_deterministic", "ccrs_default_options",
     "ccrs_solve_gn", "ccrs_solve_lm", "ccrs_controller_gn", "ccrs_controller_lm", "ccrs_calib_camera",
-    "ccrs_model_bounds", "ccrs_measure_fp64_peak", "ccrs_time_linearize", "ccrs_bench_lm_steps", "ccrs_launch_count",
+    "ccrs_joint_create", "ccrs_joint_destroy", "ccrs_joint_dim", "ccrs_joint_last_error", "ccrs_joint_launch_count",
+    "ccrs_joint_eval_rj", "ccrs_joint_solve_gn", "ccrs_model_bounds", "ccrs_measure_fp64_peak", "ccrs_time_linearize", "ccrs_bench_lm_steps", "ccrs_launch_count",
 ]
 
 STATUS = {0: "CCRS_OK", -1: "CCRS_ERR_INVALID", -2: "CCRS_ERR_CUDA", -3: "CCRS_ERR_NO_DEVICE",
@@ -112,6 +113,15 @@ def load():
     lib.ccrs_calib_camera.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp,
                                       C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Options), C.POINTER(Summary), C.c_int]
     lib.ccrs_model_bounds.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp]
+    lib.ccrs_joint_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip,
+                                      _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_int]
+    lib.ccrs_joint_destroy.argtypes = [vp]
+    lib.ccrs_joint_dim.argtypes = [vp]
+    lib.ccrs_joint_last_error.restype = C.c_char_p
+    lib.ccrs_joint_launch_count.argtypes = [vp]
+    lib.ccrs_joint_launch_count.restype = C.c_int64
+    lib.ccrs_joint_eval_rj.argtypes = [vp, _dp, _dp, _dp, C.c_int, _dp, _dp]
+    lib.ccrs_joint_solve_gn.argtypes = [vp, _dp, _dp, _dp, _dp, _dp, _up, C.POINTER(Options), C.POINTER(Summary), _dp]
     lib.ccrs_measure_fp64_peak.argtypes = [C.c_int, _dp]
     lib.ccrs_time_linearize.argtypes = [vp, _dp, C.c_int, C.c_int, _dp]
     lib.ccrs_bench_lm_steps.argtypes = [vp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.POINTER(C.c_int64)]

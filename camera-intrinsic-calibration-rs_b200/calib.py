@@ -302,3 +302,125 @@ def calib_camera(frame_feature_list: Sequence[Optional[FrameFeature]], generic_c
     cam = GenericModel(generic_camera.model, params, generic_camera.width, generic_camera.height)
     rt = {i: RvecTvec(tuple(poses[k, :3]), tuple(poses[k, 3:])) for k, i in enumerate(valid)}
     return cam, rt
+
+
+class JointProblem:
+    """Device-resident joint multi-camera problem (calib_all_camera_with_extrinsics, src/util.rs:567-715)."""
+
+    def __init__(self, model, n_cams: int, n_frames: int, block_cam, block_frame, block_offsets, x, y, z, u, v,
+                 xy_same_focal: bool = False, huber_delta: float = 1.0, device: int = 0):
+        self.lib = _abi.load()
+        self.model = MODELS[model] if isinstance(model, str) else int(model)
+        bc = np.ascontiguousarray(block_cam, dtype=np.int32)
+        bf = np.ascontiguousarray(block_frame, dtype=np.int32)
+        bo = np.ascontiguousarray(block_offsets, dtype=np.int32)
+        xs, ys, zs, us, vs = map(_f64, (x, y, z, u, v))
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        self.h = C.c_void_p()
+        code = self.lib.ccrs_joint_create(C.byref(self.h), self.model, int(xy_same_focal), int(n_cams), int(n_frames), len(bc),
+                                          ip(bc), ip(bf), ip(bo), _dp(xs), _dp(ys), _dp(zs), _dp(us), _dp(vs),
+                                          float(huber_delta), int(device))
+        self._check(code)
+        self.n_cams, self.n_frames, self.n_obs = int(n_cams), int(n_frames), int(bo[-1])
+        self.d = self.lib.ccrs_joint_dim(self.h)
+
+    def _check(self, code):
+        if code != 0:
+            raise CcrsError(code, self.lib.ccrs_joint_last_error().decode("utf-8", "replace"))
+
+    @classmethod
+    def from_rig(cls, rig, **kw):
+        return cls(rig.model, rig.n_cams, rig.n_frames, rig.block_cam, rig.block_frame, rig.block_offsets,
+                   rig.x, rig.y, rig.z, rig.u, rig.v, **kw)
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.ccrs_joint_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def eval_rj(self, intr, extr, poses, apply_loss=True):
+        intr, extr, poses = _f64(intr).reshape(-1), _f64(extr).reshape(-1), _f64(poses).reshape(-1)
+        r = np.empty(2 * self.n_obs); J = np.empty((2 * self.n_obs, self.d + 12))
+        self._check(self.lib.ccrs_joint_eval_rj(self.h, _dp(intr), _dp(extr), _dp(poses), int(apply_loss), _dp(r), _dp(J)))
+        return r, J
+
+    def solve_gn(self, intr, extr, poses, lo=None, hi=None, fixed=None, options: Optional[Options] = None):
+        a = _f64(intr).reshape(-1).copy(); e = _f64(extr).reshape(-1).copy(); p = _f64(poses).reshape(-1).copy()
+        o = options or default_options()
+        s = Summary(); hist = np.full(max(o.max_iteration, 1), np.nan)
+        lo_a = _f64(lo).reshape(-1) if lo is not None else None
+        hi_a = _f64(hi).reshape(-1) if hi is not None else None
+        fx = np.ascontiguousarray(fixed, dtype=np.uint8).reshape(-1) if fixed is not None else None
+        code = self.lib.ccrs_joint_solve_gn(self.h, _dp(a), _dp(e), _dp(p), _dp(lo_a), _dp(hi_a), _up(fx), C.byref(o), C.byref(s), _dp(hist))
+        if code not in (0, -4, -5):
+            self._check(code)
+        return a.reshape(self.n_cams, self.d), e.reshape(-1, 6), p.reshape(-1, 6), s, hist[: s.iterations]
+
+
+def calib_all_camera_with_extrinsics(cameras: Sequence[GenericModel], t_cam_i_0: Sequence[RvecTvec],
+                                     cam_rtvecs: Sequence[Dict[int, RvecTvec]],
+                                     cams_detected_feature_frames: Sequence[Sequence[Optional[FrameFeature]]],
+                                     xy_same_focal: bool, disabled_distortions: int, cam0_fixed_focal: bool,
+                                     options: Optional[Options] = None, device: int = 0):
+    """Mirror of calib_all_camera_with_extrinsics (src/util.rs:567-715).
+    Returns (intrinsics, t_i_0 list, {frame_idx: board RvecTvec}) or None where the reference returns None."""
+    n_cams = len(cameras)
+    model = cameras[0].model
+    nfull = len(cameras[0].params)
+    shift = 1 if xy_same_focal else 0
+    d = nfull - shift
+    frame_ids = sorted({f for c in range(n_cams) for f in cam_rtvecs[c]})      # valid_frame_board_to_cam0
+    fidx = {f: i for i, f in enumerate(frame_ids)}
+    bc, bf, offs, xs, ys, zs, us, vs = [], [], [0], [], [], [], [], []
+    poses = np.zeros((len(frame_ids), 6)); have_pose = np.zeros(len(frame_ids), dtype=bool)
+
+    def iso(rt):
+        from .synth import rodrigues
+        return rodrigues(np.asarray(rt.rvec)), np.asarray(rt.tvec, dtype=np.float64)
+
+    for c in range(n_cams):
+        for f, rt in cam_rtvecs[c].items():
+            ff = cams_detected_feature_frames[c][f]
+            bc.append(c); bf.append(fidx[f])
+            for fp in ff.features.values():
+                p3 = np.asarray(fp.p3d, dtype=np.float32).astype(np.float64); p2 = np.asarray(fp.p2d, dtype=np.float32).astype(np.float64)
+                xs.append(p3[0]); ys.append(p3[1]); zs.append(p3[2]); us.append(p2[0]); vs.append(p2[1])
+            offs.append(len(xs))
+            if not have_pose[fidx[f]]:                     # entry().or_insert: first camera that saw the frame wins
+                if c == 0:
+                    poses[fidx[f]] = rt.as_array()
+                else:                                      # 0 <- i <- board (util.rs:640-650): T_c_0^-1 * T_c_b
+                    import cv2
+                    Rc, tc = iso(t_cam_i_0[c]); Rb, tb = iso(rt)
+                    R = Rc.T @ Rb; t = Rc.T @ (tb - tc)
+                    poses[fidx[f]] = np.concatenate([cv2.Rodrigues(R)[0].ravel(), t])
+                have_pose[fidx[f]] = True
+    intr = np.zeros((n_cams, d)); lo = np.zeros((n_cams, d)); hi = np.zeros((n_cams, d)); fixed = np.zeros((n_cams, d), dtype=np.uint8)
+    keep = [i for i in range(nfull) if not (xy_same_focal and i == 1)]
+    for c, cam in enumerate(cameras):
+        flo, fhi = model_bounds(cam.model, cam.width, cam.height)
+        intr[c] = _f64(cam.params)[keep]; lo[c] = flo[keep]; hi[c] = fhi[keep]
+        for i in range(disabled_distortions):              # set_problem_parameter_disabled (util.rs:50-71)
+            idx = nfull - 1 - shift - i
+            fixed[c, idx] = 1; intr[c, idx] = 0.0
+    if cam0_fixed_focal:
+        fixed[0, 0] = 1                                    # problem.fix_variable("params0", 0) (util.rs:664-667)
+    extr = np.stack([t.as_array() for t in t_cam_i_0])
+    jp = JointProblem(model, n_cams, len(frame_ids), bc, bf, offs, xs, ys, zs, us, vs, xy_same_focal=xy_same_focal, device=device)
+    a, e, p, s, _ = jp.solve_gn(intr, extr, poses, lo, hi, fixed, options)
+    jp.close()
+    if s.status in (-4, -5):
+        return None
+    out_cams = []
+    for c, cam in enumerate(cameras):
+        full = np.insert(a[c], 1, a[c][0]) if xy_same_focal else a[c].copy()
+        out_cams.append(GenericModel(cam.model, full, cam.width, cam.height))
+    t_i_0 = [RvecTvec((0.0, 0.0, 0.0), (0.0, 0.0, 0.0))] + [RvecTvec(tuple(e[c, :3]), tuple(e[c, 3:])) for c in range(1, n_cams)]
+    board = {f: RvecTvec(tuple(p[i, :3]), tuple(p[i, 3:])) for f, i in fidx.items()}
+    return out_cams, t_i_0, board

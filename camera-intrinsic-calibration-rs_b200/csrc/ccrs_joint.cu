@@ -1,0 +1,537 @@
+// ccrs_joint.cu — joint multi-camera refinement: calib_all_camera_with_extrinsics (reference src/util.rs:567-715).
+//
+// Variables: params{c} (d per camera), T_c_0 = (rvec_{c}_0, tvec_{c}_0) for c > 0, T_0_b_f = (rvec_0_b_{f}, tvec_0_b_{f})
+// per frame. cam0 corners are ReprojectionFactor blocks (util.rs:603-611), the other cameras' corners are
+// OtherCamReprojectionFactor blocks with five parameter blocks (util.rs:612-631; factors.rs:204-228):
+//     r = project(theta_c ; T_c_0 * T_0_b_f * p) - p2d.
+// The per-frame board pose T_0_b_f is eliminated (6x6 Cholesky per frame, summing the blocks of every camera that saw
+// the frame) onto the shared system [theta_0 .. theta_{C-1} | T_1_0 .. T_{C-1}_0]; the host solves that small dense
+// system, exactly like the single-camera path. The reference runs Gauss-Newton here (util.rs:668-670).
+// This problem is small (BASELINE config 5: 2 cameras x 200 frames), so the kernels favour simplicity: one warp per
+// (camera, frame) block with the rows of [J | r] staged in shared memory.
+#include "../../include/ccrs_b200.h"
+#include "ccrs_device.cuh"
+#include "ccrs_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <type_traits>
+#include <vector>
+
+using namespace ccrs;
+
+namespace {
+
+thread_local char g_jerr[512] = "";
+int jfail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_jerr, sizeof(g_jerr), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define JCK(call)                                                                                        \
+  do {                                                                                                   \
+    cudaError_t _e = (call);                                                                             \
+    if (_e != cudaSuccess) return jfail(CCRS_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+constexpr int kMaxShared = 64;   // max size of the shared (intrinsics + extrinsics) system
+constexpr int kJWarps = 4;       // warps (= blocks of the problem) per CTA in k_joint_linearize
+
+struct JointDev {
+  const double *x, *y, *z, *u, *v;
+  const int32_t *block_cam, *block_frame, *block_offsets, *obs_block;
+  const int32_t *frame_block_offsets, *frame_blocks;   // CSR frame -> blocks
+  const double* intr;    // [C][d]
+  const double* extr;    // [C][6]
+  double* poses;         // [F][6]
+  int n_cams, n_frames, n_blocks, d;
+  double huber_delta;
+};
+
+template <int MODEL, bool OF>
+struct JCfg {
+  static constexpr int ND = model_nd(MODEL);
+  static constexpr int D = 4 + ND - (OF ? 1 : 0);
+  static constexpr int N = D + 12;     // [theta | w0 t0 | wc tc]
+  static constexpr int NA = N + 1;     // + r
+  static constexpr int NB = NA * (NA + 1) / 2;
+  static constexpr int KOFF = OF ? 3 : 4;
+};
+
+// rows of [J | r] (rvec basis, Huber-corrected) for one observation of a block of camera c
+template <int MODEL, bool OF>
+CCRS_D void joint_rows(const double* __restrict__ ip, const FramePose& f0, const FramePose& fc, bool other,
+                       double px, double py, double pz, double ou, double ov, double delta,
+                       double* __restrict__ au, double* __restrict__ av) {
+  using C = JCfg<MODEL, OF>;
+  const double fx = ip[0], fy = OF ? ip[0] : ip[1], cx = ip[2], cy = ip[3];
+  const double q0x = f0.R[0] * px + f0.R[1] * py + f0.R[2] * pz;
+  const double q0y = f0.R[3] * px + f0.R[4] * py + f0.R[5] * pz;
+  const double q0z = f0.R[6] * px + f0.R[7] * py + f0.R[8] * pz;
+  const double P0x = q0x + f0.t[0], P0y = q0y + f0.t[1], P0z = q0z + f0.t[2];
+  double qcx = 0, qcy = 0, qcz = 0, X = P0x, Y = P0y, Z = P0z;
+  if (other) {   // T_c_0 * (T_0_b * p)
+    qcx = fc.R[0] * P0x + fc.R[1] * P0y + fc.R[2] * P0z;
+    qcy = fc.R[3] * P0x + fc.R[4] * P0y + fc.R[5] * P0z;
+    qcz = fc.R[6] * P0x + fc.R[7] * P0y + fc.R[8] * P0z;
+    X = qcx + fc.t[0]; Y = qcy + fc.t[1]; Z = qcz + fc.t[2];
+  }
+  double m[2], dP[2][3], dk[2][kMaxNd];
+  model_eval<MODEL, true>(ip + 4, X, Y, Z, m, dP, dk);
+  const double ru = fma(fx, m[0], cx) - ou, rv = fma(fy, m[1], cy) - ov;
+  const double w = huber_weight(ru * ru + rv * rv, delta);
+#pragma unroll
+  for (int i = 0; i < C::NA; ++i) { au[i] = 0.0; av[i] = 0.0; }
+  if constexpr (OF) { au[0] = w * m[0]; av[0] = w * m[1]; au[1] = w; av[2] = w; }
+  else { au[0] = w * m[0]; av[1] = w * m[1]; au[2] = w; av[3] = w; }
+  const double wf[2] = {w * fx, w * fy};
+#pragma unroll
+  for (int j = 0; j < C::ND; ++j) { au[C::KOFF + j] = wf[0] * dk[0][j]; av[C::KOFF + j] = wf[1] * dk[1][j]; }
+#pragma unroll
+  for (int row = 0; row < 2; ++row) {
+    double* a = row ? av : au;
+    const double d0 = wf[row] * dP[row][0], d1 = wf[row] * dP[row][1], d2 = wf[row] * dP[row][2];
+    double e0 = d0, e1 = d1, e2 = d2;   // derivative w.r.t. P_0 (cam0 frame)
+    if (other) {
+      // T_c_0 columns: tvec -> d ; rvec -> (q_c x d)^T J_l(w_c)
+      const double c0 = qcy * d2 - qcz * d1, c1 = qcz * d0 - qcx * d2, c2 = qcx * d1 - qcy * d0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) a[C::D + 6 + k] = c0 * fc.Jl[k] + c1 * fc.Jl[3 + k] + c2 * fc.Jl[6 + k];
+      a[C::D + 9] = d0; a[C::D + 10] = d1; a[C::D + 11] = d2;
+      e0 = fc.R[0] * d0 + fc.R[3] * d1 + fc.R[6] * d2;   // R_c^T d
+      e1 = fc.R[1] * d0 + fc.R[4] * d1 + fc.R[7] * d2;
+      e2 = fc.R[2] * d0 + fc.R[5] * d1 + fc.R[8] * d2;
+    }
+    const double c0 = q0y * e2 - q0z * e1, c1 = q0z * e0 - q0x * e2, c2 = q0x * e1 - q0y * e0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) a[C::D + k] = c0 * f0.Jl[k] + c1 * f0.Jl[3 + k] + c2 * f0.Jl[6 + k];
+    a[C::D + 3] = e0; a[C::D + 4] = e1; a[C::D + 5] = e2;
+  }
+  au[C::N] = w * ru; av[C::N] = w * rv;
+}
+
+template <int MODEL, bool OF>
+CCRS_D void load_full_intr(const double* a, double* ip) {
+  using C = JCfg<MODEL, OF>;
+  if constexpr (OF) { ip[0] = a[0]; ip[1] = a[0]; for (int i = 1; i < C::D; ++i) ip[i + 1] = a[i]; }
+  else { for (int i = 0; i < C::D; ++i) ip[i] = a[i]; }
+}
+
+// parity hook for a3: per observation r and J (2 x (d+12))
+template <int MODEL, bool OF>
+__global__ void __launch_bounds__(128) k_joint_eval_rj(JointDev jd, int apply_loss, double* __restrict__ r,
+                                                       double* __restrict__ J, int n_obs) {
+  using C = JCfg<MODEL, OF>;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_obs) return;
+  const int b = jd.obs_block[k], c = jd.block_cam[b], f = jd.block_frame[b];
+  double ip[kMaxFull];
+  load_full_intr<MODEL, OF>(jd.intr + (size_t)c * C::D, ip);
+  FramePose f0, fc;
+  pose_from_rvec_tvec(jd.poses + 6 * (size_t)f, f0);
+  pose_from_rvec_tvec(jd.extr + 6 * (size_t)c, fc);
+  double au[C::NA], av[C::NA];
+  joint_rows<MODEL, OF>(ip, f0, fc, c > 0, jd.x[k], jd.y[k], jd.z[k], jd.u[k], jd.v[k], apply_loss ? jd.huber_delta : 0.0, au, av);
+  r[2 * (size_t)k] = au[C::N]; r[2 * (size_t)k + 1] = av[C::N];
+  if (J) for (int i = 0; i < C::N; ++i) { J[(size_t)(2 * k) * C::N + i] = au[i]; J[(size_t)(2 * k + 1) * C::N + i] = av[i]; }
+}
+
+// one warp per (camera, frame) block: packed Gram block [J r]^T [J r] of size NB, deterministic (fixed lane order)
+template <int MODEL, bool OF>
+__global__ void __launch_bounds__(32 * kJWarps) k_joint_linearize(JointDev jd, const uint16_t* __restrict__ ij_table,
+                                                                  double* __restrict__ jblk) {
+  using C = JCfg<MODEL, OF>;
+  __shared__ double rows[kJWarps][32][2 * C::NA];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kJWarps + warp;
+  if (b >= jd.n_blocks) return;
+  const int c = jd.block_cam[b], f = jd.block_frame[b];
+  double ip[kMaxFull];
+  load_full_intr<MODEL, OF>(jd.intr + (size_t)c * C::D, ip);
+  FramePose f0, fc;
+  pose_from_rvec_tvec(jd.poses + 6 * (size_t)f, f0);
+  pose_from_rvec_tvec(jd.extr + 6 * (size_t)c, fc);
+  constexpr int EPL = (C::NB + 31) / 32;   // entries per lane
+  double acc[EPL];
+  int ei[EPL], ej[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    acc[e] = 0.0;
+    const int idx = lane + 32 * e;
+    const uint16_t t = idx < C::NB ? ij_table[idx] : 0;
+    ei[e] = t >> 8; ej[e] = t & 0xff;
+  }
+  const int beg = jd.block_offsets[b], end = jd.block_offsets[b + 1];
+  for (int base = beg; base < end; base += 32) {
+    const int k = base + lane;
+    double* my = rows[warp][lane];
+    if (k < end) {
+      double au[C::NA], av[C::NA];
+      joint_rows<MODEL, OF>(ip, f0, fc, c > 0, jd.x[k], jd.y[k], jd.z[k], jd.u[k], jd.v[k], jd.huber_delta, au, av);
+#pragma unroll
+      for (int i = 0; i < C::NA; ++i) { my[i] = au[i]; my[C::NA + i] = av[i]; }
+    }
+    __syncwarp();
+    const int cnt = min(32, end - base);
+    for (int l = 0; l < cnt; ++l) {
+      const double* rw = rows[warp][l];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e)
+        acc[e] = fma(rw[ei[e]], rw[ej[e]], fma(rw[C::NA + ei[e]], rw[C::NA + ej[e]], acc[e]));
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const int idx = lane + 32 * e;
+    if (idx < C::NB) jblk[(size_t)b * C::NB + idx] = acc[e];
+  }
+}
+
+// per frame: gather the blocks of every camera, eliminate T_0_b_f. Output per frame:
+// fs[f][NS + M + 1] = packed upper S_f (shared x shared), g_s (M), sum r^2 ; el[f][6*M + 6] = X (6 x M), C^-1 g_p
+__global__ void __launch_bounds__(64) k_joint_schur(JointDev jd, const double* __restrict__ jblk, int NAJ, int M,
+                                                    double u_damp, double* __restrict__ fs, double* __restrict__ el) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= jd.n_frames) return;
+  const int d = jd.d, C = jd.n_cams, NBJ = NAJ * (NAJ + 1) / 2, NS = M * (M + 1) / 2, n = d + 12;
+  const int off_e = C * d;
+  double* S = fs + (size_t)f * (NS + M + 1);
+  double* gs = S + NS;
+  for (int i = 0; i < NS + M + 1; ++i) S[i] = 0.0;
+  double B[kMaxShared][6];
+  for (int i = 0; i < M; ++i) for (int x = 0; x < 6; ++x) B[i][x] = 0.0;
+  double L[6][6], gp[6];
+  for (int i = 0; i < 6; ++i) { gp[i] = 0.0; for (int j = 0; j < 6; ++j) L[i][j] = 0.0; }
+  double sq = 0.0;
+  auto sidx = [&](int i, int j) { return i <= j ? tri_idx(M, i, j) : tri_idx(M, j, i); };
+  for (int q = jd.frame_block_offsets[f]; q < jd.frame_block_offsets[f + 1]; ++q) {
+    const int b = jd.frame_blocks[q], c = jd.block_cam[b];
+    const double* Hb = jblk + (size_t)b * NBJ;
+    auto H = [&](int i, int j) { return i <= j ? Hb[tri_idx(NAJ, i, j)] : Hb[tri_idx(NAJ, j, i)]; };
+    // shared index of block column i (theta: 0..d-1 ; extrinsic: d+6..d+11), -1 if not a shared column
+    auto sh = [&](int i) { return i < d ? c * d + i : (i >= d + 6 && i < n && c > 0 ? off_e + 6 * (c - 1) + (i - d - 6) : -1); };
+    for (int i = 0; i < n; ++i) {
+      const int si = sh(i);
+      if (si < 0) continue;
+      for (int j = i; j < n; ++j) { const int sj = sh(j); if (sj >= 0) S[sidx(si, sj)] += H(i, j); }
+      for (int x = 0; x < 6; ++x) B[si][x] += H(i, d + x);
+      gs[si] -= H(i, n);
+    }
+    for (int i = 0; i < 6; ++i) { for (int j = 0; j <= i; ++j) L[i][j] += H(d + j, d + i); gp[i] -= H(d + i, n); }
+    sq += H(n, n);
+  }
+  gs[M] = sq;
+  int bad = 0;
+  for (int i = 0; i < 6; ++i) L[i][i] += u_damp * L[i][i];
+  for (int j = 0; j < 6; ++j) {
+    double s = L[j][j];
+    for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+    if (!(s > 0.0)) bad = 1;
+    const double il = 1.0 / sqrt(s);
+    L[j][j] = il;
+    for (int i = j + 1; i < 6; ++i) {
+      double t = L[i][j];
+      for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k];
+      L[i][j] = t * il;
+    }
+  }
+  double yg[6];
+  for (int i = 0; i < 6; ++i) { double s = gp[i]; for (int k = 0; k < i; ++k) s -= L[i][k] * yg[k]; yg[i] = s * L[i][i]; }
+  for (int a = 0; a < M; ++a) {   // Y[a] = L^-1 B[a]
+    for (int i = 0; i < 6; ++i) { double s = B[a][i]; for (int k = 0; k < i; ++k) s -= L[i][k] * B[a][k]; B[a][i] = s * L[i][i]; }
+  }
+  for (int a = 0; a < M; ++a) {
+    for (int b2 = a; b2 < M; ++b2) {
+      double s = 0.0;
+      for (int i = 0; i < 6; ++i) s += B[a][i] * B[b2][i];
+      S[tri_idx(M, a, b2)] -= s;
+    }
+    double s = 0.0;
+    for (int i = 0; i < 6; ++i) s += B[a][i] * yg[i];
+    gs[a] -= s;
+  }
+  double* e = el + (size_t)f * (6 * M + 6);
+  for (int a = 0; a < M; ++a) {   // X = L^-T Y
+    for (int i = 5; i >= 0; --i) { double s = B[a][i]; for (int k = i + 1; k < 6; ++k) s -= L[k][i] * B[a][k]; B[a][i] = s * L[i][i]; e[i * M + a] = B[a][i]; }
+  }
+  for (int i = 5; i >= 0; --i) { double s = yg[i]; for (int k = i + 1; k < 6; ++k) s -= L[k][i] * yg[k]; yg[i] = s * L[i][i]; e[6 * M + i] = yg[i]; }
+  if (bad) for (int i = 0; i < NS + M; ++i) S[i] = nan("");   // poison S and g_s (not the cost): host reports the LLT failure
+}
+
+// out[v] = sum_f fs[f][v], f ascending (fixed order)
+__global__ void k_joint_sum(const double* __restrict__ fs, int F, int NV, double* __restrict__ out) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= NV) return;
+  double s = 0.0;
+  for (int f = 0; f < F; ++f) s += fs[(size_t)f * NV + v];
+  out[v] = s;
+}
+
+__global__ void k_joint_backsub(JointDev jd, const double* __restrict__ el, const double* __restrict__ y, int M) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= jd.n_frames) return;
+  const double* e = el + (size_t)f * (6 * M + 6);
+  for (int i = 0; i < 6; ++i) {
+    double s = e[6 * M + i];
+    for (int a = 0; a < M; ++a) s -= e[i * M + a] * y[a];
+    jd.poses[6 * (size_t)f + i] += s;
+  }
+}
+
+template <class F>
+auto jdispatch(int model, int of, F&& f) {
+#define JCASE(M) case M: return of ? f(std::integral_constant<int, M>{}, std::true_type{}) : f(std::integral_constant<int, M>{}, std::false_type{});
+  switch (model) { JCASE(UCM) JCASE(EUCM) JCASE(EUCMT) JCASE(KB4) JCASE(OPENCV5) JCASE(FTHETA) }
+#undef JCASE
+  return f(std::integral_constant<int, EUCM>{}, std::false_type{});
+}
+
+bool chol_solve_dense(std::vector<double>& A, int n, double* b) {
+  for (int j = 0; j < n; ++j) {
+    double s = A[j * n + j];
+    for (int k = 0; k < j; ++k) s -= A[j * n + k] * A[j * n + k];
+    if (!(s > 0.0)) return false;
+    const double l = std::sqrt(s);
+    A[j * n + j] = l;
+    for (int i = j + 1; i < n; ++i) { double t = A[i * n + j]; for (int k = 0; k < j; ++k) t -= A[i * n + k] * A[j * n + k]; A[i * n + j] = t / l; }
+  }
+  for (int i = 0; i < n; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= A[i * n + k] * b[k]; b[i] = s / A[i * n + i]; }
+  for (int i = n - 1; i >= 0; --i) { double s = b[i]; for (int k = i + 1; k < n; ++k) s -= A[k * n + i] * b[k]; b[i] = s / A[i * n + i]; }
+  return true;
+}
+
+}  // namespace
+
+struct ccrs_joint {
+  int model = 0, one_focal = 0, d = 0, NAJ = 0, NBJ = 0, M = 0, NS = 0;
+  int n_cams = 0, n_frames = 0, n_blocks = 0, n_obs = 0, device = 0;
+  double huber = 1.0;
+  cudaStream_t stream = nullptr;
+  std::vector<void*> allocs;
+  double *x = nullptr, *y = nullptr, *z = nullptr, *u = nullptr, *v = nullptr;
+  int32_t *block_cam = nullptr, *block_frame = nullptr, *block_offsets = nullptr, *obs_block = nullptr;
+  int32_t *frame_block_offsets = nullptr, *frame_blocks = nullptr;
+  uint16_t* ij_table = nullptr;
+  double *intr = nullptr, *extr = nullptr, *poses = nullptr, *jblk = nullptr, *fs = nullptr, *el = nullptr, *red = nullptr, *ydev = nullptr;
+  int64_t launches = 0;
+
+  template <class T> cudaError_t alloc(T** p, size_t n) {
+    cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) allocs.push_back(*p);
+    return e;
+  }
+  JointDev dev() const {
+    JointDev j{};
+    j.x = x; j.y = y; j.z = z; j.u = u; j.v = v;
+    j.block_cam = block_cam; j.block_frame = block_frame; j.block_offsets = block_offsets; j.obs_block = obs_block;
+    j.frame_block_offsets = frame_block_offsets; j.frame_blocks = frame_blocks;
+    j.intr = intr; j.extr = extr; j.poses = poses;
+    j.n_cams = n_cams; j.n_frames = n_frames; j.n_blocks = n_blocks; j.d = d; j.huber_delta = huber;
+    return j;
+  }
+};
+
+namespace {
+int upload_state(ccrs_joint* p, const double* intr, const double* extr, const double* poses) {
+  JCK(cudaMemcpyAsync(p->intr, intr, (size_t)p->n_cams * p->d * 8, cudaMemcpyHostToDevice, p->stream));
+  std::vector<double> e(extr, extr + (size_t)p->n_cams * 6);
+  for (int i = 0; i < 6; ++i) e[i] = 0.0;   // cam0 is the reference frame (util.rs:689-690)
+  JCK(cudaMemcpyAsync(p->extr, e.data(), e.size() * 8, cudaMemcpyHostToDevice, p->stream));
+  if (poses) JCK(cudaMemcpyAsync(p->poses, poses, (size_t)p->n_frames * 48, cudaMemcpyHostToDevice, p->stream));
+  JCK(cudaStreamSynchronize(p->stream));
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int ccrs_joint_create(ccrs_joint** out, int model, int xy_same_focal, int n_cams, int n_frames, int n_blocks,
+                      const int32_t* block_cam, const int32_t* block_frame, const int32_t* block_offsets,
+                      const double* x, const double* y, const double* z, const double* u, const double* v,
+                      double huber_delta, int device_id) {
+  if (!out || !block_cam || !block_frame || !block_offsets || !x || !y || !z || !u || !v || n_cams < 1 || n_frames < 1 || n_blocks < 1)
+    return jfail(CCRS_ERR_INVALID, "null pointer or empty joint problem");
+  if (model < 0 || model > 5) return jfail(CCRS_ERR_INVALID, "unknown model %d", model);
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { cudaGetLastError(); return jfail(CCRS_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path"); }
+  if (device_id < 0 || device_id >= n_dev) return jfail(CCRS_ERR_INVALID, "device out of range");
+  int major = 0;
+  JCK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device_id));
+  if (major != 10) return jfail(CCRS_ERR_NO_DEVICE, "kernels are built for sm_100a only");
+  JCK(cudaSetDevice(device_id));
+  ccrs_joint* p = new ccrs_joint();
+  p->model = model; p->one_focal = xy_same_focal ? 1 : 0; p->n_cams = n_cams; p->n_frames = n_frames; p->n_blocks = n_blocks;
+  p->device = device_id; p->huber = huber_delta;
+  model_dims(model, p->one_focal, &p->d, nullptr, nullptr, nullptr);
+  p->NAJ = p->d + 13; p->NBJ = p->NAJ * (p->NAJ + 1) / 2;
+  p->M = n_cams * p->d + 6 * (n_cams - 1); p->NS = p->M * (p->M + 1) / 2;
+  if (p->M > kMaxShared) { delete p; return jfail(CCRS_ERR_INVALID, "shared system of %d unknowns exceeds %d", p->M, kMaxShared); }
+  for (int b = 0; b < n_blocks; ++b)
+    if (block_cam[b] < 0 || block_cam[b] >= n_cams || block_frame[b] < 0 || block_frame[b] >= n_frames || block_offsets[b + 1] < block_offsets[b]) {
+      delete p; return jfail(CCRS_ERR_INVALID, "bad block %d", b);
+    }
+  p->n_obs = block_offsets[n_blocks];
+  const size_t N = p->n_obs;
+  cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete p; return jfail(CCRS_ERR_CUDA, "stream"); }
+  // host-side index structures
+  std::vector<int32_t> obs_block(N), fbo(n_frames + 1, 0), fb(n_blocks);
+  for (int b = 0; b < n_blocks; ++b) for (int k = block_offsets[b]; k < block_offsets[b + 1]; ++k) obs_block[k] = b;
+  for (int b = 0; b < n_blocks; ++b) fbo[block_frame[b] + 1]++;
+  for (int f = 0; f < n_frames; ++f) fbo[f + 1] += fbo[f];
+  { std::vector<int32_t> cur(fbo.begin(), fbo.end() - 1); for (int b = 0; b < n_blocks; ++b) fb[cur[block_frame[b]]++] = b; }   // ascending block id per frame
+  std::vector<uint16_t> ij(p->NBJ);
+  { int k = 0; for (int i = 0; i < p->NAJ; ++i) for (int j = i; j < p->NAJ; ++j) ij[k++] = (uint16_t)((i << 8) | j); }
+#define JA(ptr, n) do { cudaError_t _e = p->alloc(&p->ptr, n); if (_e != cudaSuccess) { ccrs_joint_destroy(p); return jfail(CCRS_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(_e)); } } while (0)
+  JA(x, N); JA(y, N); JA(z, N); JA(u, N); JA(v, N);
+  JA(block_cam, n_blocks); JA(block_frame, n_blocks); JA(block_offsets, n_blocks + 1); JA(obs_block, N);
+  JA(frame_block_offsets, n_frames + 1); JA(frame_blocks, n_blocks); JA(ij_table, p->NBJ);
+  JA(intr, (size_t)n_cams * p->d); JA(extr, (size_t)n_cams * 6); JA(poses, (size_t)n_frames * 6);
+  JA(jblk, (size_t)n_blocks * p->NBJ); JA(fs, (size_t)n_frames * (p->NS + p->M + 1)); JA(el, (size_t)n_frames * (6 * p->M + 6));
+  JA(red, p->NS + p->M + 1); JA(ydev, p->M);
+#undef JA
+  cudaStream_t s = p->stream;
+  cudaMemcpyAsync(p->x, x, N * 8, cudaMemcpyHostToDevice, s); cudaMemcpyAsync(p->y, y, N * 8, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(p->z, z, N * 8, cudaMemcpyHostToDevice, s); cudaMemcpyAsync(p->u, u, N * 8, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(p->v, v, N * 8, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(p->block_cam, block_cam, n_blocks * 4, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(p->block_frame, block_frame, n_blocks * 4, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(p->block_offsets, block_offsets, (n_blocks + 1) * 4, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(p->obs_block, obs_block.data(), N * 4, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(p->frame_block_offsets, fbo.data(), (n_frames + 1) * 4, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(p->frame_blocks, fb.data(), n_blocks * 4, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(p->ij_table, ij.data(), p->NBJ * 2, cudaMemcpyHostToDevice, s);
+  e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) { ccrs_joint_destroy(p); return jfail(CCRS_ERR_CUDA, "upload: %s", cudaGetErrorString(e)); }
+  *out = p;
+  return 0;
+}
+
+int ccrs_joint_destroy(ccrs_joint* p) {
+  if (!p) return 0;
+  cudaSetDevice(p->device);
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  for (void* a : p->allocs) cudaFree(a);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+  return 0;
+}
+
+int ccrs_joint_dim(const ccrs_joint* p) { return p ? p->d : -1; }
+const char* ccrs_joint_last_error(void) { return g_jerr; }
+int64_t ccrs_joint_launch_count(const ccrs_joint* p) { return p ? p->launches : -1; }
+
+int ccrs_joint_eval_rj(ccrs_joint* p, const double* intr, const double* extr, const double* poses, int apply_loss,
+                       double* r, double* J) {
+  if (!p || !intr || !extr || !poses || !r) return jfail(CCRS_ERR_INVALID, "null");
+  JCK(cudaSetDevice(p->device));
+  int st = upload_state(p, intr, extr, poses);
+  if (st) return st;
+  const size_t N = p->n_obs;
+  const int n = p->d + 12;
+  double *dr = nullptr, *dJ = nullptr;
+  JCK(cudaMalloc((void**)&dr, 2 * N * 8));
+  if (J) JCK(cudaMalloc((void**)&dJ, 2 * N * n * 8));
+  JointDev jd = p->dev();
+  cudaError_t e = jdispatch(p->model, p->one_focal, [&](auto M, auto OF) {
+    k_joint_eval_rj<decltype(M)::value, decltype(OF)::value><<<(int)((N + 127) / 128), 128, 0, p->stream>>>(jd, apply_loss, dr, dJ, (int)N);
+    return cudaGetLastError();
+  });
+  p->launches++;
+  JCK(e);
+  JCK(cudaMemcpyAsync(r, dr, 2 * N * 8, cudaMemcpyDeviceToHost, p->stream));
+  if (J) JCK(cudaMemcpyAsync(J, dJ, 2 * N * n * 8, cudaMemcpyDeviceToHost, p->stream));
+  JCK(cudaStreamSynchronize(p->stream));
+  cudaFree(dr); if (dJ) cudaFree(dJ);
+  return 0;
+}
+
+// GaussNewtonOptimizer::optimize on the joint problem (util.rs:668-670). intr [C][d], extr [C][6] (row 0 ignored and
+// returned as zeros, util.rs:689-690), poses [F][6] in/out. lo/hi/fixed are [C][d] (nullable): set_problem_parameter_bound /
+// set_problem_parameter_disabled per camera (util.rs:654-663) and fix_variable("params0", 0) (util.rs:664-667).
+int ccrs_joint_solve_gn(ccrs_joint* p, double* intr, double* extr, double* poses, const double* lo, const double* hi,
+                        const unsigned char* fixed, const ccrs_options* opt_in, ccrs_summary* sum, double* err_hist) {
+  if (!p || !intr || !extr || !poses) return jfail(CCRS_ERR_INVALID, "null");
+  JCK(cudaSetDevice(p->device));
+  ccrs_options opt;
+  if (opt_in) opt = *opt_in; else ccrs_default_options(&opt);
+  ccrs_summary local;
+  if (!sum) sum = &local;
+  std::memset(sum, 0, sizeof(*sum));
+  const int d = p->d, C = p->n_cams, M = p->M, NS = p->NS, NV = NS + M + 1, F = p->n_frames;
+  for (int i = 0; i < 6; ++i) extr[i] = 0.0;
+  int st = upload_state(p, intr, extr, poses);
+  if (st) return st;
+  std::vector<double> red(NV), S((size_t)M * M), y(M);
+  double last_err = 0.0;
+  cudaEvent_t e0, e1;
+  JCK(cudaEventCreate(&e0)); JCK(cudaEventCreate(&e1));
+  JCK(cudaEventRecord(e0, p->stream));
+  int status = 0;
+  for (int it = 0; it < opt.max_iteration; ++it) {
+    JointDev jd = p->dev();
+    cudaError_t e = jdispatch(p->model, p->one_focal, [&](auto Mo, auto OF) {
+      k_joint_linearize<decltype(Mo)::value, decltype(OF)::value><<<(p->n_blocks + kJWarps - 1) / kJWarps, 32 * kJWarps, 0, p->stream>>>(jd, p->ij_table, p->jblk);
+      return cudaGetLastError();
+    });
+    JCK(e);
+    k_joint_schur<<<(F + 63) / 64, 64, 0, p->stream>>>(jd, p->jblk, p->NAJ, M, 0.0, p->fs, p->el);
+    JCK(cudaGetLastError());
+    k_joint_sum<<<(NV + 127) / 128, 128, 0, p->stream>>>(p->fs, F, NV, p->red);
+    JCK(cudaGetLastError());
+    p->launches += 3;
+    JCK(cudaMemcpyAsync(red.data(), p->red, (size_t)NV * 8, cudaMemcpyDeviceToHost, p->stream));
+    JCK(cudaStreamSynchronize(p->stream));
+    const double err = std::sqrt(red[NS + M]);
+    if (err_hist) err_hist[it] = err;
+    sum->iterations = it + 1; sum->final_error = err;
+    if (err < opt.min_error) { sum->stop_reason = 1; break; }
+    if (std::isnan(err)) { status = CCRS_ERR_NUMERIC; break; }
+    if (it > 0) {
+      if (std::fabs(last_err - err) < opt.min_abs_decrease) { sum->stop_reason = 2; break; }
+      if (std::fabs(last_err - err) / last_err < opt.min_rel_decrease) { sum->stop_reason = 3; break; }
+    }
+    last_err = err;
+    { int k = 0; for (int i = 0; i < M; ++i) for (int j = i; j < M; ++j) { S[(size_t)i * M + j] = red[k]; S[(size_t)j * M + i] = red[k]; ++k; } }
+    for (int i = 0; i < M; ++i) y[i] = red[NS + i];
+    bool poisoned = false;
+    for (int i = 0; i < M * M; ++i) poisoned |= std::isnan(S[i]);
+    if (fixed && opt.fixed_mode == 1)
+      for (int i = 0; i < C * d; ++i) if (fixed[i]) { for (int j = 0; j < M; ++j) { S[(size_t)i * M + j] = 0; S[(size_t)j * M + i] = 0; } S[(size_t)i * M + i] = 1; y[i] = 0; }
+    if (poisoned || !chol_solve_dense(S, M, y.data())) { status = CCRS_ERR_CHOLESKY; break; }
+    // ParameterBlock::update_params per variable block
+    for (int i = 0; i < C * d; ++i) {
+      double v = intr[i] + y[i];
+      if (lo && hi) v = std::min(std::max(v, lo[i]), hi[i]);
+      if (fixed && fixed[i]) v = intr[i];
+      intr[i] = v;
+    }
+    for (int c = 1; c < C; ++c) for (int i = 0; i < 6; ++i) extr[6 * c + i] += y[C * d + 6 * (c - 1) + i];
+    JCK(cudaMemcpyAsync(p->ydev, y.data(), (size_t)M * 8, cudaMemcpyHostToDevice, p->stream));
+    k_joint_backsub<<<(F + 63) / 64, 64, 0, p->stream>>>(jd, p->el, p->ydev, M);
+    JCK(cudaGetLastError());
+    p->launches++;
+    st = upload_state(p, intr, extr, nullptr);
+    if (st) return st;
+  }
+  JCK(cudaEventRecord(e1, p->stream));
+  JCK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  sum->device_ms = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  sum->status = status;
+  JCK(cudaMemcpyAsync(poses, p->poses, (size_t)F * 48, cudaMemcpyDeviceToHost, p->stream));
+  JCK(cudaStreamSynchronize(p->stream));
+  if (status == CCRS_ERR_CHOLESKY) jfail(status, "Cholesky failure (non-positive pivot)");
+  if (status == CCRS_ERR_NUMERIC) jfail(status, "NaN error");
+  return status;
+}
+
+}  // extern "C"

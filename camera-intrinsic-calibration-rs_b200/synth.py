@@ -194,3 +194,75 @@ def full_from_intr(intr: np.ndarray, xy_same_focal: bool) -> np.ndarray:
     """`new_params.insert_row(1, new_params[0])` (util.rs:466-470)."""
     a = np.asarray(intr, dtype=np.float64)
     return np.insert(a, 1, a[0]) if xy_same_focal else a.copy()
+
+
+@dataclass
+class SyntheticRig:
+    """Joint multi-camera problem (calib_all_camera_with_extrinsics, src/util.rs:567-715) in block-CSR SoA layout."""
+    model: str
+    width: int
+    height: int
+    n_cams: int
+    n_frames: int
+    block_cam: np.ndarray        # int32 (B,)
+    block_frame: np.ndarray      # int32 (B,)
+    block_offsets: np.ndarray    # int32 (B+1,)
+    x: np.ndarray; y: np.ndarray; z: np.ndarray; u: np.ndarray; v: np.ndarray
+    gt_params: np.ndarray        # (C, nparams) full vectors
+    gt_extr: np.ndarray          # (C, 6) T_c_0, row 0 zero
+    gt_poses: np.ndarray         # (F, 6) T_0_b
+    init_params: np.ndarray
+    init_extr: np.ndarray
+    init_poses: np.ndarray
+
+    @property
+    def n_obs(self) -> int:
+        return int(self.block_offsets[-1])
+
+
+def make_rig(model: str = "eucm", n_frames: int = 200, n_cams: int = 2, seed: int = 4, width: int = 1024,
+             height: int = 1024, drop_block_fraction: float = 0.1) -> SyntheticRig:
+    """joint cam0+cam1 problem, T_1_0 = rvec (0, 0.02, 0), tvec (-0.1, 0, 0); further cameras are spaced
+    another -0.1 m apart. Each camera misses a random `drop_block_fraction` of the frames."""
+    rng = np.random.default_rng(seed)
+    board = aprilgrid_board().astype(np.float64)
+    centre = board.mean(axis=0)
+    gt0 = np.array(GT_PARAMS[model], dtype=np.float64)
+    if model == "opencv5":
+        rvec, tvec = make_poses(rng, n_frames, centre, max_angle=0.4, xy_range=0.12, z_range=(0.6, 0.9))
+    else:
+        rvec, tvec = make_poses(rng, n_frames, centre, xy_range=0.15)
+    gt_params = np.stack([gt0 * (1.0 + 0.01 * c * np.sign(np.arange(len(gt0)) % 2 - 0.5)) for c in range(n_cams)])
+    gt_extr = np.zeros((n_cams, 6))
+    for c in range(1, n_cams):
+        gt_extr[c] = [0.0, 0.02 * c, 0.0, -0.1 * c, 0.0, 0.0]
+    R0 = rodrigues(rvec)
+    P0 = np.einsum("fij,kj->fki", R0, board) + tvec[:, None, :]
+    bc, bf, offs, xs, ys, zs, us, vs = [], [], [0], [], [], [], [], []
+    for c in range(n_cams):
+        Rc = rodrigues(gt_extr[c, :3])
+        Pc = np.einsum("ij,fkj->fki", Rc, P0) + gt_extr[c, 3:]
+        uv = project(model, gt_params[c], Pc).astype(np.float32).astype(np.float64)
+        inside = (uv[..., 0] >= 0) & (uv[..., 0] < width) & (uv[..., 1] >= 0) & (uv[..., 1] < height) & (Pc[..., 2] > 0.05)
+        seen = rng.uniform(size=n_frames) >= drop_block_fraction
+        for f in range(n_frames):
+            idx = np.nonzero(inside[f])[0]
+            if not seen[f] or len(idx) < 24:
+                continue
+            bc.append(c); bf.append(f); offs.append(offs[-1] + len(idx))
+            xs.append(board[idx, 0]); ys.append(board[idx, 1]); zs.append(board[idx, 2])
+            us.append(uv[f, idx, 0]); vs.append(uv[f, idx, 1])
+    cat = np.concatenate
+    poses = cat([rvec, tvec], axis=1)
+    init_params = gt_params * INIT_SCALE[model][None, :]
+    init_extr = gt_extr.copy()
+    init_extr[1:, :3] += rng.normal(scale=0.005, size=(n_cams - 1, 3))
+    init_extr[1:, 3:] += rng.normal(scale=0.005, size=(n_cams - 1, 3))
+    init_poses = poses.copy()
+    init_poses[:, :3] += rng.normal(scale=0.01, size=(n_frames, 3))
+    init_poses[:, 3:] += rng.normal(scale=0.005, size=(n_frames, 3))
+    return SyntheticRig(model=model, width=width, height=height, n_cams=n_cams, n_frames=n_frames,
+                        block_cam=np.asarray(bc, dtype=np.int32), block_frame=np.asarray(bf, dtype=np.int32),
+                        block_offsets=np.asarray(offs, dtype=np.int32), x=cat(xs), y=cat(ys), z=cat(zs), u=cat(us), v=cat(vs),
+                        gt_params=gt_params, gt_extr=gt_extr, gt_poses=poses, init_params=init_params,
+                        init_extr=init_extr, init_poses=init_poses)

@@ -226,6 +226,32 @@ int ccrs_calib_camera(int model, int width, int height, int n_frames, const int3
                       double* params, double* poses, int xy_same_focal, int disabled_distortions, int fixed_focal,
                       int use_lm, const ccrs_options* opt, ccrs_summary* summary, int device_id);
 
+/* ---- joint multi-camera refinement: calib_all_camera_with_extrinsics (src/util.rs:567-715) ----------------------
+ * Variables "params{c}" (d per camera), "rvec_{c}_0"/"tvec_{c}_0" (camera c <- camera 0, c > 0) and
+ * "rvec_0_b_{f}"/"tvec_0_b_{f}" (board -> camera 0, per frame, shared by all cameras). A block is the set of corners one
+ * camera detected in one frame: cam0 blocks are ReprojectionFactor blocks (util.rs:603-611), the others
+ * OtherCamReprojectionFactor blocks (util.rs:612-631, factors.rs:204-228). block_offsets is CSR over the SoA
+ * observation arrays. The board poses are eliminated per frame on the device; the host solves the shared system. */
+typedef struct ccrs_joint ccrs_joint;
+int ccrs_joint_create(ccrs_joint** out, int model, int xy_same_focal, int n_cams, int n_frames, int n_blocks,
+                      const int32_t* block_cam, const int32_t* block_frame, const int32_t* block_offsets,
+                      const double* x, const double* y, const double* z, const double* u, const double* v,
+                      double huber_delta, int device_id);
+int ccrs_joint_destroy(ccrs_joint* p);
+int ccrs_joint_dim(const ccrs_joint* p);
+const char* ccrs_joint_last_error(void);
+int64_t ccrs_joint_launch_count(const ccrs_joint* p);
+/* parity hook for OtherCamReprojectionFactor::residual_func (factors.rs:204-228): r [2N], J [2N][d+12] with columns
+ * [params_c | rvec_0_b tvec_0_b | rvec_c_0 tvec_c_0] (the last six are zero for cam0 blocks). intr [n_cams][d],
+ * extr [n_cams][6] (row 0 ignored), poses [n_frames][6]. */
+int ccrs_joint_eval_rj(ccrs_joint* p, const double* intr, const double* extr, const double* poses, int apply_loss,
+                       double* r, double* J);
+/* GaussNewtonOptimizer::optimize on the joint problem (util.rs:668-670). intr, extr, poses in/out; lo/hi/fixed are
+ * [n_cams][d], nullable (set_problem_parameter_bound / _disabled per camera util.rs:654-663; cam0_fixed_focal =
+ * fixed[0], util.rs:664-667). extr row 0 is returned as zeros (util.rs:689-690). */
+int ccrs_joint_solve_gn(ccrs_joint* p, double* intr, double* extr, double* poses, const double* lo, const double* hi,
+                        const unsigned char* fixed, const ccrs_options* opt, ccrs_summary* summary, double* err_hist);
+
 /* Distortion bounds of GenericModel::distortion_params_bound() for the FULL parameter vector
  * (lo/hi [nparams]; +-inf where unbounded), plus fx,fy in [0,1e4], cx in [0,w], cy in [0,h] (util.rs:36-39). */
 int ccrs_model_bounds(int model, int width, int height, double* lo, double* hi);

@@ -521,4 +521,133 @@ int oracle_lm(const oracle_problem_t* pb, double* intr, double* poses, const dou
   return 0;
 }
 
+
+// ======================================================================================================
+// Joint multi-camera problem: calib_all_camera_with_extrinsics (src/util.rs:567-715).
+// Variables: params{c} (d each), rvec_{c}_0/tvec_{c}_0 for c > 0, rvec_0_b_{f}/tvec_0_b_{f} per frame.
+// cam0 corners use ReprojectionFactor (util.rs:603-611), other cameras OtherCamReprojectionFactor (util.rs:612-631).
+// Unknown order of the dense system: [params0 .. params{C-1} | T_1_0 .. T_{C-1}_0 | T_0_b_0 .. T_0_b_{F-1}].
+// ======================================================================================================
+typedef struct {
+  int model, xy_same_focal;
+  int n_cams, n_frames, n_blocks;
+  const int32_t* block_cam;      // [n_blocks]
+  const int32_t* block_frame;    // [n_blocks]
+  const int32_t* block_offsets;  // [n_blocks+1] CSR over observations
+  const double *x, *y, *z, *u, *v;
+  double huber_delta;
+  int n_threads;
+} oracle_joint_t;
+
+}  // extern "C"
+
+namespace {
+
+// residual + Jacobian of one observation of block b. Jrow layout: [params_c (d) | T_0_b (6) | T_c_0 (6)] (d+12).
+inline void joint_obs(const oracle_joint_t* jp, int d, int c, const double* intr_c, const double* pose_0_b,
+                      const double* pose_c_0, int k, double r[2], double* J0, double* J1) {
+  const int n = d + 12;
+  Dual a[16], prm[16];
+  for (int i = 0; i < d; ++i) a[i] = Dual::var(intr_c[i], n, i);
+  if (jp->xy_same_focal) { prm[0] = a[0]; prm[1] = a[0]; for (int i = 1; i < d; ++i) prm[i + 1] = a[i]; }
+  else for (int i = 0; i < d; ++i) prm[i] = a[i];
+  Dual rv0[3], tv0[3];
+  for (int i = 0; i < 3; ++i) { rv0[i] = Dual::var(pose_0_b[i], n, d + i); tv0[i] = Dual::var(pose_0_b[3 + i], n, d + 3 + i); }
+  Dual p[3] = {Dual(jp->x[k], n), Dual(jp->y[k], n), Dual(jp->z[k], n)};
+  Dual P[3], uv[2];
+  if (c == 0) {
+    isometry_apply<Dual>(rv0, tv0, p, P);                       // ReprojectionFactor (factors.rs:160-164)
+  } else {
+    Dual rv1[3], tv1[3];
+    for (int i = 0; i < 3; ++i) { rv1[i] = Dual::var(pose_c_0[i], n, d + 6 + i); tv1[i] = Dual::var(pose_c_0[3 + i], n, d + 9 + i); }
+    isometry_chain_apply<Dual>(rv1, tv1, rv0, tv0, p, P);       // OtherCamReprojectionFactor (factors.rs:212-218)
+  }
+  project_one<Dual>(jp->model, prm, P, uv);
+  Dual r0 = uv[0] - jp->u[k], r1 = uv[1] - jp->v[k];
+  r[0] = r0.v; r[1] = r1.v;
+  for (int i = 0; i < n; ++i) { J0[i] = r0.d[i]; J1[i] = r1.d[i]; }
+}
+
+}  // namespace
+
+extern "C" {
+
+// Parity hook: per observation r (2N) and J (2N x (d+12)); cam0 blocks have zero T_c_0 columns.
+void oracle_joint_eval_rj(const oracle_joint_t* jp, const double* intr /*[C][d]*/, const double* extr /*[C][6]*/,
+                          const double* poses /*[F][6]*/, int apply_loss, double* r_out, double* J_out) {
+  const int d = model_nparams(jp->model) - (jp->xy_same_focal ? 1 : 0), n = d + 12;
+  for (int b = 0; b < jp->n_blocks; ++b) {
+    const int c = jp->block_cam[b], f = jp->block_frame[b];
+    for (int k = jp->block_offsets[b]; k < jp->block_offsets[b + 1]; ++k) {
+      double r[2], J0[32], J1[32];
+      joint_obs(jp, d, c, intr + (size_t)c * d, poses + 6 * (size_t)f, extr + 6 * (size_t)c, k, r, J0, J1);
+      const double w = apply_loss ? huber_sqrt_rho1(r[0] * r[0] + r[1] * r[1], jp->huber_delta) : 1.0;
+      r_out[2 * (size_t)k] = r[0] * w; r_out[2 * (size_t)k + 1] = r[1] * w;
+      if (J_out) for (int i = 0; i < n; ++i) { J_out[(size_t)(2 * k) * n + i] = J0[i] * w; J_out[(size_t)(2 * k + 1) * n + i] = J1[i] * w; }
+    }
+  }
+}
+
+// GaussNewtonOptimizer::optimize on the joint problem (util.rs:668-670): dense normal equations over ALL unknowns.
+// intr [C][d], extr [C][6] (row 0 unused), poses [F][6] updated in place. lo/hi/fixed: [C][d] nullable.
+int oracle_joint_gn(const oracle_joint_t* jp, double* intr, double* extr, double* poses, const double* lo,
+                    const double* hi, const unsigned char* fixed, const oracle_options_t* opt, oracle_result_t* res,
+                    double* err_hist) {
+  const int d = model_nparams(jp->model) - (jp->xy_same_focal ? 1 : 0);
+  const int C = jp->n_cams, F = jp->n_frames;
+  const int off_e = C * d, off_p = C * d + 6 * (C - 1), M = off_p + 6 * F;
+  res->iterations = 0; res->status = 0; res->stop_reason = 0; res->n_accepted = res->n_rejected = 0;
+  std::vector<double> H((size_t)M * M), g(M);
+  double last_err = 0.0;
+  for (int it = 0; it < opt->max_iteration; ++it) {
+    std::fill(H.begin(), H.end(), 0.0); std::fill(g.begin(), g.end(), 0.0);
+    double sq = 0.0;
+    for (int b = 0; b < jp->n_blocks; ++b) {
+      const int c = jp->block_cam[b], f = jp->block_frame[b];
+      int col[32];
+      for (int i = 0; i < d; ++i) col[i] = c * d + i;
+      for (int i = 0; i < 6; ++i) col[d + i] = off_p + 6 * f + i;
+      for (int i = 0; i < 6; ++i) col[d + 6 + i] = c > 0 ? off_e + 6 * (c - 1) + i : -1;
+      for (int k = jp->block_offsets[b]; k < jp->block_offsets[b + 1]; ++k) {
+        double r[2], J[2][32];
+        joint_obs(jp, d, c, intr + (size_t)c * d, poses + 6 * (size_t)f, extr + 6 * (size_t)c, k, r, J[0], J[1]);
+        const double w = huber_sqrt_rho1(r[0] * r[0] + r[1] * r[1], jp->huber_delta);
+        for (int q = 0; q < 2; ++q) {
+          const double rw = r[q] * w;
+          sq += rw * rw;
+          for (int i = 0; i < d + 12; ++i) {
+            if (col[i] < 0) continue;
+            const double ji = J[q][i] * w;
+            g[col[i]] -= ji * rw;
+            for (int j = 0; j < d + 12; ++j) if (col[j] >= 0) H[(size_t)col[i] * M + col[j]] += ji * J[q][j] * w;
+          }
+        }
+      }
+    }
+    const double err = err_metric(sq);
+    if (err_hist) err_hist[it] = err;
+    res->iterations = it + 1; res->final_error = err;
+    if (err < opt->min_error) { res->stop_reason = 1; break; }
+    if (std::isnan(err)) { res->status = -1; return -1; }
+    if (it > 0) {
+      if (std::fabs(last_err - err) < opt->min_abs_decrease) { res->stop_reason = 2; break; }
+      if (std::fabs(last_err - err) / last_err < opt->min_rel_decrease) { res->stop_reason = 3; break; }
+    }
+    last_err = err;
+    if (fixed && opt->fixed_mode == 1)
+      for (int i = 0; i < C * d; ++i) if (fixed[i]) { for (int j = 0; j < M; ++j) { H[(size_t)i * M + j] = 0; H[(size_t)j * M + i] = 0; } H[(size_t)i * M + i] = 1; g[i] = 0; }
+    if (!chol_factor(H, M)) { res->status = -2; return -2; }
+    chol_solve(H, M, g.data());
+    for (int i = 0; i < C * d; ++i) {
+      double v = intr[i] + g[i];
+      if (lo && hi) v = std::min(std::max(v, lo[i]), hi[i]);
+      if (fixed && fixed[i]) v = intr[i];
+      intr[i] = v;
+    }
+    for (int c = 1; c < C; ++c) for (int i = 0; i < 6; ++i) extr[6 * c + i] += g[off_e + 6 * (c - 1) + i];
+    for (int i = 0; i < 6 * F; ++i) poses[i] += g[off_p + i];
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -165,3 +165,45 @@ def transform_point(rvec, tvec, p):
     out = np.empty(3)
     lib().oracle_transform_point(_dp(rvec), _dp(tvec), _dp(p), _dp(out))
     return out
+
+
+class JointStruct(C.Structure):
+    _fields_ = [("model", C.c_int), ("xy_same_focal", C.c_int), ("n_cams", C.c_int), ("n_frames", C.c_int),
+                ("n_blocks", C.c_int), ("block_cam", C.POINTER(C.c_int32)), ("block_frame", C.POINTER(C.c_int32)),
+                ("block_offsets", C.POINTER(C.c_int32)),
+                ("x", C.POINTER(C.c_double)), ("y", C.POINTER(C.c_double)), ("z", C.POINTER(C.c_double)),
+                ("u", C.POINTER(C.c_double)), ("v", C.POINTER(C.c_double)), ("huber_delta", C.c_double), ("n_threads", C.c_int)]
+
+
+class OracleJoint:
+    """calib_all_camera_with_extrinsics (src/util.rs:567-715) restated on the CPU: dense normal equations."""
+
+    def __init__(self, rig, model_id: int, xy_same_focal: bool = False, huber_delta: float = 1.0):
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        self.bc = np.ascontiguousarray(rig.block_cam, dtype=np.int32)
+        self.bf = np.ascontiguousarray(rig.block_frame, dtype=np.int32)
+        self.bo = np.ascontiguousarray(rig.block_offsets, dtype=np.int32)
+        self.x, self.y, self.z, self.u, self.v = map(_f64, (rig.x, rig.y, rig.z, rig.u, rig.v))
+        self.n_cams, self.n_frames, self.n_obs = rig.n_cams, rig.n_frames, int(self.bo[-1])
+        self.d = lib().oracle_model_nparams(model_id) - (1 if xy_same_focal else 0)
+        self.c = JointStruct(model_id, int(xy_same_focal), rig.n_cams, rig.n_frames, len(self.bc), ip(self.bc), ip(self.bf),
+                             ip(self.bo), _dp(self.x), _dp(self.y), _dp(self.z), _dp(self.u), _dp(self.v), float(huber_delta), 0)
+
+    def eval_rj(self, intr, extr, poses, apply_loss=True):
+        intr, extr, poses = _f64(intr), _f64(extr), _f64(poses)
+        r = np.empty(2 * self.n_obs); J = np.empty((2 * self.n_obs, self.d + 12))
+        lib().oracle_joint_eval_rj(C.byref(self.c), _dp(intr), _dp(extr), _dp(poses), int(apply_loss), _dp(r), _dp(J))
+        return r, J
+
+    def gauss_newton(self, intr, extr, poses, lo=None, hi=None, fixed=None, options=None):
+        intr = _f64(intr).copy(); extr = _f64(extr).copy(); poses = _f64(poses).copy()
+        if options is None:
+            options = Options(); lib().oracle_default_options(C.byref(options))
+        res = Result(); hist = np.full(options.max_iteration, np.nan)
+        lo_a = _f64(lo) if lo is not None else None
+        hi_a = _f64(hi) if hi is not None else None
+        fx = np.ascontiguousarray(fixed, dtype=np.uint8) if fixed is not None else None
+        lib().oracle_joint_gn(C.byref(self.c), _dp(intr), _dp(extr), _dp(poses), _dp(lo_a), _dp(hi_a),
+                              fx.ctypes.data_as(C.POINTER(C.c_ubyte)) if fx is not None else None, C.byref(options),
+                              C.byref(res), _dp(hist))
+        return intr.reshape(self.n_cams, -1), extr.reshape(-1, 6), poses.reshape(-1, 6), res, hist[: res.iterations]
