@@ -15,7 +15,7 @@ step     : one Levenberg-Marquardt iteration of that problem = K3 reduce (+excha
 value    : total observations over all ranks / time per step, inputs resident in HBM, L2 flushed (512 MB write)
            before every timed step outside the CUDA-event bracket; max over ranks.
 e2e      : the same metric through the C-ABI entry point a user calls with HOST buffers: per step one complete
-           ccrs_problem_create (H2D of the observation arrays from pinned memory) + ccrs_set_poses + ccrs_solve_lm
+           ccrs_problem_create_f32 (H2D of the f32 observation arrays from pinned memory) + ccrs_set_poses + ccrs_solve_lm
            to convergence + ccrs_get_poses (D2H) + destroy; evals = observations x linearisations performed.
 
 `--impl reference` times the reference arm: the CPU oracle (oracle/, a restatement of the reference's num-dual +
@@ -107,7 +107,8 @@ class ClockSampler:
 def pinned(a: np.ndarray):
     """copy into page-locked host memory (torch is plumbing: allocator only)."""
     import torch
-    t = torch.empty(a.shape, dtype=torch.float64 if a.dtype == np.float64 else torch.int32, pin_memory=True)
+    dt = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32, np.dtype(np.int32): torch.int32}[a.dtype]
+    t = torch.empty(a.shape, dtype=dt, pin_memory=True)
     n = t.numpy()
     n[...] = a
     return n, t
@@ -192,7 +193,9 @@ def run_ours(args):
             pass
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------------------
-    hx, _tx = pinned(sh["x"]); hy, _ty = pinned(sh["y"]); hz, _tz = pinned(sh["z"]); hu, _tu = pinned(sh["u"]); hv, _tv = pinned(sh["v"])
+    # the reference's FeaturePoint holds f32 (src/detected_points.rs:6-9): the f32 entry point is the natural host format
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    hx, _tx = pinned(f32(sh["x"])); hy, _ty = pinned(f32(sh["y"])); hz, _tz = pinned(f32(sh["z"])); hu, _tu = pinned(f32(sh["u"])); hv, _tv = pinned(f32(sh["v"]))
     hfo, _tf = pinned(sh["frame_offsets"]); hp, _tp = pinned(poses0)
     h2d = hx.nbytes * 5 + hfo.nbytes + hp.nbytes
     d2h = hp.nbytes + d * 8
@@ -237,7 +240,7 @@ def run_ours(args):
             "wall_ms_timed_region_incl_flush": wall_ms,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h + d2h_iter),
                     "ms_per_call": e2e_total / e2e_steps * 1e3, "lm_iterations_per_call": int(summ.iterations),
-                    "what": "ccrs_problem_create(H2D from pinned) + set_poses + ccrs_solve_lm to convergence + get_poses (D2H) + destroy",
+                    "what": "ccrs_problem_create_f32 (H2D of the f32 FeaturePoint arrays from pinned memory) + set_poses + ccrs_solve_lm to convergence + get_poses (D2H) + destroy",
                     "converged_rel_err_vs_gt": rel_err},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         }

@@ -79,14 +79,21 @@ class Problem:
         self.lib = _abi.load()
         self.model = MODELS[model] if isinstance(model, str) else int(model)
         fo = np.ascontiguousarray(frame_offsets, dtype=np.int32)
-        xs, ys, zs, us, vs = map(_f64, (x, y, z, u, v))
+        f32 = all(isinstance(a, np.ndarray) and a.dtype == np.float32 for a in (x, y, z, u, v)) and problem_frame_offsets is None
+        conv = (lambda a: np.ascontiguousarray(a, dtype=np.float32)) if f32 else _f64
+        xs, ys, zs, us, vs = map(conv, (x, y, z, u, v))
         n = int(fo[-1])
         for a in (xs, ys, zs, us, vs):
             if a.shape != (n,):
                 raise ValueError("observation arrays must have frame_offsets[-1] entries")
         self.h = C.c_void_p()
         ip = C.POINTER(C.c_int32)
-        if problem_frame_offsets is None:
+        if f32:   # FeaturePoint-style f32 observations: ccrs_problem_create_f32
+            fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+            check(self.lib.ccrs_problem_create_f32(C.byref(self.h), self.model, width, height, int(xy_same_focal),
+                                                   len(fo) - 1, fo.ctypes.data_as(ip), fp(xs), fp(ys), fp(zs), fp(us),
+                                                   fp(vs), float(huber_delta), int(device)))
+        elif problem_frame_offsets is None:
             check(self.lib.ccrs_problem_create(C.byref(self.h), self.model, width, height, int(xy_same_focal),
                                                len(fo) - 1, fo.ctypes.data_as(ip), _dp(xs), _dp(ys), _dp(zs), _dp(us),
                                                _dp(vs), float(huber_delta), int(device)))

@@ -151,6 +151,7 @@ struct ccrs_problem {
   int n_frames = 0, n_problems = 1, Fs = 0;
   int64_t n_obs = 0;
   bool batch = false;
+  bool f32 = false;               // observation arrays stored as floats (ccrs_problem_create_f32)
   int device = 0;
   int n_sms = 148;
   cudaStream_t stream = nullptr;
@@ -184,6 +185,7 @@ struct ccrs_problem {
   ProblemDev dev() const {
     ProblemDev d{};
     d.x = x.p; d.y = y.p; d.z = z.p; d.u = u.p; d.v = v.p;
+    d.f32 = f32 ? 1 : 0;
     d.frame_offsets = frame_offsets.p;
     d.frame_problem = batch ? frame_problem.p : nullptr;
     d.problem_frame_offsets = problem_frame_offsets.p;
@@ -224,8 +226,8 @@ void choose_slicing(ccrs_problem* p) {
 }
 
 int upload_problem(ccrs_problem* p, int n_problems, const int32_t* problem_frame_offsets, int n_frames,
-                   const int32_t* frame_offsets, const double* x, const double* y, const double* z, const double* u,
-                   const double* v) {
+                   const int32_t* frame_offsets, const void* x, const void* y, const void* z, const void* u,
+                   const void* v) {
   p->n_frames = n_frames;
   p->n_problems = n_problems;
   p->n_obs = frame_offsets[n_frames];
@@ -237,13 +239,14 @@ int upload_problem(ccrs_problem* p, int n_problems, const int32_t* problem_frame
   p->n_schur_ctas = (n_frames + 127) / 128;
   const size_t N = (size_t)p->n_obs, F = (size_t)n_frames, Fs = (size_t)p->Fs, P = (size_t)n_problems;
   cudaStream_t s = p->stream;
-  CK(p->x.alloc(N)); CK(p->y.alloc(N)); CK(p->z.alloc(N)); CK(p->u.alloc(N)); CK(p->v.alloc(N));
+  const size_t esz = p->f32 ? 4 : 8, nel = p->f32 ? (N + 1) / 2 : N;   // floats are packed into the double-typed buffers
+  CK(p->x.alloc(nel)); CK(p->y.alloc(nel)); CK(p->z.alloc(nel)); CK(p->u.alloc(nel)); CK(p->v.alloc(nel));
   // start the big copies first so everything below overlaps with them
-  CK(cudaMemcpyAsync(p->x.p, x, N * 8, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(p->y.p, y, N * 8, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(p->z.p, z, N * 8, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(p->u.p, u, N * 8, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(p->v.p, v, N * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(p->x.p, x, N * esz, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(p->y.p, y, N * esz, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(p->z.p, z, N * esz, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(p->u.p, u, N * esz, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(p->v.p, v, N * esz, cudaMemcpyHostToDevice, s));
   CK(p->frame_offsets.alloc(F + 1));
   CK(p->problem_frame_offsets.alloc(P + 1));
   CK(p->cur.alloc(P));
@@ -306,9 +309,9 @@ double next_seq() { return (double)(++g_seq); }
 struct DevInfo { bool known = false; int major = 0, minor = 0, sms = 0; } g_dev_info[64];
 
 int create_common(ccrs_problem** out, int model, int width, int height, int xy_same_focal, int n_problems,
-                  const int32_t* problem_frame_offsets, int n_frames, const int32_t* frame_offsets, const double* x,
-                  const double* y, const double* z, const double* u, const double* v, double huber_delta, int device_id,
-                  bool batch) {
+                  const int32_t* problem_frame_offsets, int n_frames, const int32_t* frame_offsets, const void* x,
+                  const void* y, const void* z, const void* u, const void* v, double huber_delta, int device_id,
+                  bool batch, bool f32 = false) {
   if (!out || !frame_offsets || !x || !y || !z || !u || !v || n_frames <= 0 || n_problems <= 0)
     return fail(CCRS_ERR_INVALID, "null pointer or empty problem");
   if (model < 0 || model > 5) return fail(CCRS_ERR_INVALID, "unknown model %d", model);
@@ -331,7 +334,7 @@ int create_common(ccrs_problem** out, int model, int width, int height, int xy_s
   CK(cudaSetDevice(device_id));
   ccrs_problem* p = new ccrs_problem();
   p->model = model; p->width = width; p->height = height; p->one_focal = xy_same_focal ? 1 : 0;
-  p->huber = huber_delta; p->device = device_id; p->batch = batch; p->n_sms = di.sms;
+  p->huber = huber_delta; p->device = device_id; p->batch = batch; p->n_sms = di.sms; p->f32 = f32;
   if (const char* e = getenv("CCRS_K2_VARIANT")) p->k2_variant = atoi(e);
   model_dims(model, p->one_focal, &p->D, &p->NA, &p->NBLK, &p->NACC);
   p->NRED = nred_of(p->D);
@@ -610,6 +613,13 @@ int ccrs_problem_create(ccrs_problem** out, int model, int width, int height, in
                         const double* u, const double* v, double huber_delta, int device_id) {
   return create_common(out, model, width, height, xy_same_focal, 1, nullptr, n_frames, frame_offsets, x, y, z, u, v,
                        huber_delta, device_id, false);
+}
+
+int ccrs_problem_create_f32(ccrs_problem** out, int model, int width, int height, int xy_same_focal, int n_frames,
+                            const int32_t* frame_offsets, const float* x, const float* y, const float* z,
+                            const float* u, const float* v, double huber_delta, int device_id) {
+  return create_common(out, model, width, height, xy_same_focal, 1, nullptr, n_frames, frame_offsets, x, y, z, u, v,
+                       huber_delta, device_id, false, true);
 }
 
 int ccrs_batch_create(ccrs_problem** out, int model, int width, int height, int xy_same_focal, int n_problems,

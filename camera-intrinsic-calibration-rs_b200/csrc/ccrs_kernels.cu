@@ -72,6 +72,20 @@ CCRS_D void publish_host(volatile double* dst, const double* src, int n, double 
   dst[n] = seq;
 }
 
+CCRS_D void cp_async8(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+CCRS_D void cp_async4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+// observation k of an SoA array that holds doubles or (f32 != 0) floats; f32 -> f64 widening as factors.rs:141-143
+CCRS_D double ld_obs(const double* base, int k, int f32) {
+  return f32 ? (double)reinterpret_cast<const float*>(base)[k] : base[k];
+}
+CCRS_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+CCRS_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // One observation: weighted rows au, av of [J | r] in the LOCAL rotation basis (d/dphi, not d/drvec).
 // Returns the corrected squared residual. Structurally-zero entries of au/av are left untouched.
 template <int MODEL, bool OF, bool WITH_J>
@@ -136,6 +150,7 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   double* s_red = s_intr + (BATCH ? FPC * kMaxFull : 0); // [kRedChunk][kLinThreads]
 
   double* s_stat = s_red + (COST_ONLY ? kLinThreads : kRedChunk * kLinThreads);  // [2][FPC] per-frame md, cost
+  double* s_obs = s_stat + 2 * FPC;                      // [kObsStages][5][kLinThreads] cp.async ring of x,y,z,u,v
 
   if (t < nf) {
     const int f = f0 + t;
@@ -204,8 +219,39 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   if (active) {
     const int f = f0 + fl;
     const int end = pb.frame_offsets[f + 1];
-    for (int k = pb.frame_offsets[f] + lane; k < end; k += G) {
-      const double px = pb.x[k], py = pb.y[k], pz = pb.z[k], ou = pb.u[k], ov = pb.v[k];
+    const int beg = pb.frame_offsets[f] + lane;
+    // Observations are prefetched kObsStages-1 iterations ahead with 8-byte cp.async into a per-thread shared-memory
+    // ring (each thread reads back only what it fetched: no barrier), so neither DRAM nor L2 latency sits at the
+    // top of an iteration.
+    double* ring = s_obs + t;
+    auto fetch = [&](int kk, int stage) {
+      if (kk < end) {
+        double* dst = ring + stage * (5 * kLinThreads);
+        if (pb.f32) {
+          const float *fx = (const float*)pb.x, *fy = (const float*)pb.y, *fz = (const float*)pb.z, *fu = (const float*)pb.u, *fv = (const float*)pb.v;
+          cp_async4(dst, fx + kk); cp_async4(dst + kLinThreads, fy + kk); cp_async4(dst + 2 * kLinThreads, fz + kk);
+          cp_async4(dst + 3 * kLinThreads, fu + kk); cp_async4(dst + 4 * kLinThreads, fv + kk);
+        } else {
+          cp_async8(dst, pb.x + kk); cp_async8(dst + kLinThreads, pb.y + kk); cp_async8(dst + 2 * kLinThreads, pb.z + kk);
+          cp_async8(dst + 3 * kLinThreads, pb.u + kk); cp_async8(dst + 4 * kLinThreads, pb.v + kk);
+        }
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < kObsStages - 1; ++i) fetch(beg + i * G, i);
+    int it = 0;
+    for (int k = beg; k < end; k += G, ++it) {
+      fetch(k + (kObsStages - 1) * G, (it + kObsStages - 1) % kObsStages);
+      cp_async_wait<kObsStages - 1>();
+      const double* src = ring + (it % kObsStages) * (5 * kLinThreads);
+      double px, py, pz, ou, ov;
+      if (pb.f32) {
+        px = *(const float*)(src); py = *(const float*)(src + kLinThreads); pz = *(const float*)(src + 2 * kLinThreads);
+        ou = *(const float*)(src + 3 * kLinThreads); ov = *(const float*)(src + 4 * kLinThreads);
+      } else {
+        px = src[0]; py = src[kLinThreads]; pz = src[2 * kLinThreads]; ou = src[3 * kLinThreads]; ov = src[4 * kLinThreads];
+      }
       double au[C::NA], av[C::NA];
       const double c = obs_rows<MODEL, OF, !COST_ONLY>(ip, fc, px, py, pz, ou, ov, pb.huber_delta, au, av);
       if constexpr (COST_ONLY) {
@@ -473,7 +519,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_linearize_pc(const __grid_con
     int k = beg + pg * G;
     double px = 0, py = 0, pz = 0, ou = 0, ov = 0;
     bool have = k < end;
-    if (have) { px = pb.x[k]; py = pb.y[k]; pz = pb.z[k]; ou = pb.u[k]; ov = pb.v[k]; }
+    if (have) { px = ld_obs(pb.x, k, pb.f32); py = ld_obs(pb.y, k, pb.f32); pz = ld_obs(pb.z, k, pb.f32); ou = ld_obs(pb.u, k, pb.f32); ov = ld_obs(pb.v, k, pb.f32); }
     for (int it = pg; it < n_iter; it += 2) {
       const int slot = it % kPcSlots;
       const unsigned round = (unsigned)(it / kPcSlots);
@@ -482,7 +528,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_linearize_pc(const __grid_con
       const bool cur_have = have;
       k += 2 * G;
       have = k < end;
-      if (have) { px = pb.x[k]; py = pb.y[k]; pz = pb.z[k]; ou = pb.u[k]; ov = pb.v[k]; }
+      if (have) { px = ld_obs(pb.x, k, pb.f32); py = ld_obs(pb.y, k, pb.f32); pz = ld_obs(pb.z, k, pb.f32); ou = ld_obs(pb.u, k, pb.f32); ov = ld_obs(pb.v, k, pb.f32); }
       double val[P::NV];
       if (cur_have) {
         const double fx = ip[0], fy = OF ? ip[0] : ip[1], cx = ip[2], cy = ip[3];
@@ -664,7 +710,8 @@ __global__ void __launch_bounds__(128) k_eval_rj(ProblemDev pb, const double* __
   for (int i = 0; i < 3; ++i) fc[9 + i] = fp.t[i];
   double au[C::NA], av[C::NA];
   for (int i = 0; i < C::NA; ++i) { au[i] = 0.0; av[i] = 0.0; }
-  obs_rows<MODEL, OF, true>(ip, fc, pb.x[k], pb.y[k], pb.z[k], pb.u[k], pb.v[k], apply_loss ? pb.huber_delta : 0.0, au, av);
+  obs_rows<MODEL, OF, true>(ip, fc, ld_obs(pb.x, k, pb.f32), ld_obs(pb.y, k, pb.f32), ld_obs(pb.z, k, pb.f32), ld_obs(pb.u, k, pb.f32),
+                            ld_obs(pb.v, k, pb.f32), apply_loss ? pb.huber_delta : 0.0, au, av);
   r[2 * k] = au[C::N]; r[2 * k + 1] = av[C::N];
   if (J) {
     double* j0 = J + (size_t)(2 * k) * C::N;
@@ -1035,6 +1082,7 @@ static size_t lin_smem_bytes(int FPC, bool batch, bool cost_only) {
   size_t d = (size_t)FPC * kFrameConst + (batch ? (size_t)FPC * kMaxFull : 0);
   d += cost_only ? kLinThreads : (size_t)kRedChunk * kLinThreads;
   d += 2 * (size_t)FPC;  // per-frame {md, cost}
+  d += (size_t)kObsStages * 5 * kLinThreads;  // cp.async observation ring
   return d * sizeof(double);
 }
 

@@ -8,11 +8,13 @@ namespace ccrs {
 constexpr int kLinThreads = 128;     // K2 CTA size
 constexpr int kLinCtasPerSm = 2;     // K2 __launch_bounds__ occupancy target (255 regs x 128 x 2 = one register file)
 constexpr int kRedChunk = 48;        // accumulators staged per smem reduction round (48 x 128 x 8 B = 48 KB / CTA)
+constexpr int kObsStages = 4;        // cp.async ring depth of K2's observation prefetch (distance 3 iterations)
 constexpr int kFrameConst = 21;      // R(9) t(3) Jl(9) per frame in shared memory
 
 // Observation arrays and per-frame state as the kernels see them.
 struct ProblemDev {
-  const double *x, *y, *z, *u, *v;        // [N] SoA
+  const double *x, *y, *z, *u, *v;        // [N] SoA; when f32 != 0 the arrays hold floats (FeaturePoint is f32, detected_points.rs:6-9)
+  int f32;
   const int32_t* frame_offsets;            // [F+1]
   const int32_t* frame_problem;            // [F] problem of each frame (batch) — nullptr for a single problem
   const int32_t* problem_frame_offsets;    // [n_problems+1]

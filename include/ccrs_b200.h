@@ -68,6 +68,16 @@ int ccrs_problem_create(ccrs_problem** out, int model, int width, int height, in
                         const double* u, const double* v,
                         double huber_delta, int device_id);
 
+/* Same, taking the observations as the f32 values the reference stores (FeaturePoint{p2d: glam::Vec2, p3d: glam::Vec3},
+ * src/detected_points.rs:6-9): half the host->device traffic and half the HBM bytes per observation (20 B). The kernels
+ * widen f32 -> f64 on load exactly like ReprojectionFactor::new (factors.rs:141-143), so results are bit-identical to
+ * ccrs_problem_create on the widened arrays. */
+int ccrs_problem_create_f32(ccrs_problem** out, int model, int width, int height, int xy_same_focal,
+                            int n_frames, const int32_t* frame_offsets,
+                            const float* x, const float* y, const float* z,
+                            const float* u, const float* v,
+                            double huber_delta, int device_id);
+
 /* Batch of independent calibrations in one handle (BASELINE config 5): problem b owns frames
  * [problem_frame_offsets[b], problem_frame_offsets[b+1]). Same model/size/flags for all problems.
  * Intrinsic arrays passed to the calls below are then [n_problems][d]; scalars become [n_problems]. */

@@ -293,3 +293,24 @@ def test_determinism_bitwise(pkg):
         gp.close()
     for a, b in zip(outs[0], outs[1]):
         assert np.array_equal(a, b)
+
+
+def test_f32_observation_api_is_bit_identical(pkg):
+    """ccrs_problem_create_f32: FeaturePoint's f32 values (detected_points.rs:6-9) widened on load (factors.rs:141-143)
+    must give exactly the results of the f64 entry point on the widened arrays."""
+    s = pkg.synth.make_calib("eucm", 120, seed=8, drop_fraction=0.2)
+    g64 = pkg.Problem.from_synth(s)
+    f = lambda a: a.astype(np.float32)
+    assert all(np.array_equal(f(a).astype(np.float64), a) for a in (s.x, s.y, s.z, s.u, s.v))   # f32-representable inputs
+    g32 = pkg.Problem(s.model, s.width, s.height, s.frame_offsets, f(s.x), f(s.y), f(s.z), f(s.u), f(s.v))
+    for g in (g64, g32):
+        g.set_poses(s.init_poses)
+    assert np.array_equal(g64.linearize(s.init_params), g32.linearize(s.init_params))
+    assert np.array_equal(g64.frame_blocks(), g32.frame_blocks())
+    r64, J64 = g64.eval_rj(s.init_params, s.init_poses)
+    r32, J32 = g32.eval_rj(s.init_params, s.init_poses)
+    assert np.array_equal(r64, r32) and np.array_equal(J64, J32)
+    i64, s64, _ = g64.solve_lm(s.init_params)
+    i32, s32, _ = g32.solve_lm(s.init_params)
+    assert np.array_equal(i64, i32) and s64.iterations == s32.iterations
+    g64.close(); g32.close()
