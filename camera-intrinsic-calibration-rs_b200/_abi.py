@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libccrs_b200.so")
+# CCRS_B200_LIB selects another build of the same library (e.g. the `make timing` debug build); never a fallback
+LIB_PATH = os.environ.get("CCRS_B200_LIB") or os.path.join(_HERE, "libccrs_b200.so")
 
 # every symbol include/ccrs_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
@@ -21,7 +22,7 @@ SYMBOLS = [
     "ccrs_comm_unique_id", "ccrs_comm_init", "ccrs_comm_finalize", "ccrs_comm_set_deterministic", "ccrs_default_options",
     "ccrs_solve_gn", "ccrs_solve_lm", "ccrs_controller_gn", "ccrs_controller_lm", "ccrs_calib_camera",
     "ccrs_joint_create", "ccrs_joint_destroy", "ccrs_joint_dim", "ccrs_joint_last_error", "ccrs_joint_launch_count",
-    "ccrs_joint_eval_rj", "ccrs_joint_solve_gn", "ccrs_model_bounds", "ccrs_measure_fp64_peak", "ccrs_time_linearize", "ccrs_bench_lm_steps", "ccrs_launch_count",
+    "ccrs_joint_eval_rj", "ccrs_joint_solve_gn", "ccrs_model_bounds", "ccrs_measure_fp64_peak", "ccrs_time_linearize", "ccrs_bench_lm_steps", "ccrs_launch_count", "ccrs_step_trace",
 ]
 
 STATUS = {0: "CCRS_OK", -1: "CCRS_ERR_INVALID", -2: "CCRS_ERR_CUDA", -3: "CCRS_ERR_NO_DEVICE",

@@ -155,8 +155,7 @@ struct ccrs_problem {
   int device = 0;
   int n_sms = 148;
   cudaStream_t stream = nullptr;
-  int G = 1, FPC = 128, n_lin_ctas = 0, n_schur_ctas = 0;
-  int k2_variant = 0;             // 0 = k_linearize (2 CTAs x 128 threads / SM), 1 = k_linearize_pc (warp-specialised)
+  int G = 1, FPW = 32, n_lin_ctas = 0, n_schur_ctas = 0;
   double huber = 1.0;
   int64_t launches = 0;
 
@@ -164,6 +163,9 @@ struct ccrs_problem {
   DevBuf<int32_t> frame_offsets, frame_problem, problem_frame_offsets, obs_frame, cur, acc_to_blk;
   DevBuf<double> poses[2], blocks[2], frame_cost[2];
   DevBuf<double> elim, frame_red, pose_scale, frame_md, cta_part;
+#ifdef CCRS_K2_TIMING
+  DevBuf<double> k2_dbg;   // [n_warps][10] int64 phase clocks
+#endif
   DevBuf<double> red_out, stat_out, gather, intr_dev, ya_dev, u_dev, scale_dev, l2_flush;
   DevBuf<unsigned char> mask_dev;
   DevBuf<unsigned int> tickets;   // [0] K2 statistics, [1] K3 reduction
@@ -201,28 +203,30 @@ struct ccrs_problem {
 
 namespace {
 
-// Lanes per frame G: the G that minimises (waves of CTAs) x (observations per lane) for this device.
+// Lanes per frame G (1..32; a warp owns 32/G frames): the G that minimises
+// (waves of CTAs) x (observations per lane + per-warp overhead) for this device.
 void choose_slicing(ccrs_problem* p) {
-  const int slots = p->n_sms * (p->k2_variant == 1 ? 1 : kLinCtasPerSm);  // resident CTAs (128 streams each)
+  const int slots = p->n_sms * kLinCtasPerSm;  // resident CTAs (kLinWarps warps each)
   int max_cnt = 1;
   for (int f = 0; f < p->n_frames; ++f) max_cnt = std::max(max_cnt, p->h_frame_offsets[f + 1] - p->h_frame_offsets[f]);
   double best = 1e300;
   int bestG = 1;
-  for (int G = 1; G <= kLinThreads; ++G) {
-    const int fpc = kLinThreads / G;
-    const int ctas = (p->n_frames + fpc - 1) / fpc;
+  for (int G = 1; G <= 32; ++G) {
+    const int fpw = 32 / G;
+    const int warps = (p->n_frames + fpw - 1) / fpw;
+    const int ctas = (warps + kLinWarps - 1) / kLinWarps;
     const int waves = (ctas + slots - 1) / slots;
     const int per_lane = (max_cnt + G - 1) / G;
-    // cost model: per-lane observations dominate; a small per-slice constant covers the basis change + reduction
-    // cost model: per-lane observations dominate; a per-CTA constant covers prologue (pose maths), pipeline fill,
-    // basis change and the shared-memory reduction (measured: ~12 iterations' worth)
-    const double cost = (double)waves * (per_lane + 12.0);
+    // cost model: per-lane observations dominate; a per-warp constant covers prologue (pose maths), pipeline fill,
+    // basis change and the shared-memory reduction (in units of main-loop iterations)
+    const double cost = (double)waves * (per_lane + kLinOverheadIters);
     if (cost < best - 1e-12) { best = cost; bestG = G; }
   }
-  if (const char* e = getenv("CCRS_FORCE_G")) { const int g = atoi(e); if (g >= 1 && g <= kLinThreads) bestG = g; }
+  if (const char* e = getenv("CCRS_FORCE_G")) { const int g = atoi(e); if (g >= 1 && g <= 32) bestG = g; }
   p->G = bestG;
-  p->FPC = kLinThreads / bestG;
-  p->n_lin_ctas = (p->n_frames + p->FPC - 1) / p->FPC;
+  p->FPW = 32 / bestG;
+  const int warps = (p->n_frames + p->FPW - 1) / p->FPW;
+  p->n_lin_ctas = (warps + kLinWarps - 1) / kLinWarps;
 }
 
 int upload_problem(ccrs_problem* p, int n_problems, const int32_t* problem_frame_offsets, int n_frames,
@@ -264,7 +268,7 @@ int upload_problem(ccrs_problem* p, int n_problems, const int32_t* problem_frame
   CK(p->frame_red.alloc(std::max((size_t)p->NRED * Fs, (size_t)p->n_schur_ctas * p->NRED)));
   CK(p->pose_scale.alloc(6 * Fs));
   CK(p->frame_md.alloc(Fs));
-  CK(p->cta_part.alloc((size_t)2 * p->n_lin_ctas));
+  CK(p->cta_part.alloc((size_t)2 * p->n_lin_ctas * kLinWarps));
   CK(p->red_out.alloc(P * p->NRED));
   CK(p->stat_out.alloc(P * 2));
   CK(p->intr_dev.alloc(P * p->D)); CK(p->ya_dev.alloc(P * p->D)); CK(p->u_dev.alloc(P)); CK(p->scale_dev.alloc(P * p->D));
@@ -335,7 +339,6 @@ int create_common(ccrs_problem** out, int model, int width, int height, int xy_s
   ccrs_problem* p = new ccrs_problem();
   p->model = model; p->width = width; p->height = height; p->one_focal = xy_same_focal ? 1 : 0;
   p->huber = huber_delta; p->device = device_id; p->batch = batch; p->n_sms = di.sms; p->f32 = f32;
-  if (const char* e = getenv("CCRS_K2_VARIANT")) p->k2_variant = atoi(e);
   model_dims(model, p->one_focal, &p->D, &p->NA, &p->NBLK, &p->NACC);
   p->NRED = nred_of(p->D);
   p->NOUT = p->D * p->D + 3 * p->D + 1;
@@ -346,6 +349,19 @@ int create_common(ccrs_problem** out, int model, int width, int height, int xy_s
   *out = p;
   return 0;
 }
+
+// Host-side phase trace of the single-problem LM iteration (ccrs_step_trace): where the time between kernels goes.
+//   0 K3 launch call | 1 K3 execution + publish latency (launch return -> sequence number seen) | 2 host: unpack,
+//   d x d solve, trial point | 3 K2 launch call | 4 K2 execution + publish latency | 5 host: accept/reject, bookkeeping
+struct StepTrace {
+  bool on = false;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  long n = 0;
+  double t_mark = 0.0;
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; }
+  void mark(int slot) { if (!on) return; const double t = now(); if (slot >= 0 && t_mark > 0.0) acc[slot] += t - t_mark; t_mark = t; }
+};
+StepTrace g_trace;
 
 // Spin on a sequence number the GPU writes to mapped host memory after its results (kernel-to-host latency of a
 // PCIe write instead of a D2H copy + stream synchronisation). Falls back to the stream status so a failed launch
@@ -445,7 +461,7 @@ int do_linearize(ccrs_problem* p, const double* intr, int which, bool cost_only,
   if (p->pend && (p->pend_in_place ? which != 0 : which != 1)) { int st = flush_pending(p); if (st) return st; }
   LinParams prm{};
   prm.pb = p->dev();
-  prm.which = which; prm.G = p->G; prm.FPC = p->FPC;
+  prm.which = which; prm.G = p->G; prm.FPW = p->FPW;
   prm.acc_to_blk = p->acc_to_blk.p;
   if (p->pend) {
     prm.backsub = p->pend_in_place ? 2 : 1;
@@ -475,8 +491,11 @@ int do_linearize(ccrs_problem* p, const double* intr, int which, bool cost_only,
     prm.host_stat = (publish && !p->comm) ? p->h_stat.p : nullptr;
     if (seq_out) *seq_out = p->seq;
   }
-  if (p->k2_variant == 1 && !cost_only) CK(launch_linearize_pc(p->model, p->one_focal, p->batch, prm, p->n_lin_ctas, p->stream));
-  else CK(launch_linearize(p->model, p->one_focal, p->batch, cost_only, prm, p->n_lin_ctas, p->stream));
+#ifdef CCRS_K2_TIMING
+  if (!p->k2_dbg.p) CK(p->k2_dbg.alloc((size_t)10 * p->n_lin_ctas * kLinWarps));
+  prm.dbg = reinterpret_cast<long long*>(p->k2_dbg.p);
+#endif
+  CK(launch_linearize(p->model, p->one_focal, p->batch, cost_only, prm, p->n_lin_ctas, p->stream));
   p->launches++;
   if (!p->batch && publish && p->comm) {
     int st = exchange(p, p->stat_out.p, 2, p->h_stat.p, p->seq);   // h_stat[0..1] = sums, h_stat[2] = seq
@@ -547,11 +566,15 @@ int do_reduce(ccrs_problem* p, int which, const double* u, int use_scale, double
     p->seq = next_seq();
     prm.seq = p->seq;
     prm.host_red = p->comm ? nullptr : p->h_red.p;
+    g_trace.mark(5);
     CK(launch_schur(D, prm, p->stream));
     p->launches++;
     if (p->comm) { st = exchange(p, p->red_out.p, (size_t)p->NRED, p->h_red.p, p->seq); if (st) return st; }
+    g_trace.mark(0);
     st = wait_seq(p, p->h_red.p + p->NRED, p->seq);
     if (st) return st;
+    g_trace.mark(1);
+    if (g_trace.on) g_trace.n++;
   }
   // unpack: packed upper S -> full row-major
   const int NS = D * (D + 1) / 2;
@@ -581,9 +604,13 @@ int be_backsub(void* ctx, const double* y_a, const double* u, const unsigned cha
 int be_trial_stats(void* ctx, const double* intr_trial, int speculative, double* out) {
   ccrs_problem* p = (ccrs_problem*)ctx;
   double seq = 0.0;
+  g_trace.mark(2);
   int st = do_linearize(p, intr_trial, 1, !speculative, true, &seq);
   if (st) return st;
-  return fetch_stats(p, speculative ? 1 : 0, seq, out);
+  g_trace.mark(3);
+  st = fetch_stats(p, speculative ? 1 : 0, seq, out);
+  g_trace.mark(4);
+  return st;
 }
 int be_accept(void* ctx, const unsigned char* mask) { return ccrs_accept((ccrs_problem*)ctx, mask); }
 
@@ -669,6 +696,25 @@ int ccrs_problem_n_frames(const ccrs_problem* p) { return p ? p->n_frames : -1; 
 int64_t ccrs_problem_n_obs(const ccrs_problem* p) { return p ? p->n_obs : -1; }
 int ccrs_problem_n_problems(const ccrs_problem* p) { return p ? p->n_problems : -1; }
 int64_t ccrs_launch_count(const ccrs_problem* p) { return p ? p->launches : -1; }
+
+int ccrs_step_trace(int enable, double* avg_us /* [6] or NULL */, int64_t* n_iterations) {
+  if (avg_us) for (int i = 0; i < 6; ++i) avg_us[i] = g_trace.n ? g_trace.acc[i] / g_trace.n : 0.0;
+  if (n_iterations) *n_iterations = g_trace.n;
+  g_trace = StepTrace{};
+  g_trace.on = enable != 0;
+  return 0;
+}
+
+#ifdef CCRS_K2_TIMING
+// debug builds only (make timing): per-warp phase clocks of the last K2 launch, [n_warps][10] int64
+extern "C" int ccrs_debug_k2_timing(ccrs_problem* p, long long* out, int cap_warps) {
+  if (!p || !p->k2_dbg.p) return -1;
+  const int nw = p->n_lin_ctas * kLinWarps;
+  cudaStreamSynchronize(p->stream);
+  cudaMemcpy(out, p->k2_dbg.p, (size_t)10 * std::min(nw, cap_warps) * sizeof(long long), cudaMemcpyDeviceToHost);
+  return nw;
+}
+#endif
 
 int ccrs_set_poses(ccrs_problem* p, const double* poses) {
   if (!p || !poses) return fail(CCRS_ERR_INVALID, "null");

@@ -78,6 +78,38 @@ CCRS_HD void pose_from_rvec_tvec(const double* rt, FramePose& fp) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Branch-free FP64 reciprocal / rsqrt / sqrt for operands known to be normal, finite and positive (depths,
+// norms, squared residuals above the Huber threshold). CUDA's `1.0/x`, `rsqrt`, `sqrt` wrap the same MUFU seed in a
+// special-case test plus a slow-path call, which splits the observation loop into many basic blocks and stops
+// ptxas from overlapping the dependent model chain with the independent Gram-block DFMAs. These are single
+// straight-line sequences (MUFU seed, relative error 2^-22, one cubically convergent step, one correction):
+// error <= ~1 ulp.
+// ---------------------------------------------------------------------------------------------
+CCRS_D double rcp_fast(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  e = fma(e, e, e);          // e + e^2  ->  y (1 + e + e^2) = (1/x)(1 - e^3)
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);       // correction step
+  return fma(y, e, y);
+}
+CCRS_D double rsqrt_fast(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double t = x * y;
+  const double e = fma(-t, y, 1.0);            // 1 - x y^2
+  const double p = fma(0.375, e, 0.5) * e;     // e/2 + 3 e^2/8  ->  error O(e^3)
+  return fma(y, p, y);
+}
+CCRS_D double sqrt_fast(double x) {
+  const double y = rsqrt_fast(x);
+  const double s = x * y;
+  const double r = fma(-s, s, x);              // one Newton correction of s ~ sqrt(x)
+  return fma(r, 0.5 * y, s);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Camera models. k = distortion parameters (params[4..]). WITH_J selects value-only evaluation.
 // Outputs: m[2]; dP[2][3] = dm/dP; dk[2][ND] = dm/dk.
 // ---------------------------------------------------------------------------------------------
@@ -89,11 +121,11 @@ CCRS_D void model_eval(const double* __restrict__ k, double x, double y, double 
     const double beta = (MODEL == UCM) ? 1.0 : k[1];
     const double r2 = x * x + y * y;
     const double rho2 = fma(beta, r2, z * z);
-    const double irho = rsqrt(rho2);
+    const double irho = rsqrt_fast(rho2);
     const double rho = rho2 * irho;
     const double oma = 1.0 - alpha;
     const double nrm = fma(alpha, rho, oma * z);
-    const double in = 1.0 / nrm;
+    const double in = rcp_fast(nrm);
     double mx = x * in, my = y * in;
     if constexpr (!WITH_J) {
       if constexpr (MODEL == EUCMT) {
@@ -185,7 +217,7 @@ CCRS_D void model_eval(const double* __restrict__ k, double x, double y, double 
     }
   } else {  // OPENCV5: k = k1 k2 p1 p2 k3
     const double k1 = k[0], k2 = k[1], p1 = k[2], p2 = k[3], k3 = k[4];
-    const double iz = 1.0 / z;
+    const double iz = rcp_fast(z);
     const double a = x * iz, b = y * iz;
     const double a2 = a * a, b2 = b * b, ab = a * b;
     const double r2 = a2 + b2;
@@ -207,10 +239,12 @@ CCRS_D void model_eval(const double* __restrict__ k, double x, double y, double 
 }
 
 // Huber corrector (tiny-solver Corrector with HuberLoss, reference util.rs:413): sqrt(rho'(s)).
+// Branch-free: the weight is always evaluated (on a safe operand) and selected.
 CCRS_D double huber_weight(double s, double delta) {
-  double w = 1.0;
-  if (delta > 0.0 && s > delta * delta) w = sqrt(delta * rsqrt(s));
-  return w;
+  const bool out = delta > 0.0 && s > delta * delta;
+  const double sc = out ? s : 1.0;
+  const double w = sqrt_fast(delta * rsqrt_fast(sc));
+  return out ? w : 1.0;
 }
 
 }  // namespace ccrs

@@ -130,85 +130,147 @@ CCRS_D double obs_rows(const double* __restrict__ ip /* full intrinsics */, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2 / K5. One CTA owns FPC consecutive frames; G lanes cooperate on a frame, lane j taking observations
-// j, j+G, ... (so the G lanes read G consecutive doubles of each SoA array: coalesced, no reliance on L1).
-// Every lane keeps the whole packed Gram block of its slice in registers (NACC FP64 accumulators), rotates it
-// from the local rotation basis to the rvec basis once (J_l), then the slices of a frame are summed in lane
-// order through shared memory and the frame block is written SoA to HBM.
+// K2 / K5. Warp-autonomous: warp w of the grid owns FPW = 32/G consecutive frames; G lanes cooperate on a frame,
+// lane j taking observations j, j+G, ... (so the G lanes read G consecutive doubles of each SoA array: coalesced,
+// no reliance on L1). Every lane keeps the whole packed Gram block of its slice in registers (NACC FP64
+// accumulators), rotates it from the local rotation basis to the rvec basis once (J_l), then the slices of a
+// frame are summed in lane order through the warp's own shared memory and the frame block is written SoA to HBM.
+// No CTA-wide barrier anywhere: prologue (fused K4 + pose exponential), main loop and reduction of one warp
+// overlap with whatever phase the other resident warps are in.
 // ------------------------------------------------------------------------------------------------
+constexpr int kRedStride = 33;    // row stride of the reduction staging buffer (odd: no bank conflicts)
+constexpr int kA2bDoubles = 72;   // per-warp copy of the accumulator -> block-entry table (<= 144 int32)
+CCRS_HD constexpr int lin_warp_smem_doubles(int FPW, bool batch, bool cost_only) {
+  return FPW * kFrameConst + (batch ? FPW * kMaxFull : 0) + 2 * FPW + (cost_only ? 32 : kRedChunk * kRedStride) +
+         kObsStages * 5 * 32 + kA2bDoubles;
+}
+
 template <int MODEL, bool OF, bool BATCH, bool COST_ONLY>
 __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const __grid_constant__ LinParams prm) {
   using C = Cfg<MODEL, OF>;
   extern __shared__ double smem[];
   const ProblemDev& pb = prm.pb;
-  const int t = threadIdx.x;
-  const int G = prm.G, FPC = prm.FPC;
-  const int f0 = blockIdx.x * FPC;
-  const int nf = min(FPC, pb.n_frames - f0);
-  double* s_fc = smem;                                   // [FPC][kFrameConst]
-  double* s_intr = s_fc + FPC * kFrameConst;             // [FPC][kMaxFull]   (BATCH only)
-  double* s_red = s_intr + (BATCH ? FPC * kMaxFull : 0); // [kRedChunk][kLinThreads]
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = prm.G, FPW = prm.FPW;
+  const int gw = blockIdx.x * kLinWarps + wid;          // warp index in the grid
+  const int f0 = gw * FPW;
+  const int nf = max(0, min(FPW, pb.n_frames - f0));    // frames of this warp
+  double* s_fc = smem + (size_t)wid * lin_warp_smem_doubles(FPW, BATCH, COST_ONLY);  // [FPW][kFrameConst]
+  double* s_intr = s_fc + FPW * kFrameConst;             // [FPW][kMaxFull]   (BATCH only)
+  double* s_stat = s_intr + (BATCH ? FPW * kMaxFull : 0);  // [2][FPW] per-frame md, cost
+  double* s_red = s_stat + 2 * FPW;                      // [kRedChunk][kRedStride]
+  double* s_obs = s_red + (COST_ONLY ? 32 : kRedChunk * kRedStride);  // [kObsStages][5][32] cp.async ring of x,y,z,u,v
+  int* s_a2b = reinterpret_cast<int*>(s_obs + kObsStages * 5 * 32);  // [NACC] accumulator -> packed block entry
+  if constexpr (!COST_ONLY) {
+    for (int i = lane; i < C::NACC; i += 32) s_a2b[i] = __ldg(prm.acc_to_blk + i);   // visible after the prologue's __syncwarp
+  }
 
-  double* s_stat = s_red + (COST_ONLY ? kLinThreads : kRedChunk * kLinThreads);  // [2][FPC] per-frame md, cost
-  double* s_obs = s_stat + 2 * FPC;                      // [kObsStages][5][kLinThreads] cp.async ring of x,y,z,u,v
+#ifdef CCRS_K2_TIMING
+  long long tck[6];
+  unsigned long long gt0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
+  tck[0] = clock64();
+#define CCRS_TCK(i) tck[i] = clock64()
+#else
+#define CCRS_TCK(i)
+#endif
+  const int fl = lane / G;            // frame of this lane within the warp
+  const int sl = lane - fl * G;       // slice of the frame
+  const bool active = fl < nf;
+  const int f = f0 + (active ? fl : 0);
 
-  if (t < nf) {
-    const int f = f0 + t;
+  // Observations are prefetched kObsStages-1 iterations ahead with 8-byte cp.async into a per-thread shared-memory
+  // ring (each thread reads back only what it fetched: no barrier), so neither DRAM nor L2 latency sits at the
+  // top of an iteration. The first stages are issued before the pose prologue so their latency overlaps it.
+  const int end = active ? pb.frame_offsets[f + 1] : 0;
+  const int beg = active ? pb.frame_offsets[f] + sl : 0;
+  double* ring = s_obs + lane;
+  auto fetch = [&](int kk, int stage) {
+    if (kk < end) {
+      double* dst = ring + stage * (5 * 32);
+      if (pb.f32) {
+        const float *fx = (const float*)pb.x, *fy = (const float*)pb.y, *fz = (const float*)pb.z, *fu = (const float*)pb.u, *fv = (const float*)pb.v;
+        cp_async4(dst, fx + kk); cp_async4(dst + 32, fy + kk); cp_async4(dst + 64, fz + kk);
+        cp_async4(dst + 96, fu + kk); cp_async4(dst + 128, fv + kk);
+      } else {
+        cp_async8(dst, pb.x + kk); cp_async8(dst + 32, pb.y + kk); cp_async8(dst + 64, pb.z + kk);
+        cp_async8(dst + 96, pb.u + kk); cp_async8(dst + 128, pb.v + kk);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int i = 0; i < kObsStages - 1; ++i) fetch(beg + i * G, i);
+
+  // ---- prologue: every lane of a frame evaluates the frame's pose redundantly (same addresses: broadcast loads);
+  //      slice 0 stores. Fused K4: y_p = cg - X y_a ; pose += D_p y_p ; model decrease y_p^T g'_p + u sum dd_i y_p,i^2
+  double md = 0.0;   // model decrease of this lane's frame (same value in all lanes of the frame)
+  if (active) {
     const int prob = BATCH ? pb.frame_problem[f] : 0;
     const int cur = cur_of(pb, prob);
     double rt[6];
-    double md = 0.0;
     if (prm.backsub) {
-      // fused K4: y_p = cg - X y_a ; pose += D_p y_p ; model decrease y_p^T g'_p + u * sum dd_i y_p,i^2
       const double* src = pb.poses[cur] + 6 * (size_t)f;
       double* dst = pb.poses[prm.backsub == 2 ? cur : (cur ^ 1)] + 6 * (size_t)f;
       const bool moves = !(BATCH && prm.active && !prm.active[prob]);
-      const double* ya = BATCH ? prm.ya_dev + (size_t)prob * C::D : prm.y_a;
-      const double u = BATCH ? (prm.u_dev ? prm.u_dev[prob] : 0.0) : prm.u;
-      const double* el = prm.elim + f;
-      const size_t Fs = pb.Fs;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        double v = src[i];
-        if (moves) {
-          double yp = el[(size_t)(6 * C::D + i) * Fs];
+      for (int i = 0; i < 6; ++i) rt[i] = src[i];
+      if (moves) {
+        const double* ya = BATCH ? prm.ya_dev + (size_t)prob * C::D : prm.y_a;
+        const double u = BATCH ? (prm.u_dev ? prm.u_dev[prob] : 0.0) : prm.u;
+        const double* el = prm.elim + f;
+        const size_t Fs = pb.Fs;
+        // all loads first (read-only path: none of them can alias the pose store below)
+        double X[6][C::D], cg[6], gp[6], dd[6], sp[6];
 #pragma unroll
-          for (int a = 0; a < C::D; ++a) yp -= el[(size_t)(i * C::D + a) * Fs] * ya[a];
-          const double sp = prm.pose_scale ? prm.pose_scale[(size_t)i * Fs + f] : 1.0;
-          v += sp * yp;
-          md += yp * el[(size_t)(6 * C::D + 6 + i) * Fs] + u * el[(size_t)(6 * C::D + 12 + i) * Fs] * yp * yp;
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+          for (int a = 0; a < C::D; ++a) X[i][a] = __ldg(el + (size_t)(i * C::D + a) * Fs);
+          cg[i] = __ldg(el + (size_t)(6 * C::D + i) * Fs);
+          gp[i] = __ldg(el + (size_t)(6 * C::D + 6 + i) * Fs);
+          dd[i] = __ldg(el + (size_t)(6 * C::D + 12 + i) * Fs);
+          sp[i] = prm.pose_scale ? __ldg(prm.pose_scale + (size_t)i * Fs + f) : 1.0;
         }
-        rt[i] = v;
-        dst[i] = v;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          double yp = cg[i];
+#pragma unroll
+          for (int a = 0; a < C::D; ++a) yp -= X[i][a] * ya[a];
+          rt[i] += sp[i] * yp;
+          md += yp * gp[i] + u * dd[i] * yp * yp;
+        }
       }
-      if (BATCH && prm.frame_md) prm.frame_md[f] = md;
+      if (sl == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) dst[i] = rt[i];
+        if (BATCH && prm.frame_md) prm.frame_md[f] = md;
+      }
     } else {
       const double* src = pb.poses[cur ^ prm.which] + 6 * (size_t)f;
 #pragma unroll
       for (int i = 0; i < 6; ++i) rt[i] = src[i];
     }
-    s_stat[t] = md;
     FramePose fp;
     pose_from_rvec_tvec(rt, fp);
-    double* o = s_fc + t * kFrameConst;
+    if (sl == 0) {
+      double* o = s_fc + fl * kFrameConst;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) o[i] = fp.R[i];
+      for (int i = 0; i < 9; ++i) o[i] = fp.R[i];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) o[9 + i] = fp.t[i];
+      for (int i = 0; i < 3; ++i) o[9 + i] = fp.t[i];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) o[12 + i] = fp.Jl[i];
-    if constexpr (BATCH) {
-      const double* a = prm.intr_dev + (size_t)prob * C::D;
-      double* si = s_intr + t * kMaxFull;
-      if constexpr (OF) { si[0] = a[0]; si[1] = a[0]; for (int i = 1; i < C::D; ++i) si[i + 1] = a[i]; }
-      else { for (int i = 0; i < C::D; ++i) si[i] = a[i]; }
+      for (int i = 0; i < 9; ++i) o[12 + i] = fp.Jl[i];
+      if constexpr (BATCH) {
+        const double* a = prm.intr_dev + (size_t)prob * C::D;
+        double* si = s_intr + fl * kMaxFull;
+        if constexpr (OF) { si[0] = a[0]; si[1] = a[0]; for (int i = 1; i < C::D; ++i) si[i + 1] = a[i]; }
+        else { for (int i = 0; i < C::D; ++i) si[i] = a[i]; }
+      }
     }
   }
-  __syncthreads();
+  __syncwarp();
+  CCRS_TCK(1);
 
-  const int fl = t / G;
-  const int lane = t - fl * G;
-  const bool active = fl < nf;
   const double* ip = BATCH ? (s_intr + (active ? fl : 0) * kMaxFull) : prm.intr;
   const double* fc = s_fc + (active ? fl : 0) * kFrameConst;
 
@@ -217,46 +279,29 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   for (int i = 0; i < (COST_ONLY ? 1 : C::NACC); ++i) acc[i] = 0.0;
 
   if (active) {
-    const int f = f0 + fl;
-    const int end = pb.frame_offsets[f + 1];
-    const int beg = pb.frame_offsets[f] + lane;
-    // Observations are prefetched kObsStages-1 iterations ahead with 8-byte cp.async into a per-thread shared-memory
-    // ring (each thread reads back only what it fetched: no barrier), so neither DRAM nor L2 latency sits at the
-    // top of an iteration.
-    double* ring = s_obs + t;
-    auto fetch = [&](int kk, int stage) {
-      if (kk < end) {
-        double* dst = ring + stage * (5 * kLinThreads);
-        if (pb.f32) {
-          const float *fx = (const float*)pb.x, *fy = (const float*)pb.y, *fz = (const float*)pb.z, *fu = (const float*)pb.u, *fv = (const float*)pb.v;
-          cp_async4(dst, fx + kk); cp_async4(dst + kLinThreads, fy + kk); cp_async4(dst + 2 * kLinThreads, fz + kk);
-          cp_async4(dst + 3 * kLinThreads, fu + kk); cp_async4(dst + 4 * kLinThreads, fv + kk);
-        } else {
-          cp_async8(dst, pb.x + kk); cp_async8(dst + kLinThreads, pb.y + kk); cp_async8(dst + 2 * kLinThreads, pb.z + kk);
-          cp_async8(dst + 3 * kLinThreads, pb.u + kk); cp_async8(dst + 4 * kLinThreads, pb.v + kk);
-        }
-      }
-      cp_async_commit();
+    const int f32 = pb.f32;
+    // rows of [J | r] for the observation in ring slot `stage` (branch-free: both widths are read and selected)
+    auto rows_of = [&](int stage, double* __restrict__ au, double* __restrict__ av) -> double {
+      const double* src = ring + stage * (5 * 32);
+      const double px = f32 ? (double)*(const float*)(src) : src[0];
+      const double py = f32 ? (double)*(const float*)(src + 32) : src[32];
+      const double pz = f32 ? (double)*(const float*)(src + 64) : src[64];
+      const double ou = f32 ? (double)*(const float*)(src + 96) : src[96];
+      const double ov = f32 ? (double)*(const float*)(src + 128) : src[128];
+      return obs_rows<MODEL, OF, !COST_ONLY>(ip, fc, px, py, pz, ou, ov, pb.huber_delta, au, av);
     };
-#pragma unroll
-    for (int i = 0; i < kObsStages - 1; ++i) fetch(beg + i * G, i);
-    int it = 0;
-    for (int k = beg; k < end; k += G, ++it) {
-      fetch(k + (kObsStages - 1) * G, (it + kObsStages - 1) % kObsStages);
-      cp_async_wait<kObsStages - 1>();
-      const double* src = ring + (it % kObsStages) * (5 * kLinThreads);
-      double px, py, pz, ou, ov;
-      if (pb.f32) {
-        px = *(const float*)(src); py = *(const float*)(src + kLinThreads); pz = *(const float*)(src + 2 * kLinThreads);
-        ou = *(const float*)(src + 3 * kLinThreads); ov = *(const float*)(src + 4 * kLinThreads);
-      } else {
-        px = src[0]; py = src[kLinThreads]; pz = src[2 * kLinThreads]; ou = src[3 * kLinThreads]; ov = src[4 * kLinThreads];
+    if constexpr (COST_ONLY) {
+      int it = 0;
+      for (int k = beg; k < end; k += G, ++it) {
+        fetch(k + (kObsStages - 1) * G, (it + kObsStages - 1) % kObsStages);
+        cp_async_wait<kObsStages - 1>();
+        acc[0] += rows_of(it % kObsStages, nullptr, nullptr);
       }
-      double au[C::NA], av[C::NA];
-      const double c = obs_rows<MODEL, OF, !COST_ONLY>(ip, fc, px, py, pz, ou, ov, pb.huber_delta, au, av);
-      if constexpr (COST_ONLY) {
-        acc[0] += c;
-      } else {
+    } else {
+      // Software-pipelined by hand: the model chain of observation i+1 (rsqrt -> reciprocal -> Huber, one long
+      // dependent sequence) is issued in the same basic block as the NACC independent DFMAs that accumulate
+      // observation i, so ptxas interleaves them and the FP64 pipe stays busy with two warps per sub-partition.
+      auto accumulate = [&](const double* __restrict__ au, const double* __restrict__ av) {
         static_for<0, C::NA>([&](auto I) {
           static_for<decltype(I)::value, C::NA>([&](auto J) {
             constexpr int i = decltype(I)::value, j = decltype(J)::value;
@@ -267,8 +312,30 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
             }
           });
         });
+      };
+      if (beg < end) {
+        double au0[C::NA], av0[C::NA], au1[C::NA], av1[C::NA];
+        cp_async_wait<kObsStages - 2>();
+        rows_of(0, au0, av0);
+        int it = 0, k = beg;
+        while (true) {
+          // slot (it+1) holds observation i+1 — or stale data when the slice is exhausted (result discarded)
+          fetch(k + (kObsStages - 1) * G, (it + kObsStages - 1) % kObsStages);
+          cp_async_wait<kObsStages - 2>();
+          rows_of((it + 1) % kObsStages, au1, av1);
+          accumulate(au0, av0);
+          k += G; ++it;
+          if (k >= end) break;
+          fetch(k + (kObsStages - 1) * G, (it + kObsStages - 1) % kObsStages);
+          cp_async_wait<kObsStages - 2>();
+          rows_of((it + 1) % kObsStages, au0, av0);
+          accumulate(au1, av1);
+          k += G; ++it;
+          if (k >= end) break;
+        }
       }
     }
+    CCRS_TCK(2);
     if constexpr (!COST_ONLY) {
       // basis change phi -> rvec on this slice's block: H <- T^T H T, T = blkdiag(I_D, J_l, I_3, 1)
       const double* Jl = fc + 12;
@@ -302,391 +369,124 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
     }
   }
 
-  // ---- sum the G slices of each frame in lane order (fixed order -> deterministic) and store SoA ----
+  CCRS_TCK(3);
+  // ---- frame cost = sum over the frame's slices of the (r,r) entry, in slice order (the same order as the block
+  //      reduction below, so it equals the stored entry bit for bit); shuffles: the G lanes of a frame are adjacent
+  double fcost;
+  {
+    const double v = active ? acc[COST_ONLY ? 0 : C::NACC - 1] : 0.0;
+    fcost = v;
+    for (int j = 1; j < G; ++j) fcost += __shfl_down_sync(0xffffffffu, v, j);   // valid in slice 0 of each frame
+  }
+  // ---- fused statistics (single problem): {model decrease, cost} summed over frames in a fixed order: per-warp
+  //      partials in frame order, published with a release-atomic ticket BEFORE the block reduction so the atomic's
+  //      round trip overlaps it; the last warp to take a ticket sums the warp partials (fixed tree) at the very end.
+  unsigned ticket_old = 0;
+  const unsigned n_warps = gridDim.x * kLinWarps;
+  if constexpr (!BATCH) {
+    double wmd = 0.0, wcost = 0.0;
+    for (int i = 0; i < nf; ++i) {
+      wmd += __shfl_sync(0xffffffffu, md, i * G);
+      wcost += __shfl_sync(0xffffffffu, fcost, i * G);
+    }
+    if (lane == 0) {
+      prm.cta_part[2 * gw] = wmd;
+      prm.cta_part[2 * gw + 1] = wcost;
+      asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(ticket_old) : "l"(prm.ticket) : "memory");
+    }
+  }
+
+  // ---- sum the G slices of each frame in slice order (fixed order -> deterministic) and store SoA ----
   if constexpr (COST_ONLY) {
-    s_red[t] = acc[0];
-    __syncthreads();
-    if (t < nf) {
-      double s = 0.0;
-      for (int j = 0; j < G; ++j) s += s_red[t * G + j];
-      const int f = f0 + t;
+    if (active && sl == 0) {
       const int prob = BATCH ? pb.frame_problem[f] : 0;
-      pb.frame_cost[cur_of(pb, prob) ^ prm.which][f] = s;
-      s_stat[FPC + t] = s;
+      pb.frame_cost[cur_of(pb, prob) ^ prm.which][f] = fcost;
     }
   } else {
     constexpr int NCH = (C::NACC + kRedChunk - 1) / kRedChunk;
+    // Staged through the warp's shared memory in chunks of kRedChunk entries, rows padded to kRedStride doubles
+    // (bank-conflict-free both ways). Lane (fl, sl) then sums, for its own frame, the entries e = sl, sl+G, ... over
+    // the frame's G slices in slice order and stores them: every lane of the frame works, the six lanes that hold
+    // the same entry of consecutive frames store consecutive doubles.
+    double* const out = pb.blocks[(BATCH ? (active ? cur_of(pb, pb.frame_problem[f]) : 0) : cur_of(pb, 0)) ^ prm.which] + f;
+    const double* const srow = s_red + fl * G;
     static_for<0, NCH>([&](auto CH) {
       constexpr int ch = decltype(CH)::value;
       constexpr int cnt = (C::NACC - ch * kRedChunk) < kRedChunk ? (C::NACC - ch * kRedChunk) : kRedChunk;
-      if (ch > 0) __syncthreads();
+      if (ch > 0) __syncwarp();
       if (active) {
         static_for<0, cnt>([&](auto E) {
           constexpr int e = decltype(E)::value;
-          s_red[e * kLinThreads + t] = acc[ch * kRedChunk + e];
+          s_red[e * kRedStride + lane] = acc[ch * kRedChunk + e];
         });
       }
-      __syncthreads();
-      for (int o = t; o < cnt * nf; o += kLinThreads) {
-        const int e = o / nf, ff = o - e * nf;
-        const double* src = s_red + e * kLinThreads + ff * G;
-        double s = 0.0;
-        for (int j = 0; j < G; ++j) s += src[j];
-        const int f = f0 + ff;
-        const int prob = BATCH ? pb.frame_problem[f] : 0;
-        double* out = pb.blocks[cur_of(pb, prob) ^ prm.which];
-        out[(size_t)prm.acc_to_blk[ch * kRedChunk + e] * pb.Fs + f] = s;
-        if (ch * kRedChunk + e == C::NACC - 1) s_stat[FPC + ff] = s;   // (r,r) entry = the frame's corrected cost
-      }
-    });
-  }
-
-  // ---- fused statistics (single problem): {model decrease, cost} summed over frames in a fixed order ----
-  if constexpr (!BATCH) {
-    __shared__ int s_last;
-    __syncthreads();
-    if (t == 0) {
-      double md = 0.0, cost = 0.0;
-      for (int i = 0; i < nf; ++i) { md += s_stat[i]; cost += s_stat[FPC + i]; }
-      prm.cta_part[2 * blockIdx.x] = md;
-      prm.cta_part[2 * blockIdx.x + 1] = cost;
-      __threadfence();
-      s_last = (atomicAdd(prm.ticket, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (s_last) {  // last CTA to finish: sum the CTA partials in CTA order (64 strided lanes x 2 values, fixed tree)
-      __threadfence();
-      double* sh = s_red;
-      const int v = t & 1, lane2 = t >> 1;   // 64 lanes per value
-      double a = 0.0;
-      for (int b = lane2; b < (int)gridDim.x; b += kLinThreads / 2) a += __ldcg(prm.cta_part + 2 * b + v);
-      sh[t] = a;
-      __syncthreads();
-      for (int w = kLinThreads / 2; w >= 2; w >>= 1) {
-        if (t < w) sh[t] += sh[t + w];
-        __syncthreads();
-      }
-      if (t == 0) {
-        prm.stat_dev[0] = sh[0]; prm.stat_dev[1] = sh[1];
-        *prm.ticket = 0u;
-        if (prm.host_stat) { double tmp[3] = {sh[0], sh[1], 0.0}; publish_host(prm.host_stat, tmp, 3, prm.seq); }
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K2, warp-specialised variant ("PC": producers / consumers). One CTA of 384 threads per SM:
-//   warps 0-3  consumers  (one per SM sub-partition): own the NACC FP64 accumulators of 32 observation streams each
-//                         and do nothing but LDS + independent DFMAs — a steady stream that keeps the FP64 pipe busy;
-//   warps 4-11 producers  (two per sub-partition): evaluate pose transform, camera model, analytic Jacobian factors
-//                         and the Huber weight (long dependent chains: rsqrt, reciprocal) for the same streams, one
-//                         iteration ahead, and hand NV = 14 + 2 ND factors per observation over through a shared
-//                         memory ring guarded by mbarriers (full/empty per slot and consumer warp).
-// setmaxnreg moves registers from the producers (128) to the consumers (240), so the whole packed Gram block of a
-// stream stays in registers while 12 warps are resident instead of 8. Same stream decomposition, same summation
-// order and same outputs as k_linearize.
-// ------------------------------------------------------------------------------------------------
-constexpr int kPcThreads = 384;
-constexpr int kPcStreams = 128;
-constexpr int kPcSlots = 4;
-
-CCRS_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-CCRS_D void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-CCRS_D void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-CCRS_D void mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-
-template <int MODEL, bool OF>
-struct PcCfg {
-  using C = Cfg<MODEL, OF>;
-  static constexpr int NV = 14 + 2 * C::ND;   // w*mx, w*my, w, dk_u[ND], dk_v[ND], du[3], dv[3], q[3], w*ru, w*rv
-  static constexpr int I_DKU = 3, I_DKV = 3 + C::ND, I_DU = 3 + 2 * C::ND, I_DV = I_DU + 3, I_Q = I_DU + 6, I_R = I_DU + 9;
-};
-
-template <int MODEL, bool OF, bool BATCH>
-__global__ void __launch_bounds__(kPcThreads, 1) k_linearize_pc(const __grid_constant__ LinParams prm) {
-  using C = Cfg<MODEL, OF>;
-  using P = PcCfg<MODEL, OF>;
-  extern __shared__ double smem[];
-  const ProblemDev& pb = prm.pb;
-  const int t = threadIdx.x;
-  const int G = prm.G, FPC = prm.FPC;
-  const int f0 = blockIdx.x * FPC;
-  const int nf = min(FPC, pb.n_frames - f0);
-  // shared memory carve-up
-  double* s_fc = smem;                                          // [FPC][kFrameConst]
-  double* s_intr = s_fc + FPC * kFrameConst;                    // [FPC][kMaxFull] (BATCH)
-  double* s_stat = s_intr + (BATCH ? FPC * kMaxFull : 0);       // [2][FPC]
-  unsigned long long* s_bar = (unsigned long long*)(s_stat + 2 * FPC);   // full[kPcSlots][4], empty[kPcSlots][4]
-  int* s_misc = (int*)(s_bar + 2 * kPcSlots * 4);               // [0] n_iter, [1] last-CTA flag
-  double* s_ring = (double*)(s_misc + 4);                       // [kPcSlots][NV][128]; later [NACC][128]
-
-  if (t == 0) {
-    s_misc[0] = 0;
-    for (int i = 0; i < 2 * kPcSlots * 4; ++i) mbar_init(s_bar + i, 32);
-  }
-  __syncthreads();
-  if (t < nf) {
-    const int f = f0 + t;
-    const int prob = BATCH ? pb.frame_problem[f] : 0;
-    const int cur = cur_of(pb, prob);
-    double rt[6];
-    double md = 0.0;
-    if (prm.backsub) {
-      const double* src = pb.poses[cur] + 6 * (size_t)f;
-      double* dst = pb.poses[prm.backsub == 2 ? cur : (cur ^ 1)] + 6 * (size_t)f;
-      const bool moves = !(BATCH && prm.active && !prm.active[prob]);
-      const double* ya = BATCH ? prm.ya_dev + (size_t)prob * C::D : prm.y_a;
-      const double u = BATCH ? (prm.u_dev ? prm.u_dev[prob] : 0.0) : prm.u;
-      const double* el = prm.elim + f;
-      const size_t Fs = pb.Fs;
+      __syncwarp();
+      // the slice count is one of the ten values choose_slicing() can pick: fully unrolled sums, no inner branches
+      auto store_rounds = [&](auto GG) {
+        constexpr int g = decltype(GG)::value;
+        if (active) {
+#pragma unroll 2
+          for (int e = sl; e < cnt; e += (g > 0 ? g : G)) {
+            const double* src = srow + e * kRedStride;
+            double s = src[0];
+            if constexpr (g > 0) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        double v = src[i];
-        if (moves) {
-          double yp = el[(size_t)(6 * C::D + i) * Fs];
-#pragma unroll
-          for (int a = 0; a < C::D; ++a) yp -= el[(size_t)(i * C::D + a) * Fs] * ya[a];
-          const double sp = prm.pose_scale ? prm.pose_scale[(size_t)i * Fs + f] : 1.0;
-          v += sp * yp;
-          md += yp * el[(size_t)(6 * C::D + 6 + i) * Fs] + u * el[(size_t)(6 * C::D + 12 + i) * Fs] * yp * yp;
-        }
-        rt[i] = v;
-        dst[i] = v;
-      }
-      if (BATCH && prm.frame_md) prm.frame_md[f] = md;
-    } else {
-      const double* src = pb.poses[cur ^ prm.which] + 6 * (size_t)f;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) rt[i] = src[i];
-    }
-    s_stat[t] = md;
-    FramePose fp;
-    pose_from_rvec_tvec(rt, fp);
-    double* o = s_fc + t * kFrameConst;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) o[i] = fp.R[i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) o[9 + i] = fp.t[i];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) o[12 + i] = fp.Jl[i];
-    if constexpr (BATCH) {
-      const double* a = prm.intr_dev + (size_t)prob * C::D;
-      double* si = s_intr + t * kMaxFull;
-      if constexpr (OF) { si[0] = a[0]; si[1] = a[0]; for (int i = 1; i < C::D; ++i) si[i + 1] = a[i]; }
-      else { for (int i = 0; i < C::D; ++i) si[i] = a[i]; }
-    }
-    const int cnt = pb.frame_offsets[f + 1] - pb.frame_offsets[f];
-    atomicMax(&s_misc[0], (cnt + G - 1) / G);
-  }
-  __syncthreads();
-  const int n_iter = s_misc[0];
-  const int warp = t >> 5;
-
-  if (warp >= 4) {
-    // =============================== producers ===============================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 128;\n");
-    const int pt = t - kPcStreams;
-    const int pg = pt / kPcStreams;            // producer group 0/1: even / odd iterations
-    const int sidx = pt - pg * kPcStreams;     // stream
-    const int cw = sidx >> 5;                  // consumer warp served
-    const int fl = sidx / G;
-    const int lane = sidx - fl * G;
-    const bool active = fl < nf;
-    const double* ip = BATCH ? (s_intr + (active ? fl : 0) * kMaxFull) : prm.intr;
-    const double* fc = s_fc + (active ? fl : 0) * kFrameConst;
-    const int f = f0 + (active ? fl : 0);
-    const int beg = pb.frame_offsets[f] + lane;
-    const int end = active ? pb.frame_offsets[f + 1] : beg;  // inactive stream: empty range
-    unsigned long long* full = s_bar;
-    unsigned long long* empty = s_bar + kPcSlots * 4;
-    // software prefetch of the next observation of this stream handled by this group
-    int k = beg + pg * G;
-    double px = 0, py = 0, pz = 0, ou = 0, ov = 0;
-    bool have = k < end;
-    if (have) { px = ld_obs(pb.x, k, pb.f32); py = ld_obs(pb.y, k, pb.f32); pz = ld_obs(pb.z, k, pb.f32); ou = ld_obs(pb.u, k, pb.f32); ov = ld_obs(pb.v, k, pb.f32); }
-    for (int it = pg; it < n_iter; it += 2) {
-      const int slot = it % kPcSlots;
-      const unsigned round = (unsigned)(it / kPcSlots);
-      // current observation (already loaded) and prefetch of the next one
-      const double cpx = px, cpy = py, cpz = pz, cou = ou, cov = ov;
-      const bool cur_have = have;
-      k += 2 * G;
-      have = k < end;
-      if (have) { px = ld_obs(pb.x, k, pb.f32); py = ld_obs(pb.y, k, pb.f32); pz = ld_obs(pb.z, k, pb.f32); ou = ld_obs(pb.u, k, pb.f32); ov = ld_obs(pb.v, k, pb.f32); }
-      double val[P::NV];
-      if (cur_have) {
-        const double fx = ip[0], fy = OF ? ip[0] : ip[1], cx = ip[2], cy = ip[3];
-        const double qx = fma(fc[0], cpx, fma(fc[1], cpy, fc[2] * cpz));
-        const double qy = fma(fc[3], cpx, fma(fc[4], cpy, fc[5] * cpz));
-        const double qz = fma(fc[6], cpx, fma(fc[7], cpy, fc[8] * cpz));
-        double m[2], dP[2][3], dk[2][kMaxNd];
-        model_eval<MODEL, true>(ip + 4, qx + fc[9], qy + fc[10], qz + fc[11], m, dP, dk);
-        const double ru = fma(fx, m[0], cx) - cou;
-        const double rv = fma(fy, m[1], cy) - cov;
-        const double w = huber_weight(ru * ru + rv * rv, pb.huber_delta);
-        const double wfx = w * fx, wfy = w * fy;
-        val[0] = w * m[0]; val[1] = w * m[1]; val[2] = w;
-#pragma unroll
-        for (int j = 0; j < C::ND; ++j) { val[P::I_DKU + j] = wfx * dk[0][j]; val[P::I_DKV + j] = wfy * dk[1][j]; }
-#pragma unroll
-        for (int j = 0; j < 3; ++j) { val[P::I_DU + j] = wfx * dP[0][j]; val[P::I_DV + j] = wfy * dP[1][j]; }
-        val[P::I_Q] = qx; val[P::I_Q + 1] = qy; val[P::I_Q + 2] = qz;
-        val[P::I_R] = w * ru; val[P::I_R + 1] = w * rv;
-      } else {
-#pragma unroll
-        for (int j = 0; j < P::NV; ++j) val[j] = 0.0;   // contributes exact zeros
-      }
-      mbar_wait(empty + slot * 4 + cw, (round & 1u) ^ 1u);
-      double* dst = s_ring + (size_t)slot * P::NV * kPcStreams + sidx;
-#pragma unroll
-      for (int j = 0; j < P::NV; ++j) dst[j * kPcStreams] = val[j];
-      mbar_arrive(full + slot * 4 + cw);
-    }
-  } else {
-    // =============================== consumers ===============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 240;\n");
-    const int sidx = t;
-    const int cw = warp;
-    const int fl = sidx / G;
-    const bool active = fl < nf;
-    const double* fc = s_fc + (active ? fl : 0) * kFrameConst;
-    unsigned long long* full = s_bar;
-    unsigned long long* empty = s_bar + kPcSlots * 4;
-    double acc[C::NACC];
-#pragma unroll
-    for (int i = 0; i < C::NACC; ++i) acc[i] = 0.0;
-    for (int it = 0; it < n_iter; ++it) {
-      const int slot = it % kPcSlots;
-      const unsigned round = (unsigned)(it / kPcSlots);
-      mbar_wait(full + slot * 4 + cw, round & 1u);
-      const double* src = s_ring + (size_t)slot * P::NV * kPcStreams + sidx;
-      double val[P::NV];
-#pragma unroll
-      for (int j = 0; j < P::NV; ++j) val[j] = src[j * kPcStreams];
-      mbar_arrive(empty + slot * 4 + cw);
-      double au[C::NA], av[C::NA];
-      if constexpr (OF) { au[0] = val[0]; av[0] = val[1]; au[1] = val[2]; av[2] = val[2]; }
-      else { au[0] = val[0]; av[1] = val[1]; au[2] = val[2]; av[3] = val[2]; }
-#pragma unroll
-      for (int j = 0; j < C::ND; ++j) { au[C::KOFF + j] = val[P::I_DKU + j]; av[C::KOFF + j] = val[P::I_DKV + j]; }
-      const double qx = val[P::I_Q], qy = val[P::I_Q + 1], qz = val[P::I_Q + 2];
-      const double du0 = val[P::I_DU], du1 = val[P::I_DU + 1], du2 = val[P::I_DU + 2];
-      const double dv0 = val[P::I_DV], dv1 = val[P::I_DV + 1], dv2 = val[P::I_DV + 2];
-      au[C::D + 0] = qy * du2 - qz * du1; au[C::D + 1] = qz * du0 - qx * du2; au[C::D + 2] = qx * du1 - qy * du0;
-      av[C::D + 0] = qy * dv2 - qz * dv1; av[C::D + 1] = qz * dv0 - qx * dv2; av[C::D + 2] = qx * dv1 - qy * dv0;
-      au[C::D + 3] = du0; au[C::D + 4] = du1; au[C::D + 5] = du2;
-      av[C::D + 3] = dv0; av[C::D + 4] = dv1; av[C::D + 5] = dv2;
-      au[C::N] = val[P::I_R]; av[C::N] = val[P::I_R + 1];
-      static_for<0, C::NA>([&](auto I) {
-        static_for<decltype(I)::value, C::NA>([&](auto J) {
-          constexpr int i = decltype(I)::value, j = decltype(J)::value;
-          constexpr int kk = C::kidx(i, j);
-          if constexpr (kk >= 0) {
-            if constexpr (C::hasu(i, j)) acc[kk] = fma(au[i], au[j], acc[kk]);
-            if constexpr (C::hasv(i, j)) acc[kk] = fma(av[i], av[j], acc[kk]);
+              for (int j = 1; j < g; ++j) s += src[j];
+            } else {
+              for (int j = 1; j < G; ++j) s += src[j];
+            }
+            out[(size_t)s_a2b[ch * kRedChunk + e] * pb.Fs] = s;
           }
-        });
-      });
-    }
-    // basis change phi -> rvec (same as k_linearize)
-    {
-      const double* Jl = fc + 12;
-      static_for<0, C::NA>([&](auto Cc) {
-        constexpr int c = decltype(Cc)::value;
-        if constexpr (c < C::D || c >= C::D + 3) {
-          constexpr int k0 = c < C::D ? C::kidx(c, C::D + 0) : C::kidx(C::D + 0, c);
-          constexpr int k1 = c < C::D ? C::kidx(c, C::D + 1) : C::kidx(C::D + 1, c);
-          constexpr int k2 = c < C::D ? C::kidx(c, C::D + 2) : C::kidx(C::D + 2, c);
-          const double h0 = acc[k0], h1 = acc[k1], h2 = acc[k2];
-          acc[k0] = fma(Jl[0], h0, fma(Jl[3], h1, Jl[6] * h2));
-          acc[k1] = fma(Jl[1], h0, fma(Jl[4], h1, Jl[7] * h2));
-          acc[k2] = fma(Jl[2], h0, fma(Jl[5], h1, Jl[8] * h2));
         }
-      });
-      constexpr int p = C::D;
-      const double h00 = acc[C::kidx(p, p)], h01 = acc[C::kidx(p, p + 1)], h02 = acc[C::kidx(p, p + 2)];
-      const double h11 = acc[C::kidx(p + 1, p + 1)], h12 = acc[C::kidx(p + 1, p + 2)], h22 = acc[C::kidx(p + 2, p + 2)];
-      double tmp[3][3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        tmp[0][c] = fma(h00, Jl[c], fma(h01, Jl[3 + c], h02 * Jl[6 + c]));
-        tmp[1][c] = fma(h01, Jl[c], fma(h11, Jl[3 + c], h12 * Jl[6 + c]));
-        tmp[2][c] = fma(h02, Jl[c], fma(h12, Jl[3 + c], h22 * Jl[6 + c]));
+      };
+      switch (G) {
+        case 1: store_rounds(std::integral_constant<int, 1>{}); break;
+        case 2: store_rounds(std::integral_constant<int, 2>{}); break;
+        case 3: store_rounds(std::integral_constant<int, 3>{}); break;
+        case 4: store_rounds(std::integral_constant<int, 4>{}); break;
+        case 5: store_rounds(std::integral_constant<int, 5>{}); break;
+        case 6: store_rounds(std::integral_constant<int, 6>{}); break;
+        case 8: store_rounds(std::integral_constant<int, 8>{}); break;
+        case 10: store_rounds(std::integral_constant<int, 10>{}); break;
+        case 16: store_rounds(std::integral_constant<int, 16>{}); break;
+        default: store_rounds(std::integral_constant<int, 0>{}); break;
       }
-      auto g = [&](int a, int b) { return fma(Jl[a], tmp[0][b], fma(Jl[3 + a], tmp[1][b], Jl[6 + a] * tmp[2][b])); };
-      acc[C::kidx(p, p)] = g(0, 0); acc[C::kidx(p, p + 1)] = g(0, 1); acc[C::kidx(p, p + 2)] = g(0, 2);
-      acc[C::kidx(p + 1, p + 1)] = g(1, 1); acc[C::kidx(p + 1, p + 2)] = g(1, 2); acc[C::kidx(p + 2, p + 2)] = g(2, 2);
-    }
-    // all consumers are past the ring before it is overwritten by the accumulator dump
-    asm volatile("bar.sync 1, 128;\n" ::: "memory");
-    static_for<0, C::NACC>([&](auto E) {
-      constexpr int e = decltype(E)::value;
-      s_ring[e * kPcStreams + sidx] = acc[e];
     });
   }
-  __syncthreads();
 
-  // ---- all 384 threads: sum the G slices of each frame in lane order, store SoA; frame cost = (r,r) entry ----
-  for (int o = t; o < C::NACC * nf; o += kPcThreads) {
-    const int e = o / nf, ff = o - e * nf;
-    const double* src = s_ring + e * kPcStreams + ff * G;
-    double s = 0.0;
-    for (int j = 0; j < G; ++j) s += src[j];
-    const int f = f0 + ff;
-    const int prob = BATCH ? pb.frame_problem[f] : 0;
-    double* out = pb.blocks[cur_of(pb, prob) ^ prm.which];
-    out[(size_t)prm.acc_to_blk[e] * pb.Fs + f] = s;
-    if (e == C::NACC - 1) s_stat[FPC + ff] = s;
-  }
+  CCRS_TCK(4);
   if constexpr (!BATCH) {
-    __syncthreads();
-    if (t == 0) {
-      double md = 0.0, cost = 0.0;
-      for (int i = 0; i < nf; ++i) { md += s_stat[i]; cost += s_stat[FPC + i]; }
-      prm.cta_part[2 * blockIdx.x] = md;
-      prm.cta_part[2 * blockIdx.x + 1] = cost;
-      __threadfence();
-      s_misc[1] = (atomicAdd(prm.ticket, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (s_misc[1]) {
-      __threadfence();
-      double* sh = s_ring;   // the accumulator dump has been consumed
-      __syncthreads();
-      if (t < 128) {
-        const int v = t & 1, lane2 = t >> 1;
-        double a = 0.0;
-        for (int b = lane2; b < (int)gridDim.x; b += 64) a += __ldcg(prm.cta_part + 2 * b + v);
-        sh[t] = a;
+    const unsigned last = __shfl_sync(0xffffffffu, (unsigned)(ticket_old == n_warps - 1), 0);
+    if (last) {
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      double a = 0.0, b = 0.0;
+      for (unsigned w = lane; w < n_warps; w += 32) { a += __ldcg(prm.cta_part + 2 * w); b += __ldcg(prm.cta_part + 2 * w + 1); }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
       }
-      __syncthreads();
-      for (int w = 64; w >= 2; w >>= 1) {
-        if (t < w) sh[t] += sh[t + w];
-        __syncthreads();
-      }
-      if (t == 0) {
-        prm.stat_dev[0] = sh[0]; prm.stat_dev[1] = sh[1];
+      if (lane == 0) {
+        prm.stat_dev[0] = a; prm.stat_dev[1] = b;
         *prm.ticket = 0u;
-        if (prm.host_stat) { double tmp[3] = {sh[0], sh[1], 0.0}; publish_host(prm.host_stat, tmp, 3, prm.seq); }
+        if (prm.host_stat) { double tmp[3] = {a, b, 0.0}; publish_host(prm.host_stat, tmp, 3, prm.seq); }
       }
     }
   }
+#ifdef CCRS_K2_TIMING
+  CCRS_TCK(5);
+  if (prm.dbg && lane == 0) {
+    long long* o = prm.dbg + (size_t)gw * 10;
+    unsigned smid, warpid;
+    unsigned long long gt1;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+    o[0] = (long long)gt0; o[1] = smid;
+    for (int i = 0; i < 6; ++i) o[2 + i] = tck[i];
+    o[8] = (long long)gt1; o[9] = warpid;
+  }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1078,18 +878,14 @@ void fill_acc_to_blk(int model, int one_focal, int32_t* table) {
   });
 }
 
-static size_t lin_smem_bytes(int FPC, bool batch, bool cost_only) {
-  size_t d = (size_t)FPC * kFrameConst + (batch ? (size_t)FPC * kMaxFull : 0);
-  d += cost_only ? kLinThreads : (size_t)kRedChunk * kLinThreads;
-  d += 2 * (size_t)FPC;  // per-frame {md, cost}
-  d += (size_t)kObsStages * 5 * kLinThreads;  // cp.async observation ring
-  return d * sizeof(double);
+static size_t lin_smem_bytes(int FPW, bool batch, bool cost_only) {
+  return (size_t)kLinWarps * lin_warp_smem_doubles(FPW, batch, cost_only) * sizeof(double);
 }
 
 template <int MODEL, bool OF, bool BATCH, bool COST>
 static cudaError_t launch_lin_t(const LinParams& prm, int n_ctas, cudaStream_t s) {
   auto kern = k_linearize<MODEL, OF, BATCH, COST>;
-  const size_t smem = lin_smem_bytes(prm.FPC, BATCH, COST);
+  const size_t smem = lin_smem_bytes(prm.FPW, BATCH, COST);
   static bool configured = false;  // per instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -1107,37 +903,6 @@ cudaError_t launch_linearize(int model, int one_focal, bool batch, bool cost_onl
     constexpr bool of = decltype(OF)::value;
     if (batch) return cost_only ? launch_lin_t<m, of, true, true>(prm, n_ctas, s) : launch_lin_t<m, of, true, false>(prm, n_ctas, s);
     return cost_only ? launch_lin_t<m, of, false, true>(prm, n_ctas, s) : launch_lin_t<m, of, false, false>(prm, n_ctas, s);
-  });
-}
-
-static size_t pc_smem_bytes(int FPC, bool batch, int NV, int NACC) {
-  size_t d = (size_t)FPC * kFrameConst + (batch ? (size_t)FPC * kMaxFull : 0) + 2 * (size_t)FPC;
-  d += 2 * kPcSlots * 4;  // mbarriers (8 B each)
-  d += 2;                 // s_misc (4 ints)
-  const size_t ring = (size_t)kPcSlots * NV * kPcStreams, dump = (size_t)NACC * kPcStreams;
-  d += ring > dump ? ring : dump;
-  return d * sizeof(double);
-}
-
-template <int MODEL, bool OF, bool BATCH>
-static cudaError_t launch_pc_t(const LinParams& prm, int n_ctas, cudaStream_t s) {
-  auto kern = k_linearize_pc<MODEL, OF, BATCH>;
-  const size_t smem = pc_smem_bytes(prm.FPC, BATCH, PcCfg<MODEL, OF>::NV, Cfg<MODEL, OF>::NACC);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  kern<<<n_ctas, kPcThreads, smem, s>>>(prm);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_linearize_pc(int model, int one_focal, bool batch, const LinParams& prm, int n_ctas, cudaStream_t s) {
-  return dispatch_model(model, one_focal, [&](auto M, auto OF) {
-    constexpr int m = decltype(M)::value;
-    constexpr bool of = decltype(OF)::value;
-    return batch ? launch_pc_t<m, of, true>(prm, n_ctas, s) : launch_pc_t<m, of, false>(prm, n_ctas, s);
   });
 }
 

@@ -6,8 +6,10 @@
 namespace ccrs {
 
 constexpr int kLinThreads = 128;     // K2 CTA size
+constexpr int kLinWarps = kLinThreads / 32;
+constexpr double kLinOverheadIters = 6.0;  // K2 per-warp prologue + reduction cost in main-loop iterations (slicing cost model)
 constexpr int kLinCtasPerSm = 2;     // K2 __launch_bounds__ occupancy target (255 regs x 128 x 2 = one register file)
-constexpr int kRedChunk = 48;        // accumulators staged per smem reduction round (48 x 128 x 8 B = 48 KB / CTA)
+constexpr int kRedChunk = 48;        // accumulators staged per smem reduction round (48 x 32 x 8 B = 12 KB / warp)
 constexpr int kObsStages = 4;        // cp.async ring depth of K2's observation prefetch (distance 3 iterations)
 constexpr int kFrameConst = 21;      // R(9) t(3) Jl(9) per frame in shared memory
 
@@ -35,7 +37,7 @@ struct LinParams {
   const int32_t* acc_to_blk;  // [NACC] sparse accumulator -> dense packed block index
   int which;                // 0 = current point, 1 = trial point
   int G;                    // lanes per frame
-  int FPC;                  // frames per CTA = kLinThreads / G
+  int FPW;                  // frames per warp = 32 / G
   // ---- fused K4 (pose back-substitution) in the prologue: 0 none, 1 trial = current + step, 2 in place (GN)
   int backsub;
   const double* elim;       // [(6D+18)][Fs] from K3
@@ -47,11 +49,12 @@ struct LinParams {
   const unsigned char* active;  // batch: problems whose poses may move (nullable)
   double* frame_md;         // [Fs] per-frame model-decrease part (batch reduces it per problem)
   // ---- fused statistics (single problem): per-CTA partial {md, cost}, final sum by the last CTA in CTA order
-  double* cta_part;         // [n_ctas][2]
+  double* cta_part;         // [n_ctas * kLinWarps][2] per-warp partials
   unsigned int* ticket;
   double* stat_dev;         // [2] = {md, cost}
   volatile double* host_stat;  // mapped pinned [4] = {md, cost, -, seq}; nullptr when a cross-rank exchange follows
   double seq;
+  long long* dbg;           // [n_warps][10] per-warp phase clocks (only written by -DCCRS_K2_TIMING builds)
 };
 
 struct SchurParams {
@@ -90,8 +93,6 @@ void fill_acc_to_blk(int model, int one_focal, int32_t* table);
 
 cudaError_t launch_linearize(int model, int one_focal, bool batch, bool cost_only, const LinParams& prm, int n_ctas,
                              cudaStream_t s);
-// warp-specialised K2 (384 threads, one CTA per SM); same LinParams, same outputs
-cudaError_t launch_linearize_pc(int model, int one_focal, bool batch, const LinParams& prm, int n_ctas, cudaStream_t s);
 cudaError_t launch_eval_rj(int model, int one_focal, const ProblemDev& pb, const double* intr_dev, const double* poses,
                            int apply_loss, double* r, double* J, int64_t n_obs, cudaStream_t s);
 cudaError_t launch_schur(int D, const SchurParams& prm, cudaStream_t s);

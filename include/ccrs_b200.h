@@ -278,6 +278,11 @@ int ccrs_time_linearize(ccrs_problem* p, const double* intr, int reps, int flush
  * timed_launches = kernels launched inside the timed iterations. */
 int ccrs_bench_lm_steps(ccrs_problem* p, const double* intr0, const double* poses0, int warmup, int steps,
                         int reset_every, int flush_l2, double* step_ms, int64_t* timed_launches);
+/* Host-side phase trace of single-problem LM iterations (process-wide). Returns the averages accumulated since the
+ * last call, in microseconds per iteration, then resets and enables/disables tracing:
+ *   [0] K3 launch call  [1] K3 execution + publish latency  [2] host: unpack, d x d solve, trial point
+ *   [3] K2 launch call  [4] K2 execution + publish latency  [5] host: accept/reject, bookkeeping */
+int ccrs_step_trace(int enable, double* avg_us, int64_t* n_iterations);
 /* Kernel launches issued by this handle since creation. */
 int64_t ccrs_launch_count(const ccrs_problem* p);
 
