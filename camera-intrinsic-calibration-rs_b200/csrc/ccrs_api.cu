@@ -165,6 +165,7 @@ struct ccrs_problem {
   DevBuf<double> elim, frame_red, pose_scale, frame_md, cta_part;
 #ifdef CCRS_K2_TIMING
   DevBuf<double> k2_dbg;   // [n_warps][10] int64 phase clocks
+  DevBuf<double> k3_dbg;   // [n_warps][8]
 #endif
   DevBuf<double> red_out, stat_out, gather, intr_dev, ya_dev, u_dev, scale_dev, l2_flush;
   DevBuf<unsigned char> mask_dev;
@@ -269,6 +270,7 @@ int upload_problem(ccrs_problem* p, int n_problems, const int32_t* problem_frame
   CK(p->pose_scale.alloc(6 * Fs));
   CK(p->frame_md.alloc(Fs));
   CK(p->cta_part.alloc((size_t)2 * p->n_lin_ctas * kLinWarps));
+  CK(launch_arm(p->cta_part.p, (size_t)2 * p->n_lin_ctas * kLinWarps, s));
   CK(p->red_out.alloc(P * p->NRED));
   CK(p->stat_out.alloc(P * 2));
   CK(p->intr_dev.alloc(P * p->D)); CK(p->ya_dev.alloc(P * p->D)); CK(p->u_dev.alloc(P)); CK(p->scale_dev.alloc(P * p->D));
@@ -363,17 +365,31 @@ struct StepTrace {
 };
 StepTrace g_trace;
 
-// Spin on a sequence number the GPU writes to mapped host memory after its results (kernel-to-host latency of a
-// PCIe write instead of a D2H copy + stream synchronisation). Falls back to the stream status so a failed launch
-// cannot hang the host.
-int wait_seq(ccrs_problem* p, volatile double* flag, double seq) {
+// Results the host needs every iteration come back through mapped pinned host memory WITHOUT any device-side fence
+// (a system-scope fence costs ~2-3 us per use): before the launch the host arms the n result words with a sentinel
+// bit pattern (a NaN payload no computation produces; the Cholesky-failure poison is the canonical quiet NaN); the
+// kernel simply stores its n results; the host spins until none of the n words is the sentinel. Each word is written
+// once with a single 8-byte store, so a word is either the sentinel or the final value. Falls back to the stream
+// status so a failed launch cannot hang the host.
+constexpr uint64_t kSentinelBits = 0x7ff8dead5e471e15ULL;
+void arm_payload(volatile double* dst, int n) {
+  volatile uint64_t* w = reinterpret_cast<volatile uint64_t*>(dst);
+  for (int i = 0; i < n; ++i) w[i] = kSentinelBits;
+  std::atomic_thread_fence(std::memory_order_seq_cst);
+}
+int wait_payload(ccrs_problem* p, volatile double* src, int n) {
+  volatile uint64_t* w = reinterpret_cast<volatile uint64_t*>(src);
   for (unsigned long spins = 1;; ++spins) {
-    if (*flag == seq) return 0;
+    int i = n - 1;
+    while (i >= 0 && w[i] != kSentinelBits) --i;
+    if (i < 0) return 0;
     if ((spins & 0x3fff) == 0) {
       cudaError_t e = cudaStreamQuery(p->stream);
       if (e == cudaSuccess) {
-        if (*flag == seq) return 0;
-        return fail(CCRS_ERR_CUDA, "stream drained but result %g was never published", seq);
+        i = n - 1;
+        while (i >= 0 && w[i] != kSentinelBits) --i;
+        if (i < 0) return 0;
+        return fail(CCRS_ERR_CUDA, "stream drained but %d result words were never published", n);
       }
       if (e != cudaErrorNotReady) return fail(CCRS_ERR_CUDA, "stream error while waiting: %s", cudaGetErrorString(e));
     }
@@ -382,6 +398,7 @@ int wait_seq(ccrs_problem* p, volatile double* flag, double seq) {
 
 // sum `count` doubles across ranks on the device (stream-ordered), in place; optionally publish to mapped host memory
 int exchange(ccrs_problem* p, double* buf, size_t count, volatile double* host_out, double seq) {
+  if (host_out) arm_payload(host_out, (int)count);
   if (!p->comm) {
     if (host_out) { CK(launch_sum_partials(buf, 1, (int)count, buf, host_out, seq, p->stream)); p->launches++; }
     return 0;
@@ -489,10 +506,11 @@ int do_linearize(ccrs_problem* p, const double* intr, int which, bool cost_only,
     p->seq = next_seq();
     prm.seq = p->seq;
     prm.host_stat = (publish && !p->comm) ? p->h_stat.p : nullptr;
+    if (prm.host_stat) arm_payload(prm.host_stat, 2);
     if (seq_out) *seq_out = p->seq;
   }
 #ifdef CCRS_K2_TIMING
-  if (!p->k2_dbg.p) CK(p->k2_dbg.alloc((size_t)10 * p->n_lin_ctas * kLinWarps));
+  if (!p->k2_dbg.p) CK(p->k2_dbg.alloc((size_t)12 * p->n_lin_ctas * kLinWarps));
   prm.dbg = reinterpret_cast<long long*>(p->k2_dbg.p);
 #endif
   CK(launch_linearize(p->model, p->one_focal, p->batch, cost_only, prm, p->n_lin_ctas, p->stream));
@@ -508,9 +526,8 @@ int do_linearize(ccrs_problem* p, const double* intr, int which, bool cost_only,
 int fetch_stats(ccrs_problem* p, int batch_mode, double seq, double* out /* [P][2] */) {
   const int P = p->n_problems;
   if (!p->batch) {
-    // without a communicator the kernel publishes {md, cost, 0} then seq at [3]; with one, sum_partials publishes
-    // {md, cost} then seq at [2]
-    int st = wait_seq(p, p->comm ? p->h_stat.p + 2 : p->h_stat.p + 3, seq);
+    // {md, cost} published by K2's last warp (or by k_sum_partials after the cross-rank exchange)
+    int st = wait_payload(p, p->h_stat.p, 2);
     if (st) return st;
     out[0] = p->h_stat.p[0]; out[1] = p->h_stat.p[1];
     return 0;
@@ -566,12 +583,17 @@ int do_reduce(ccrs_problem* p, int which, const double* u, int use_scale, double
     p->seq = next_seq();
     prm.seq = p->seq;
     prm.host_red = p->comm ? nullptr : p->h_red.p;
+    if (prm.host_red) arm_payload(prm.host_red, p->NRED);
     g_trace.mark(5);
+#ifdef CCRS_K2_TIMING
+    if (!p->k3_dbg.p) CK(p->k3_dbg.alloc((size_t)8 * (p->n_frames / 32 + 8)));
+    prm.dbg = reinterpret_cast<long long*>(p->k3_dbg.p);
+#endif
     CK(launch_schur(D, prm, p->stream));
     p->launches++;
     if (p->comm) { st = exchange(p, p->red_out.p, (size_t)p->NRED, p->h_red.p, p->seq); if (st) return st; }
     g_trace.mark(0);
-    st = wait_seq(p, p->h_red.p + p->NRED, p->seq);
+    st = wait_payload(p, p->h_red.p, p->NRED);
     if (st) return st;
     g_trace.mark(1);
     if (g_trace.on) g_trace.n++;
@@ -706,12 +728,19 @@ int ccrs_step_trace(int enable, double* avg_us /* [6] or NULL */, int64_t* n_ite
 }
 
 #ifdef CCRS_K2_TIMING
+extern "C" int ccrs_debug_k3_timing(ccrs_problem* p, long long* out, int cap_warps) {
+  if (!p || !p->k3_dbg.p) return -1;
+  const int nw = (p->n_frames + 31) / 32;
+  cudaStreamSynchronize(p->stream);
+  cudaMemcpy(out, p->k3_dbg.p, (size_t)8 * std::min(nw, cap_warps) * sizeof(long long), cudaMemcpyDeviceToHost);
+  return nw;
+}
 // debug builds only (make timing): per-warp phase clocks of the last K2 launch, [n_warps][10] int64
 extern "C" int ccrs_debug_k2_timing(ccrs_problem* p, long long* out, int cap_warps) {
   if (!p || !p->k2_dbg.p) return -1;
   const int nw = p->n_lin_ctas * kLinWarps;
   cudaStreamSynchronize(p->stream);
-  cudaMemcpy(out, p->k2_dbg.p, (size_t)10 * std::min(nw, cap_warps) * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaMemcpy(out, p->k2_dbg.p, (size_t)12 * std::min(nw, cap_warps) * sizeof(long long), cudaMemcpyDeviceToHost);
   return nw;
 }
 #endif

@@ -63,26 +63,35 @@ struct Cfg {
   static constexpr int NACC = nacc();
 };
 
+// bit pattern that arms a result slot which validates itself (device partials, mapped host results): a NaN payload
+// no computation produces (the Cholesky-failure poison is the canonical quiet NaN)
+constexpr long long kArmBits = 0x7ff8dead5e471e15LL;
+__global__ void k_arm(double* p, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    p[i] = __longlong_as_double(kArmBits);
+}
+
 CCRS_D int cur_of(const ProblemDev& pb, int prob) { return pb.cur ? pb.cur[prob] : pb.cur_val; }
 
-// publish n doubles + a sequence number to mapped host memory (the host spins on the sequence number)
-CCRS_D void publish_host(volatile double* dst, const double* src, int n, double seq) {
+// publish n doubles to mapped host memory: plain stores, no fence — the host armed the n words with a sentinel and
+// spins until all of them changed (ccrs_api.cu: arm_payload / wait_payload)
+CCRS_D void publish_host(volatile double* dst, const double* src, int n) {
   for (int i = 0; i < n; ++i) dst[i] = src[i];
-  __threadfence_system();
-  dst[n] = seq;
 }
 
 CCRS_D void cp_async8(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
 }
 CCRS_D void cp_async4(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
 }
 // observation k of an SoA array that holds doubles or (f32 != 0) floats; f32 -> f64 widening as factors.rs:141-143
 CCRS_D double ld_obs(const double* base, int k, int f32) {
   return f32 ? (double)reinterpret_cast<const float*>(base)[k] : base[k];
 }
-CCRS_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// no "memory" clobber on the issue side: ordinary loads may be scheduled across the prefetch (the pose prologue's loads
+// then overlap it); the wait below is the barrier that orders the ring reads
+CCRS_D void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>
 CCRS_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -166,7 +175,7 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   }
 
 #ifdef CCRS_K2_TIMING
-  long long tck[6];
+  long long tck[8];
   unsigned long long gt0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
   tck[0] = clock64();
@@ -390,12 +399,14 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
       wcost += __shfl_sync(0xffffffffu, fcost, i * G);
     }
     if (lane == 0) {
-      prm.cta_part[2 * gw] = wmd;
-      prm.cta_part[2 * gw + 1] = wcost;
-      asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(ticket_old) : "l"(prm.ticket) : "memory");
+      // no fence: the two partial words validate themselves (armed with kArmBits by the previous launch's last
+      // warp / at creation); the relaxed ticket only elects the warp that sums, its round trip overlaps the reduction
+      reinterpret_cast<double2*>(prm.cta_part)[gw] = make_double2(wmd, wcost);
+      ticket_old = atomicAdd(prm.ticket, 1u);
     }
   }
 
+  CCRS_TCK(6);
   // ---- sum the G slices of each frame in slice order (fixed order -> deterministic) and store SoA ----
   if constexpr (COST_ONLY) {
     if (active && sl == 0) {
@@ -458,9 +469,29 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   if constexpr (!BATCH) {
     const unsigned last = __shfl_sync(0xffffffffu, (unsigned)(ticket_old == n_warps - 1), 0);
     if (last) {
-      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      // every warp has taken its ticket, so every partial store has been issued: read the slots from L2 (16 loads
+      // in flight per lane) until none still holds the arming pattern, sum in a fixed order, re-arm for the next launch
+      double2* part = reinterpret_cast<double2*>(prm.cta_part);
       double a = 0.0, b = 0.0;
-      for (unsigned w = lane; w < n_warps; w += 32) { a += __ldcg(prm.cta_part + 2 * w); b += __ldcg(prm.cta_part + 2 * w + 1); }
+      for (unsigned w0 = lane; w0 < n_warps; w0 += 32 * 16) {
+        double2 t[16];
+        bool ok;
+        do {
+          ok = true;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const unsigned w = w0 + 32 * q;
+            t[q] = w < n_warps ? __ldcg(part + w) : make_double2(0.0, 0.0);
+            ok = ok && (__double_as_longlong(t[q].x) != kArmBits) && (__double_as_longlong(t[q].y) != kArmBits);
+          }
+        } while (!ok);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          a += t[q].x; b += t[q].y;
+          const unsigned w = w0 + 32 * q;
+          if (w < n_warps) part[w] = make_double2(__longlong_as_double(kArmBits), __longlong_as_double(kArmBits));
+        }
+      }
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) {
         a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -469,14 +500,14 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
       if (lane == 0) {
         prm.stat_dev[0] = a; prm.stat_dev[1] = b;
         *prm.ticket = 0u;
-        if (prm.host_stat) { double tmp[3] = {a, b, 0.0}; publish_host(prm.host_stat, tmp, 3, prm.seq); }
+        if (prm.host_stat) { double tmp[2] = {a, b}; publish_host(prm.host_stat, tmp, 2); }
       }
     }
   }
 #ifdef CCRS_K2_TIMING
   CCRS_TCK(5);
   if (prm.dbg && lane == 0) {
-    long long* o = prm.dbg + (size_t)gw * 10;
+    long long* o = prm.dbg + (size_t)gw * 12;
     unsigned smid, warpid;
     unsigned long long gt1;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -484,7 +515,7 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
     o[0] = (long long)gt0; o[1] = smid;
     for (int i = 0; i < 6; ++i) o[2 + i] = tck[i];
-    o[8] = (long long)gt1; o[9] = warpid;
+    o[8] = (long long)gt1; o[9] = warpid; o[10] = tck[6]; o[11] = 0;
   }
 #endif
 }
@@ -534,6 +565,7 @@ __global__ void __launch_bounds__(128) k_eval_rj(ProblemDev pb, const double* __
 // written and reduced per problem by k_segreduce.
 // ------------------------------------------------------------------------------------------------
 constexpr int kSchurThreads = 128;
+constexpr int kSchurSplit = 3;      // lanes per value in the last CTA's sum over CTA partials
 
 template <int D, bool BATCH>
 __global__ void __launch_bounds__(kSchurThreads) k_schur(const __grid_constant__ SchurParams prm, double* __restrict__ partials) {
@@ -548,6 +580,13 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(const __grid_constant__
 #pragma unroll
   for (int i = 0; i < NRED; ++i) red[i] = 0.0;
   int bad = 0;
+#ifdef CCRS_K2_TIMING
+  long long tk[6];
+  tk[0] = clock64();
+#define CCRS_TK3(i) tk[i] = clock64()
+#else
+#define CCRS_TK3(i)
+#endif
   if (valid) {
     const int prob = BATCH ? pb.frame_problem[f] : 0;
     const double* blk = pb.blocks[cur_of(pb, prob) ^ prm.which] + f;
@@ -575,7 +614,7 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(const __grid_constant__
 #pragma unroll
       for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
       if (!(s > 0.0)) bad = 1;
-      const double l = sqrt(s), il = 1.0 / l;
+      const double il = rsqrt_fast(s > 0.0 ? s : 1.0);
       L[j][j] = il;  // store the reciprocal of the pivot
 #pragma unroll
       for (int i = j + 1; i < 6; ++i) {
@@ -585,6 +624,7 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(const __grid_constant__
         L[i][j] = tt * il;
       }
     }
+    CCRS_TK3(1);
     // Y[a] = L^-1 B'[a,:]^T
     double Yv[D][6];
 #pragma unroll
@@ -661,6 +701,7 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(const __grid_constant__
       for (int i = 0; i < NRED; ++i) red[i] = nan("");
     }
   }
+  CCRS_TK3(2);
   if constexpr (BATCH) {
     if (valid) {
 #pragma unroll
@@ -672,38 +713,72 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(const __grid_constant__
 #pragma unroll
     for (int i = 0; i < NRED; ++i) s_red[i * LD + threadIdx.x] = red[i];
     __syncthreads();
-    if (threadIdx.x < NRED) {
-      const double* src = s_red + threadIdx.x * LD;
-      double s = 0.0;
-      for (int j = 0; j < kSchurThreads; ++j) s += src[j];
-      partials[(size_t)blockIdx.x * NRED + threadIdx.x] = s;
+    {  // SPLIT threads per value, each summing a contiguous segment of frames in order; fixed combine
+      constexpr int SPLIT = kSchurThreads / NRED;
+      constexpr int SEG = (kSchurThreads + SPLIT - 1) / SPLIT;
+      __shared__ double s_seg[kSchurThreads];
+      if (threadIdx.x < SPLIT * NRED) {
+        const int v = threadIdx.x / SPLIT, h = threadIdx.x - SPLIT * v;
+        const int j0 = h * SEG, j1 = min(kSchurThreads, j0 + SEG);
+        const double* src = s_red + v * LD;
+        double s = 0.0;
+        for (int j = j0; j < j1; ++j) s += src[j];
+        s_seg[threadIdx.x] = s;
+      }
+      __syncthreads();
+      if (threadIdx.x < NRED) {
+        double s = s_seg[SPLIT * threadIdx.x];
+#pragma unroll
+        for (int h = 1; h < SPLIT; ++h) s += s_seg[SPLIT * threadIdx.x + h];
+        partials[(size_t)blockIdx.x * NRED + threadIdx.x] = s;
+      }
     }
-    __threadfence();
+    CCRS_TK3(3);
+    __syncthreads();   // partial stores of this CTA happen-before thread 0's release below (cumulativity)
+    if (threadIdx.x == 0) {
+      unsigned old;
+      asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(prm.ticket) : "memory");
+      s_last = (old == gridDim.x - 1);
+    }
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(prm.ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (s_last) {  // last CTA: sum the CTA partials in CTA order; two interleaved halves per value, fixed combine
-      __threadfence();
-      static_assert(2 * NRED <= 2 * kSchurThreads, "NRED too large");
+    CCRS_TK3(4);
+    if (s_last) {  // last CTA: sum the CTA partials in CTA order; kSchurSplit interleaved lanes per value, fixed combine
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      static_assert(kSchurSplit * NRED <= NRED * (kSchurThreads + 1), "staging buffer too small");
       const int nb = gridDim.x;
-      for (int idx = threadIdx.x; idx < 2 * NRED; idx += kSchurThreads) {
-        const int v = idx >> 1, h = idx & 1;
+      for (int idx = threadIdx.x; idx < kSchurSplit * NRED; idx += kSchurThreads) {
+        const int v = idx / kSchurSplit, h = idx - v * kSchurSplit;
         double a = 0.0;
-        for (int b = h; b < nb; b += 2) a += __ldcg(partials + (size_t)b * NRED + v);
+        for (int b0 = h; b0 < nb; b0 += 16 * kSchurSplit) {   // 16 loads in flight, then a fixed-order sum
+          double t[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int b = b0 + q * kSchurSplit;
+            t[q] = b < nb ? __ldcg(partials + (size_t)b * NRED + v) : 0.0;
+          }
+#pragma unroll
+          for (int q = 0; q < 16; ++q) a += t[q];
+        }
         s_red[idx] = a;
       }
       __syncthreads();
       if (threadIdx.x < NRED) {
-        const double tot = s_red[2 * threadIdx.x] + s_red[2 * threadIdx.x + 1];
+        double tot = s_red[kSchurSplit * threadIdx.x];
+#pragma unroll
+        for (int h = 1; h < kSchurSplit; ++h) tot += s_red[kSchurSplit * threadIdx.x + h];
         prm.red_out[threadIdx.x] = tot;
-        if (prm.host_red) { prm.host_red[threadIdx.x] = tot; __threadfence_system(); }
+        if (prm.host_red) prm.host_red[threadIdx.x] = tot;   // sentinel protocol: no fence
       }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        *prm.ticket = 0u;
-        if (prm.host_red) { __threadfence_system(); prm.host_red[NRED] = prm.seq; }
-      }
+      if (threadIdx.x == 0) *prm.ticket = 0u;
     }
+#ifdef CCRS_K2_TIMING
+    CCRS_TK3(5);
+    if (prm.dbg && (threadIdx.x & 31) == 0 && valid) {
+      long long* o = prm.dbg + (size_t)(blockIdx.x * (kSchurThreads / 32) + (threadIdx.x >> 5)) * 8;
+      for (int i = 0; i < 6; ++i) o[i] = tk[i];
+      o[6] = s_last; o[7] = 0;
+    }
+#endif
   }
 }
 
@@ -715,11 +790,7 @@ __global__ void k_sum_partials(const double* __restrict__ partials, int n_part, 
     double s = 0.0;
     for (int b = 0; b < n_part; ++b) s += partials[(size_t)b * NV + v];
     out[v] = s;
-    if (host_out) { host_out[v] = s; __threadfence_system(); }
-  }
-  if (host_out) {  // single CTA when publishing (NV <= blockDim.x)
-    __syncthreads();
-    if (threadIdx.x == 0) { __threadfence_system(); host_out[NV] = seq; }
+    if (host_out) host_out[v] = s;   // sentinel protocol: no fence
   }
 }
 
@@ -1000,6 +1071,11 @@ cudaError_t launch_trial_stats(const ProblemDev& pb, int rr_idx, int mode, const
 
 cudaError_t launch_flip_cur(int32_t* cur, const unsigned char* mask_dev, int n_problems, cudaStream_t s) {
   k_flip_cur<<<(n_problems + 127) / 128, 128, 0, s>>>(cur, mask_dev, n_problems);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_arm(double* p, size_t n, cudaStream_t s) {
+  k_arm<<<(unsigned)std::min<size_t>((n + 255) / 256, 1024), 256, 0, s>>>(p, n);
   return cudaGetLastError();
 }
 

@@ -49,7 +49,7 @@ struct LinParams {
   const unsigned char* active;  // batch: problems whose poses may move (nullable)
   double* frame_md;         // [Fs] per-frame model-decrease part (batch reduces it per problem)
   // ---- fused statistics (single problem): per-CTA partial {md, cost}, final sum by the last CTA in CTA order
-  double* cta_part;         // [n_ctas * kLinWarps][2] per-warp partials
+  double* cta_part;         // [n_ctas * kLinWarps][2] per-warp partials, armed (k_arm) between launches; 16-byte aligned
   unsigned int* ticket;
   double* stat_dev;         // [2] = {md, cost}
   volatile double* host_stat;  // mapped pinned [4] = {md, cost, -, seq}; nullptr when a cross-rank exchange follows
@@ -72,6 +72,7 @@ struct SchurParams {
   double* red_out;              // [NRED] device
   volatile double* host_red;    // mapped pinned [NRED+1] (last = seq); nullptr when a cross-rank exchange follows
   double seq;
+  long long* dbg;               // [n_warps][8] per-warp phase clocks (only written by -DCCRS_K2_TIMING builds)
 };
 
 struct BacksubParams {
@@ -110,6 +111,8 @@ cudaError_t launch_sum_partials(const double* partials, int n_part, int NV, doub
 cudaError_t launch_trial_stats(const ProblemDev& pb, int rr_idx, int mode, const double* frame_md, double* stat_out,
                                cudaStream_t s);
 cudaError_t launch_flip_cur(int32_t* cur, const unsigned char* mask_dev, int n_problems, cudaStream_t s);
+// fill p[0..n) with the arming bit pattern (self-validating result slots)
+cudaError_t launch_arm(double* p, size_t n, cudaStream_t s);
 cudaError_t launch_fp64_peak(double* out, int n_ctas, int iters, cudaStream_t s);
 cudaError_t launch_l2_flush(double* buf, size_t n, cudaStream_t s);
 

@@ -15,7 +15,7 @@ gp.set_poses(s.init_poses)
 lib = c._abi.load()
 for flush in (True, False):
     ms = gp.time_linearize(s.init_params, reps=5, flush_l2=flush)
-    buf = np.zeros((20000, 10), dtype=np.int64)
+    buf = np.zeros((20000, 12), dtype=np.int64)
     lib.ccrs_debug_k2_timing.restype = C.c_int
     nw = lib.ccrs_debug_k2_timing(gp.h, buf.ctypes.data_as(C.c_void_p), 20000)
     b = buf[:nw]
@@ -23,6 +23,7 @@ for flush in (True, False):
     ph = np.diff(b[:, 2:8], axis=1)
     names = ["prologue", "main loop", "basis chg", "reduce+store", "stats"]
     print(f"flush_l2={flush}: K2 {ms*1e3:.2f} us, {nw} warps; launch skew (globaltimer ns) median {np.median(gt):.0f} max {gt.max()}")
+    print(f"  of reduce+store: cost shuffles + partial publish + release ticket: median {np.median(b[:, 10] - b[:, 5]):.0f} cycles")
     tot = (b[:, 7] - b[:, 2])
     print(f"  warp lifetime cycles: median {np.median(tot):.0f} max {tot.max()} min {tot.min()}")
     for i, n in enumerate(names):
@@ -39,4 +40,18 @@ for flush in (True, False):
     sm = b[:, 1]
     per_sm = np.bincount(sm.astype(int))
     print(f"  warps per SM: min {per_sm[per_sm>0].min()} max {per_sm.max()} SMs used {np.count_nonzero(per_sm)}")
+# K3 phases (one reduce with damping)
+gp.set_poses(s.init_poses)
+gp.linearize(s.init_params)
+for rep in range(3):
+    gp.reduce(0, 1e-4)
+buf = np.zeros((20000, 8), dtype=np.int64)
+lib.ccrs_debug_k3_timing.restype = C.c_int
+nw = lib.ccrs_debug_k3_timing(gp.h, buf.ctypes.data_as(C.c_void_p), 20000)
+b = buf[:nw]
+ph = np.diff(b[:, 0:6], axis=1)
+print(f"K3: {nw} warps")
+for i, n in enumerate(["load+cholesky", "solve+reduce-terms+stores", "CTA reduction", "fence+ticket", "last CTA / tail"]):
+    print(f"  {n:26s} median {np.median(ph[:, i]):8.0f}  max {ph[:, i].max():8d}")
+print(f"  warp lifetime median {np.median(b[:,5]-b[:,0]):.0f} max {(b[:,5]-b[:,0]).max()}; span first start -> last end {b[:,5].max()-b[:,0].min()} (clock64 differs per SM: indicative)")
 gp.close()
