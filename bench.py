@@ -4,7 +4,8 @@
 metric   : residual+Jacobian evals/s (and LM iterations/s) at ~1M corner observations, EUCM
 workload : configs[3] — EUCM, 7,000 frames x 144 corners (1,007,999 obs after the image-bounds filter) PER GPU,
            synthetic (SURVEY.md §8(d) generator, seed 3), frames sharded across ranks, one exchange of the reduced
-           intrinsic system per linearisation (NCCL all-gather + rank-order sum on the device). Weak scaling: every
+           intrinsic system per linearisation (fused into K3/K2: peer-memory stores over NVLink + rank-order sum in
+           the kernel's last CTA; NCCL all-gather + rank-order sum when peer memory is unavailable). Weak scaling: every
            rank owns 7,000 frames, the job is one calibration problem of N x 7,000 frames.
 step     : one Levenberg-Marquardt iteration of that problem = K3 reduce (+exchange) -> host d x d solve -> K4
            back-substitution -> K2 linearisation of the trial point (speculative LM: the trial cost comes from the
@@ -134,6 +135,8 @@ def run_ours(args):
     prob = pkg.Problem(MODEL, s.width, s.height, sh["frame_offsets"], sh["x"], sh["y"], sh["z"], sh["u"], sh["v"], device=dev)
     pkg.dist.init_comm(prob, rank, world)
     d = prob.d
+    exch = "none (single GPU)" if world == 1 else ("fused into K2/K3 over peer memory (NVLink P2P stores, rank-order sum)" if pkg._abi.load().ccrs_comm_uses_peer_memory()
+                                                 else "NCCL all-gather + rank-order sum")
 
     def barrier():
         torch.cuda.synchronize()
@@ -233,7 +236,7 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "ours",
             "config": {"workload": WORKLOAD, "model": MODEL, "frames_per_gpu": FRAMES_PER_GPU, "obs_total": int(n_total),
-                       "obs_per_gpu": int(n_local), "parallelism": f"frame-sharded x{world}, NCCL all-gather + rank-order sum of the reduced system",
+                       "obs_per_gpu": int(n_local), "parallelism": f"frame-sharded x{world}", "exchange": exch,
                        "l2": "flushed (512 MB write) before every timed step, outside the event bracket", "loop": "speculative LM"},
             "lm_iterations_per_s": 1e3 / ms_per_step,
             "l2_warm": {"ms_per_step": warm_ms_per_step, "value": n_total / (warm_ms_per_step * 1e-3), "lm_iterations_per_s": 1e3 / warm_ms_per_step},

@@ -19,7 +19,7 @@ SYMBOLS = [
     "ccrs_problem_dim", "ccrs_problem_nblk", "ccrs_problem_n_frames", "ccrs_problem_n_obs", "ccrs_problem_n_problems",
     "ccrs_set_poses", "ccrs_get_poses", "ccrs_eval_rj", "ccrs_linearize", "ccrs_get_frame_blocks",
     "ccrs_compute_scale", "ccrs_set_intr_scale", "ccrs_reduce", "ccrs_backsub", "ccrs_eval_cost", "ccrs_accept",
-    "ccrs_comm_unique_id", "ccrs_comm_init", "ccrs_comm_finalize", "ccrs_comm_set_deterministic", "ccrs_default_options",
+    "ccrs_comm_unique_id", "ccrs_comm_init", "ccrs_comm_finalize", "ccrs_comm_set_deterministic", "ccrs_comm_uses_peer_memory", "ccrs_default_options",
     "ccrs_solve_gn", "ccrs_solve_lm", "ccrs_controller_gn", "ccrs_controller_lm", "ccrs_calib_camera",
     "ccrs_joint_create", "ccrs_joint_destroy", "ccrs_joint_dim", "ccrs_joint_last_error", "ccrs_joint_launch_count",
     "ccrs_joint_eval_rj", "ccrs_joint_solve_gn", "ccrs_model_bounds", "ccrs_measure_fp64_peak", "ccrs_time_linearize", "ccrs_bench_lm_steps", "ccrs_launch_count", "ccrs_step_trace",

@@ -28,7 +28,7 @@ struct NcclApi {
   int (*GetUniqueId)(ncclUniqueId*) = nullptr;
   int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
-  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;   // dtype 0 = ncclInt8
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool ok = false;
@@ -59,6 +59,19 @@ NcclApi& nccl() {
 // one process = one GPU = one communicator, shared by every handle of the process (created once: ncclCommInitRank
 // costs ~100 ms, far more than a whole calibration)
 struct GlobalComm { ncclComm_t comm = nullptr; int rank = 0, world = 1; } g_comm;
+
+// Process-wide peer-memory exchange buffer (PeerXchg in ccrs_kernels.cuh): [area][parity][rank][kXchgMaxVals] doubles,
+// cudaMalloc'd (not pooled: it is exported with cudaIpcGetMemHandle), armed, and every other rank's buffer opened with
+// cudaIpcOpenMemHandle. Areas: 0 = K3 reduced system, 1 = K2 {model decrease, cost}. Exchanges alternate parity per area
+// (all ranks issue the same sequence), so a rank that races ahead never overwrites a slot its peer has not consumed.
+constexpr int kXchgAreas = 2;
+struct GlobalPeer {
+  bool ok = false;
+  double* local = nullptr;
+  double* peer[kXchgMaxRanks] = {};
+  unsigned long count[kXchgAreas] = {};
+  size_t doubles() const { return (size_t)kXchgAreas * 2 * kXchgMaxRanks * kXchgMaxVals; }
+} g_peer;
 
 thread_local char g_err[512] = "";
 int fail(int code, const char* fmt, ...) {
@@ -396,6 +409,17 @@ int wait_payload(ccrs_problem* p, volatile double* src, int n) {
   }
 }
 
+// peer-memory exchange usable for this handle / payload?
+bool use_peer(const ccrs_problem* p, size_t count) {
+  return p->comm && g_peer.ok && p->deterministic && !p->batch && count <= (size_t)kXchgMaxVals;
+}
+void fill_peer(const ccrs_problem* p, int area, PeerXchg* px) {
+  for (int r = 0; r < kXchgMaxRanks; ++r) px->peer[r] = g_peer.peer[r];
+  px->world = p->world; px->rank = p->rank;
+  const unsigned long parity = g_peer.count[area]++ & 1ul;
+  px->off = (int)(((size_t)area * 2 + parity) * kXchgMaxRanks * kXchgMaxVals);
+}
+
 // sum `count` doubles across ranks on the device (stream-ordered), in place; optionally publish to mapped host memory
 int exchange(ccrs_problem* p, double* buf, size_t count, volatile double* host_out, double seq) {
   if (host_out) arm_payload(host_out, (int)count);
@@ -505,8 +529,10 @@ int do_linearize(ccrs_problem* p, const double* intr, int which, bool cost_only,
     prm.stat_dev = p->stat_out.p;
     p->seq = next_seq();
     prm.seq = p->seq;
-    prm.host_stat = (publish && !p->comm) ? p->h_stat.p : nullptr;
+    const bool peer = publish && use_peer(p, 2);
+    prm.host_stat = (publish && (!p->comm || peer)) ? p->h_stat.p : nullptr;
     if (prm.host_stat) arm_payload(prm.host_stat, 2);
+    if (peer) fill_peer(p, 1, &prm.px);
     if (seq_out) *seq_out = p->seq;
   }
 #ifdef CCRS_K2_TIMING
@@ -515,7 +541,7 @@ int do_linearize(ccrs_problem* p, const double* intr, int which, bool cost_only,
 #endif
   CK(launch_linearize(p->model, p->one_focal, p->batch, cost_only, prm, p->n_lin_ctas, p->stream));
   p->launches++;
-  if (!p->batch && publish && p->comm) {
+  if (!p->batch && publish && p->comm && !use_peer(p, 2)) {
     int st = exchange(p, p->stat_out.p, 2, p->h_stat.p, p->seq);   // h_stat[0..1] = sums, h_stat[2] = seq
     if (st) return st;
   }
@@ -582,8 +608,10 @@ int do_reduce(ccrs_problem* p, int which, const double* u, int use_scale, double
     prm.red_out = p->red_out.p;
     p->seq = next_seq();
     prm.seq = p->seq;
-    prm.host_red = p->comm ? nullptr : p->h_red.p;
+    const bool peer = use_peer(p, (size_t)p->NRED);
+    prm.host_red = (p->comm && !peer) ? nullptr : p->h_red.p;
     if (prm.host_red) arm_payload(prm.host_red, p->NRED);
+    if (peer) fill_peer(p, 0, &prm.px);
     g_trace.mark(5);
 #ifdef CCRS_K2_TIMING
     if (!p->k3_dbg.p) CK(p->k3_dbg.alloc((size_t)8 * (p->n_frames / 32 + 8)));
@@ -591,7 +619,7 @@ int do_reduce(ccrs_problem* p, int which, const double* u, int use_scale, double
 #endif
     CK(launch_schur(D, prm, p->stream));
     p->launches++;
-    if (p->comm) { st = exchange(p, p->red_out.p, (size_t)p->NRED, p->h_red.p, p->seq); if (st) return st; }
+    if (p->comm && !peer) { st = exchange(p, p->red_out.p, (size_t)p->NRED, p->h_red.p, p->seq); if (st) return st; }
     g_trace.mark(0);
     st = wait_payload(p, p->h_red.p, p->NRED);
     if (st) return st;
@@ -944,6 +972,69 @@ int ccrs_accept(ccrs_problem* p, const unsigned char* mask) {
   return 0;
 }
 
+// Build the peer-memory exchange after the communicator exists: all-gather the IPC handles over NCCL, open the
+// peers' buffers. Any failure (no P2P, different nodes, CCRS_P2P=0) leaves g_peer.ok false: the NCCL path is used.
+static void peer_teardown() {
+  for (int r = 0; r < kXchgMaxRanks; ++r) {
+    if (g_peer.peer[r] && g_peer.peer[r] != g_peer.local) cudaIpcCloseMemHandle(g_peer.peer[r]);
+    g_peer.peer[r] = nullptr;
+  }
+  if (g_peer.local) cudaFree(g_peer.local);
+  g_peer = GlobalPeer{};
+}
+static int peer_setup(int rank, int world, cudaStream_t s) {
+  peer_teardown();
+  if (const char* e = getenv("CCRS_P2P")) if (atoi(e) == 0) return 0;
+  if (world < 2 || world > kXchgMaxRanks) return 0;
+  NcclApi& n = nccl();
+  const size_t bytes = g_peer.doubles() * sizeof(double);
+  if (cudaMalloc((void**)&g_peer.local, bytes) != cudaSuccess) { cudaGetLastError(); g_peer.local = nullptr; return 0; }
+  if (launch_arm(g_peer.local, g_peer.doubles(), s) != cudaSuccess) return 0;
+  cudaIpcMemHandle_t mine;
+  int have = cudaIpcGetMemHandle(&mine, g_peer.local) == cudaSuccess ? 1 : 0;
+  if (!have) cudaGetLastError();
+  // every rank must take the same path: gather {have flag, handle} from everybody
+  constexpr size_t REC = sizeof(cudaIpcMemHandle_t) + 8;
+  unsigned char rec[REC] = {};
+  rec[0] = (unsigned char)have;
+  std::memcpy(rec + 8, &mine, sizeof(mine));
+  unsigned char *d_send = nullptr, *d_recv = nullptr;
+  if (cudaMalloc((void**)&d_send, REC) != cudaSuccess || cudaMalloc((void**)&d_recv, REC * world) != cudaSuccess) return 0;
+  std::vector<unsigned char> all(REC * world);
+  int ok = 1;
+  if (cudaMemcpyAsync(d_send, rec, REC, cudaMemcpyHostToDevice, s) != cudaSuccess) ok = 0;
+  if (ok && n.AllGather(d_send, d_recv, REC, 0 /* ncclInt8 */, g_comm.comm, s) != 0) ok = 0;
+  if (ok && cudaMemcpyAsync(all.data(), d_recv, REC * world, cudaMemcpyDeviceToHost, s) != cudaSuccess) ok = 0;
+  if (cudaStreamSynchronize(s) != cudaSuccess) ok = 0;
+  cudaFree(d_send); cudaFree(d_recv);
+  if (!ok) { cudaGetLastError(); return 0; }
+  for (int r = 0; r < world; ++r) if (!all[REC * r]) ok = 0;
+  int opened = ok;
+  if (ok) {
+    for (int r = 0; r < world && opened; ++r) {
+      if (r == rank) { g_peer.peer[r] = g_peer.local; continue; }
+      cudaIpcMemHandle_t hnd;
+      std::memcpy(&hnd, all.data() + REC * r + 8, sizeof(hnd));
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened = 0; break; }
+      g_peer.peer[r] = (double*)ptr;
+    }
+  }
+  // agree on the outcome (a rank that could not open a peer must not leave the others spinning on it)
+  double flag = opened ? 1.0 : 0.0, *d_flag = nullptr;
+  if (cudaMalloc((void**)&d_flag, 8) != cudaSuccess) return 0;
+  cudaMemcpyAsync(d_flag, &flag, 8, cudaMemcpyHostToDevice, s);
+  // min over ranks via sum of (1 - flag): all-reduce of a double
+  double miss = 1.0 - flag;
+  cudaMemcpyAsync(d_flag, &miss, 8, cudaMemcpyHostToDevice, s);
+  int r2 = n.AllReduce(d_flag, d_flag, 1, kNcclFloat64, kNcclSum, g_comm.comm, s);
+  cudaMemcpyAsync(&miss, d_flag, 8, cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  cudaFree(d_flag);
+  g_peer.ok = (r2 == 0 && miss == 0.0);
+  return 0;
+}
+
 int ccrs_comm_unique_id(void* unique_id_128) {
   NcclApi& n = nccl();
   if (!n.ok) return fail(CCRS_ERR_COMM, "libnccl.so.2 not loadable: %s", dlerror());
@@ -972,10 +1063,14 @@ int ccrs_comm_init(ccrs_problem* p, const void* unique_id_128, int rank, int wor
   if (r != 0) return fail(CCRS_ERR_COMM, "ncclCommInitRank: %s", n.GetErrorString ? n.GetErrorString(r) : "?");
   g_comm.rank = rank; g_comm.world = world_size;
   p->comm = g_comm.comm; p->rank = rank; p->world = world_size;
+  peer_setup(rank, world_size, p->stream);
   return 0;
 }
 
+int ccrs_comm_uses_peer_memory(void) { return g_peer.ok ? 1 : 0; }
+
 int ccrs_comm_finalize(void) {
+  peer_teardown();
   if (g_comm.comm && nccl().ok) nccl().CommDestroy(g_comm.comm);
   g_comm.comm = nullptr;
   return 0;

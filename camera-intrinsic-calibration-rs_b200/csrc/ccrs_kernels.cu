@@ -71,6 +71,26 @@ __global__ void k_arm(double* p, size_t n) {
     p[i] = __longlong_as_double(kArmBits);
 }
 
+// value v of this rank's partial -> sum over ranks (see PeerXchg). Called by one thread per value.
+CCRS_D double peer_exchange(const PeerXchg& px, int v, double mine) {
+  const size_t slot = (size_t)px.off + v;
+  for (int r = 0; r < px.world; ++r)
+    *reinterpret_cast<volatile double*>(px.peer[r] + slot + (size_t)px.rank * kXchgMaxVals) = mine;
+  volatile double* loc = px.peer[px.rank] + slot;
+  double tot = 0.0;
+  const long long t0 = clock64();
+  for (int r = 0; r < px.world; ++r) {
+    double x = loc[(size_t)r * kXchgMaxVals];
+    while (__double_as_longlong(x) == kArmBits) {
+      if (clock64() - t0 > 4000000000LL) { x = nan(""); break; }   // ~2 s: a peer never arrived -> poison, not a hang
+      x = loc[(size_t)r * kXchgMaxVals];
+    }
+    tot += x;                                                       // rank order
+    loc[(size_t)r * kXchgMaxVals] = __longlong_as_double(kArmBits); // re-arm for the next use of this area
+  }
+  return tot;
+}
+
 CCRS_D int cur_of(const ProblemDev& pb, int prob) { return pb.cur ? pb.cur[prob] : pb.cur_val; }
 
 // publish n doubles to mapped host memory: plain stores, no fence — the host armed the n words with a sentinel and
@@ -497,6 +517,12 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
         a += __shfl_xor_sync(0xffffffffu, a, o);
         b += __shfl_xor_sync(0xffffffffu, b, o);
       }
+      if (prm.px.world > 1) {
+        const double mine = lane == 0 ? a : b;
+        const double tot = lane < 2 ? peer_exchange(prm.px, lane, mine) : 0.0;
+        a = __shfl_sync(0xffffffffu, tot, 0);
+        b = __shfl_sync(0xffffffffu, tot, 1);
+      }
       if (lane == 0) {
         prm.stat_dev[0] = a; prm.stat_dev[1] = b;
         *prm.ticket = 0u;
@@ -766,6 +792,7 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(const __grid_constant__
         double tot = s_red[kSchurSplit * threadIdx.x];
 #pragma unroll
         for (int h = 1; h < kSchurSplit; ++h) tot += s_red[kSchurSplit * threadIdx.x + h];
+        if (prm.px.world > 1) tot = peer_exchange(prm.px, threadIdx.x, tot);
         prm.red_out[threadIdx.x] = tot;
         if (prm.host_red) prm.host_red[threadIdx.x] = tot;   // sentinel protocol: no fence
       }

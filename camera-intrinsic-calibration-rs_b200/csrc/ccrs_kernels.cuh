@@ -30,6 +30,19 @@ struct ProblemDev {
   double huber_delta;
 };
 
+// Cross-GPU exchange fused into the producing kernel (frame-sharded problems, one process per GPU on one NVLink
+// node): the thread that holds value v of this rank's partial result stores it straight into slot [rank][v] of EVERY
+// rank's exchange buffer over peer memory, spins until the slots of all ranks in its own buffer are filled, sums them
+// in rank order (bitwise identical on all ranks) and re-arms the slots. Slots validate themselves (armed bit pattern),
+// so there is no fence, no flag and no collective launch. world <= 1 disables it.
+constexpr int kXchgMaxRanks = 8;
+constexpr int kXchgMaxVals = 96;
+struct PeerXchg {
+  double* peer[kXchgMaxRanks];   // rank r's buffer as mapped in this process (peer[rank] is the local buffer)
+  int world, rank;
+  int off;                       // double offset of the [world][kXchgMaxVals] slot area used by this exchange
+};
+
 struct LinParams {
   ProblemDev pb;
   const double* intr_dev;   // [n_problems][D] (batch) — single problem passes intr[] by value below
@@ -55,6 +68,7 @@ struct LinParams {
   volatile double* host_stat;  // mapped pinned [4] = {md, cost, -, seq}; nullptr when a cross-rank exchange follows
   double seq;
   long long* dbg;           // [n_warps][10] per-warp phase clocks (only written by -DCCRS_K2_TIMING builds)
+  PeerXchg px;              // cross-GPU sum of {md, cost} inside the kernel (px.world > 1)
 };
 
 struct SchurParams {
@@ -73,6 +87,7 @@ struct SchurParams {
   volatile double* host_red;    // mapped pinned [NRED+1] (last = seq); nullptr when a cross-rank exchange follows
   double seq;
   long long* dbg;               // [n_warps][8] per-warp phase clocks (only written by -DCCRS_K2_TIMING builds)
+  PeerXchg px;                  // cross-GPU sum of the reduced system inside the kernel (px.world > 1)
 };
 
 struct BacksubParams {

@@ -162,6 +162,10 @@ int ccrs_comm_finalize(void);
 /* deterministic = 1: all-gather the per-rank partials and sum in rank order on every rank (default);
  * 0: ncclAllReduce(sum) as north_star names. */
 int ccrs_comm_set_deterministic(ccrs_problem* p, int deterministic);
+/* 1 when the per-iteration exchange runs over peer memory inside K2/K3 (all ranks on one NVLink node; IPC handles
+ * were exchanged at ccrs_comm_init), 0 when it falls back to NCCL collectives (CCRS_P2P=0, no P2P, non-deterministic
+ * all-reduce requested). */
+int ccrs_comm_uses_peer_memory(void);
 
 /* ---- loop controllers (host side): replace GaussNewtonOptimizer::optimize (util.rs:443-464) and
  * tiny-solver's LevenbergMarquardtOptimizer::optimize (named by north_star). ------------------------ */
