@@ -220,7 +220,7 @@ namespace {
 // Lanes per frame G (1..32; a warp owns 32/G frames): the G that minimises
 // (waves of CTAs) x (observations per lane + per-warp overhead) for this device.
 void choose_slicing(ccrs_problem* p) {
-  const int slots = p->n_sms * kLinCtasPerSm;  // resident CTAs (kLinWarps warps each)
+  const int slots = p->n_sms * kLinCtasPerSm;  // resident CTAs (kLinWarps frame groups each)
   int max_cnt = 1;
   for (int f = 0; f < p->n_frames; ++f) max_cnt = std::max(max_cnt, p->h_frame_offsets[f + 1] - p->h_frame_offsets[f]);
   double best = 1e300;

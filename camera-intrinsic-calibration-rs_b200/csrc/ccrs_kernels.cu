@@ -174,6 +174,153 @@ CCRS_HD constexpr int lin_warp_smem_doubles(int FPW, bool batch, bool cost_only)
          kObsStages * 5 * 32 + kA2bDoubles;
 }
 
+// Executed by the whole warp that took the last ticket: every producer of a {model decrease, cost} partial has taken
+// its ticket, so every partial store has been issued. Sum the n_parts slots in a fixed order, exchange across GPUs,
+// publish.
+CCRS_D void stats_finalize(const LinParams& prm, unsigned n_parts, int lane) {
+  // every warp has taken its ticket, so every partial store has been issued: read the slots from L2 (16 loads
+  // in flight per lane) until none still holds the arming pattern, sum in a fixed order, re-arm for the next launch
+  double2* part = reinterpret_cast<double2*>(prm.cta_part);
+  double a = 0.0, b = 0.0;
+  for (unsigned w0 = lane; w0 < n_parts; w0 += 32 * 16) {
+    double2 t[16];
+    bool ok;
+    do {
+      ok = true;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const unsigned w = w0 + 32 * q;
+        t[q] = w < n_parts ? __ldcg(part + w) : make_double2(0.0, 0.0);
+        ok = ok && (__double_as_longlong(t[q].x) != kArmBits) && (__double_as_longlong(t[q].y) != kArmBits);
+      }
+    } while (!ok);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      a += t[q].x; b += t[q].y;
+      const unsigned w = w0 + 32 * q;
+      if (w < n_parts) part[w] = make_double2(__longlong_as_double(kArmBits), __longlong_as_double(kArmBits));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (prm.px.world > 1) {
+    const double mine = lane == 0 ? a : b;
+    const double tot = lane < 2 ? peer_exchange(prm.px, lane, mine) : 0.0;
+    a = __shfl_sync(0xffffffffu, tot, 0);
+    b = __shfl_sync(0xffffffffu, tot, 1);
+  }
+  if (lane == 0) {
+    prm.stat_dev[0] = a; prm.stat_dev[1] = b;
+    *prm.ticket = 0u;
+    if (prm.host_stat) { double tmp[2] = {a, b}; publish_host(prm.host_stat, tmp, 2); }
+  }
+}
+
+// basis change phi -> rvec on one slice's packed block: H <- T^T H T, T = blkdiag(I_D, J_l, I_3, 1)
+template <class C>
+CCRS_D void basis_change(double (&acc)[C::NACC], const double* __restrict__ Jl) {
+  static_for<0, C::NA>([&](auto Cc) {
+    constexpr int c = decltype(Cc)::value;
+    if constexpr (c < C::D || c >= C::D + 3) {
+      constexpr int k0 = c < C::D ? C::kidx(c, C::D + 0) : C::kidx(C::D + 0, c);
+      constexpr int k1 = c < C::D ? C::kidx(c, C::D + 1) : C::kidx(C::D + 1, c);
+      constexpr int k2 = c < C::D ? C::kidx(c, C::D + 2) : C::kidx(C::D + 2, c);
+      const double h0 = acc[k0], h1 = acc[k1], h2 = acc[k2];
+      acc[k0] = fma(Jl[0], h0, fma(Jl[3], h1, Jl[6] * h2));
+      acc[k1] = fma(Jl[1], h0, fma(Jl[4], h1, Jl[7] * h2));
+      acc[k2] = fma(Jl[2], h0, fma(Jl[5], h1, Jl[8] * h2));
+    }
+  });
+  {
+    constexpr int p = C::D;
+    const double h00 = acc[C::kidx(p, p)], h01 = acc[C::kidx(p, p + 1)], h02 = acc[C::kidx(p, p + 2)];
+    const double h11 = acc[C::kidx(p + 1, p + 1)], h12 = acc[C::kidx(p + 1, p + 2)], h22 = acc[C::kidx(p + 2, p + 2)];
+    double tmp[3][3];  // H_pp * Jl
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      tmp[0][c] = fma(h00, Jl[c], fma(h01, Jl[3 + c], h02 * Jl[6 + c]));
+      tmp[1][c] = fma(h01, Jl[c], fma(h11, Jl[3 + c], h12 * Jl[6 + c]));
+      tmp[2][c] = fma(h02, Jl[c], fma(h12, Jl[3 + c], h22 * Jl[6 + c]));
+    }
+    auto g = [&](int a, int b) { return fma(Jl[a], tmp[0][b], fma(Jl[3 + a], tmp[1][b], Jl[6 + a] * tmp[2][b])); };
+    acc[C::kidx(p, p)] = g(0, 0); acc[C::kidx(p, p + 1)] = g(0, 1); acc[C::kidx(p, p + 2)] = g(0, 2);
+    acc[C::kidx(p + 1, p + 1)] = g(1, 1); acc[C::kidx(p + 1, p + 2)] = g(1, 2); acc[C::kidx(p + 2, p + 2)] = g(2, 2);
+  }
+}
+
+// rank-2 update of the packed Gram block with the two weighted rows of one observation (structural zeros skipped)
+template <class C>
+CCRS_D void gram_accumulate(double (&acc)[C::NACC], const double* __restrict__ au, const double* __restrict__ av) {
+  static_for<0, C::NA>([&](auto I) {
+    static_for<decltype(I)::value, C::NA>([&](auto J) {
+      constexpr int i = decltype(I)::value, j = decltype(J)::value;
+      constexpr int kk = C::kidx(i, j);
+      if constexpr (kk >= 0) {
+        if constexpr (C::hasu(i, j)) acc[kk] = fma(au[i], au[j], acc[kk]);
+        if constexpr (C::hasv(i, j)) acc[kk] = fma(av[i], av[j], acc[kk]);
+      }
+    });
+  });
+}
+
+// Sum the G slices of each frame of a warp in slice order (fixed order -> deterministic) and store the frame blocks SoA.
+// `out` = block buffer + this lane's frame.
+template <class C>
+CCRS_D void slices_reduce_store(double (&acc)[C::NACC], bool active, int lane, int fl, int sl, int G,
+                                double* __restrict__ s_red, const int* __restrict__ s_a2b, double* __restrict__ out, size_t Fs) {
+  constexpr int NCH = (C::NACC + kRedChunk - 1) / kRedChunk;
+  // Staged through the warp's shared memory in chunks of kRedChunk entries, rows padded to kRedStride doubles
+  // (bank-conflict-free both ways). Lane (fl, sl) then sums, for its own frame, the entries e = sl, sl+G, ... over
+  // the frame's G slices in slice order and stores them: every lane of the frame works, the six lanes that hold
+  // the same entry of consecutive frames store consecutive doubles.
+  const double* const srow = s_red + fl * G;
+  static_for<0, NCH>([&](auto CH) {
+    constexpr int ch = decltype(CH)::value;
+    constexpr int cnt = (C::NACC - ch * kRedChunk) < kRedChunk ? (C::NACC - ch * kRedChunk) : kRedChunk;
+    if (ch > 0) __syncwarp();
+    if (active) {
+      static_for<0, cnt>([&](auto E) {
+        constexpr int e = decltype(E)::value;
+        s_red[e * kRedStride + lane] = acc[ch * kRedChunk + e];
+      });
+    }
+    __syncwarp();
+    // the slice count is one of the ten values choose_slicing() can pick: fully unrolled sums, no inner branches
+    auto store_rounds = [&](auto GG) {
+      constexpr int g = decltype(GG)::value;
+      if (active) {
+#pragma unroll 2
+        for (int e = sl; e < cnt; e += (g > 0 ? g : G)) {
+          const double* src = srow + e * kRedStride;
+          double s = src[0];
+          if constexpr (g > 0) {
+#pragma unroll
+            for (int j = 1; j < g; ++j) s += src[j];
+          } else {
+            for (int j = 1; j < G; ++j) s += src[j];
+          }
+          out[(size_t)s_a2b[ch * kRedChunk + e] * Fs] = s;
+        }
+      }
+    };
+    switch (G) {
+      case 1: store_rounds(std::integral_constant<int, 1>{}); break;
+      case 2: store_rounds(std::integral_constant<int, 2>{}); break;
+      case 3: store_rounds(std::integral_constant<int, 3>{}); break;
+      case 4: store_rounds(std::integral_constant<int, 4>{}); break;
+      case 5: store_rounds(std::integral_constant<int, 5>{}); break;
+      case 6: store_rounds(std::integral_constant<int, 6>{}); break;
+      case 8: store_rounds(std::integral_constant<int, 8>{}); break;
+      case 10: store_rounds(std::integral_constant<int, 10>{}); break;
+      case 16: store_rounds(std::integral_constant<int, 16>{}); break;
+      default: store_rounds(std::integral_constant<int, 0>{}); break;
+    }
+  });
+}
+
 template <int MODEL, bool OF, bool BATCH, bool COST_ONLY>
 __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const __grid_constant__ LinParams prm) {
   using C = Cfg<MODEL, OF>;
@@ -330,18 +477,7 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
       // Software-pipelined by hand: the model chain of observation i+1 (rsqrt -> reciprocal -> Huber, one long
       // dependent sequence) is issued in the same basic block as the NACC independent DFMAs that accumulate
       // observation i, so ptxas interleaves them and the FP64 pipe stays busy with two warps per sub-partition.
-      auto accumulate = [&](const double* __restrict__ au, const double* __restrict__ av) {
-        static_for<0, C::NA>([&](auto I) {
-          static_for<decltype(I)::value, C::NA>([&](auto J) {
-            constexpr int i = decltype(I)::value, j = decltype(J)::value;
-            constexpr int kk = C::kidx(i, j);
-            if constexpr (kk >= 0) {
-              if constexpr (C::hasu(i, j)) acc[kk] = fma(au[i], au[j], acc[kk]);
-              if constexpr (C::hasv(i, j)) acc[kk] = fma(av[i], av[j], acc[kk]);
-            }
-          });
-        });
-      };
+      auto accumulate = [&](const double* __restrict__ au, const double* __restrict__ av) { gram_accumulate<C>(acc, au, av); };
       if (beg < end) {
         double au0[C::NA], av0[C::NA], au1[C::NA], av1[C::NA];
         cp_async_wait<kObsStages - 2>();
@@ -366,35 +502,7 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
     }
     CCRS_TCK(2);
     if constexpr (!COST_ONLY) {
-      // basis change phi -> rvec on this slice's block: H <- T^T H T, T = blkdiag(I_D, J_l, I_3, 1)
-      const double* Jl = fc + 12;
-      static_for<0, C::NA>([&](auto Cc) {
-        constexpr int c = decltype(Cc)::value;
-        if constexpr (c < C::D || c >= C::D + 3) {
-          constexpr int k0 = c < C::D ? C::kidx(c, C::D + 0) : C::kidx(C::D + 0, c);
-          constexpr int k1 = c < C::D ? C::kidx(c, C::D + 1) : C::kidx(C::D + 1, c);
-          constexpr int k2 = c < C::D ? C::kidx(c, C::D + 2) : C::kidx(C::D + 2, c);
-          const double h0 = acc[k0], h1 = acc[k1], h2 = acc[k2];
-          acc[k0] = fma(Jl[0], h0, fma(Jl[3], h1, Jl[6] * h2));
-          acc[k1] = fma(Jl[1], h0, fma(Jl[4], h1, Jl[7] * h2));
-          acc[k2] = fma(Jl[2], h0, fma(Jl[5], h1, Jl[8] * h2));
-        }
-      });
-      {
-        constexpr int p = C::D;
-        const double h00 = acc[C::kidx(p, p)], h01 = acc[C::kidx(p, p + 1)], h02 = acc[C::kidx(p, p + 2)];
-        const double h11 = acc[C::kidx(p + 1, p + 1)], h12 = acc[C::kidx(p + 1, p + 2)], h22 = acc[C::kidx(p + 2, p + 2)];
-        double tmp[3][3];  // H_pp * Jl
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          tmp[0][c] = fma(h00, Jl[c], fma(h01, Jl[3 + c], h02 * Jl[6 + c]));
-          tmp[1][c] = fma(h01, Jl[c], fma(h11, Jl[3 + c], h12 * Jl[6 + c]));
-          tmp[2][c] = fma(h02, Jl[c], fma(h12, Jl[3 + c], h22 * Jl[6 + c]));
-        }
-        auto g = [&](int a, int b) { return fma(Jl[a], tmp[0][b], fma(Jl[3 + a], tmp[1][b], Jl[6 + a] * tmp[2][b])); };
-        acc[C::kidx(p, p)] = g(0, 0); acc[C::kidx(p, p + 1)] = g(0, 1); acc[C::kidx(p, p + 2)] = g(0, 2);
-        acc[C::kidx(p + 1, p + 1)] = g(1, 1); acc[C::kidx(p + 1, p + 2)] = g(1, 2); acc[C::kidx(p + 2, p + 2)] = g(2, 2);
-      }
+      basis_change<C>(acc, fc + 12);
     }
   }
 
@@ -434,100 +542,15 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
       pb.frame_cost[cur_of(pb, prob) ^ prm.which][f] = fcost;
     }
   } else {
-    constexpr int NCH = (C::NACC + kRedChunk - 1) / kRedChunk;
-    // Staged through the warp's shared memory in chunks of kRedChunk entries, rows padded to kRedStride doubles
-    // (bank-conflict-free both ways). Lane (fl, sl) then sums, for its own frame, the entries e = sl, sl+G, ... over
-    // the frame's G slices in slice order and stores them: every lane of the frame works, the six lanes that hold
-    // the same entry of consecutive frames store consecutive doubles.
     double* const out = pb.blocks[(BATCH ? (active ? cur_of(pb, pb.frame_problem[f]) : 0) : cur_of(pb, 0)) ^ prm.which] + f;
-    const double* const srow = s_red + fl * G;
-    static_for<0, NCH>([&](auto CH) {
-      constexpr int ch = decltype(CH)::value;
-      constexpr int cnt = (C::NACC - ch * kRedChunk) < kRedChunk ? (C::NACC - ch * kRedChunk) : kRedChunk;
-      if (ch > 0) __syncwarp();
-      if (active) {
-        static_for<0, cnt>([&](auto E) {
-          constexpr int e = decltype(E)::value;
-          s_red[e * kRedStride + lane] = acc[ch * kRedChunk + e];
-        });
-      }
-      __syncwarp();
-      // the slice count is one of the ten values choose_slicing() can pick: fully unrolled sums, no inner branches
-      auto store_rounds = [&](auto GG) {
-        constexpr int g = decltype(GG)::value;
-        if (active) {
-#pragma unroll 2
-          for (int e = sl; e < cnt; e += (g > 0 ? g : G)) {
-            const double* src = srow + e * kRedStride;
-            double s = src[0];
-            if constexpr (g > 0) {
-#pragma unroll
-              for (int j = 1; j < g; ++j) s += src[j];
-            } else {
-              for (int j = 1; j < G; ++j) s += src[j];
-            }
-            out[(size_t)s_a2b[ch * kRedChunk + e] * pb.Fs] = s;
-          }
-        }
-      };
-      switch (G) {
-        case 1: store_rounds(std::integral_constant<int, 1>{}); break;
-        case 2: store_rounds(std::integral_constant<int, 2>{}); break;
-        case 3: store_rounds(std::integral_constant<int, 3>{}); break;
-        case 4: store_rounds(std::integral_constant<int, 4>{}); break;
-        case 5: store_rounds(std::integral_constant<int, 5>{}); break;
-        case 6: store_rounds(std::integral_constant<int, 6>{}); break;
-        case 8: store_rounds(std::integral_constant<int, 8>{}); break;
-        case 10: store_rounds(std::integral_constant<int, 10>{}); break;
-        case 16: store_rounds(std::integral_constant<int, 16>{}); break;
-        default: store_rounds(std::integral_constant<int, 0>{}); break;
-      }
-    });
+    slices_reduce_store<C>(acc, active, lane, fl, sl, G, s_red, s_a2b, out, (size_t)pb.Fs);
   }
 
   CCRS_TCK(4);
   if constexpr (!BATCH) {
     const unsigned last = __shfl_sync(0xffffffffu, (unsigned)(ticket_old == n_warps - 1), 0);
     if (last) {
-      // every warp has taken its ticket, so every partial store has been issued: read the slots from L2 (16 loads
-      // in flight per lane) until none still holds the arming pattern, sum in a fixed order, re-arm for the next launch
-      double2* part = reinterpret_cast<double2*>(prm.cta_part);
-      double a = 0.0, b = 0.0;
-      for (unsigned w0 = lane; w0 < n_warps; w0 += 32 * 16) {
-        double2 t[16];
-        bool ok;
-        do {
-          ok = true;
-#pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const unsigned w = w0 + 32 * q;
-            t[q] = w < n_warps ? __ldcg(part + w) : make_double2(0.0, 0.0);
-            ok = ok && (__double_as_longlong(t[q].x) != kArmBits) && (__double_as_longlong(t[q].y) != kArmBits);
-          }
-        } while (!ok);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          a += t[q].x; b += t[q].y;
-          const unsigned w = w0 + 32 * q;
-          if (w < n_warps) part[w] = make_double2(__longlong_as_double(kArmBits), __longlong_as_double(kArmBits));
-        }
-      }
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
-        a += __shfl_xor_sync(0xffffffffu, a, o);
-        b += __shfl_xor_sync(0xffffffffu, b, o);
-      }
-      if (prm.px.world > 1) {
-        const double mine = lane == 0 ? a : b;
-        const double tot = lane < 2 ? peer_exchange(prm.px, lane, mine) : 0.0;
-        a = __shfl_sync(0xffffffffu, tot, 0);
-        b = __shfl_sync(0xffffffffu, tot, 1);
-      }
-      if (lane == 0) {
-        prm.stat_dev[0] = a; prm.stat_dev[1] = b;
-        *prm.ticket = 0u;
-        if (prm.host_stat) { double tmp[2] = {a, b}; publish_host(prm.host_stat, tmp, 2); }
-      }
+      stats_finalize(prm, n_warps, lane);
     }
   }
 #ifdef CCRS_K2_TIMING
