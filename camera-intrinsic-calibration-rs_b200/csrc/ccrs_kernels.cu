@@ -123,11 +123,66 @@ CCRS_D double obs_rows(const double* __restrict__ ip /* full intrinsics */, cons
                        double* __restrict__ au, double* __restrict__ av) {
   using C = Cfg<MODEL, OF>;
   const double fx = ip[0], fy = OF ? ip[0] : ip[1], cx = ip[2], cy = ip[3];
-  // q = R p ; P = q + t       (Isometry3::new(tvec, rvec) * p3d, factors.rs:162-163)
-  const double qx = fma(fc[0], px, fma(fc[1], py, fc[2] * pz));
-  const double qy = fma(fc[3], px, fma(fc[4], py, fc[5] * pz));
-  const double qz = fma(fc[6], px, fma(fc[7], py, fc[8] * pz));
-  const double X = qx + fc[9], Y = qy + fc[10], Z = qz + fc[11];
+  // P = R p + t as one FMA chain per component, q = R p recovered off the critical path
+  // (Isometry3::new(tvec, rvec) * p3d, factors.rs:162-163)
+  const double X = fma(fc[0], px, fma(fc[1], py, fma(fc[2], pz, fc[9])));
+  const double Y = fma(fc[3], px, fma(fc[4], py, fma(fc[5], pz, fc[10])));
+  const double Z = fma(fc[6], px, fma(fc[7], py, fma(fc[8], pz, fc[11])));
+  const double qx = X - fc[9], qy = Y - fc[10], qz = Z - fc[11];
+  if constexpr (MODEL == UCM || MODEL == EUCM) {
+    // Fused UCM / EUCM path (project_one, factors.rs:165). The dependent chain of an observation is
+    //   rho2 -> 1/rho -> n -> 1/n -> m -> r -> s -> Huber w -> weighted Jacobian rows,
+    // shortened by (i) seeding 1/n from an FP32 evaluation of n that runs beside the FP64 1/rho refinement, and
+    // (ii) forming the rows directly from a = w f / n and b = a m instead of scaling an unweighted Jacobian.
+    const double alpha = ip[4];
+    const double beta = (MODEL == UCM) ? 1.0 : ip[5];
+    const double oma = 1.0 - alpha;
+    const double r2 = fma(X, X, Y * Y);
+    const double rho2 = fma(beta, r2, Z * Z);
+    const float rho2f = (float)rho2;
+    float rhof;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rhof) : "f"(rho2f));
+    float inf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inf) : "f"(fmaf((float)alpha, rhof, (float)oma * (float)Z)));
+    const double irho = rsqrt_fast(rho2);
+    const double rho = rho2 * irho;
+    const double nrm = fma(alpha, rho, oma * Z);
+    const double in = rcp_refine(nrm, (double)inf);
+    const double mx = X * in, my = Y * in;
+    const double ru = fma(fx, mx, cx) - ou;                 // - p2d (factors.rs:167-171)
+    const double rv = fma(fy, my, cy) - ov;
+    const double s = fma(ru, ru, rv * rv);
+    const double w = huber_weight(s, delta);                // Corrector: r *= sqrt(rho'), J *= sqrt(rho')
+    if constexpr (WITH_J) {
+      // dn/dP = (alpha beta x / rho, alpha beta y / rho, alpha z / rho + 1 - alpha); dn/dalpha = rho - z; dn/dbeta = alpha r2 / (2 rho)
+      const double a_irho = alpha * irho, ab_irho = (MODEL == UCM) ? a_irho : a_irho * beta;
+      const double nx = ab_irho * X, ny = ab_irho * Y, nz = fma(a_irho, Z, oma);
+      const double na = rho - Z;
+      const double au_a = (w * fx) * in, av_a = (w * fy) * in;     // a = w f / n
+      const double nbu = -(au_a * mx), nbv = -(av_a * my);         // -b = -a m
+      const double du0 = fma(nbu, nx, au_a), du1 = nbu * ny, du2 = nbu * nz;
+      const double dv0 = nbv * nx, dv1 = fma(nbv, ny, av_a), dv2 = nbv * nz;
+      if constexpr (OF) {
+        au[0] = w * mx; av[0] = w * my;  // shared focal column
+        au[1] = w;                        // cx
+        av[2] = w;                        // cy
+      } else {
+        au[0] = w * mx; av[1] = w * my;
+        au[2] = w; av[3] = w;
+      }
+      au[C::KOFF] = nbu * na; av[C::KOFF] = nbv * na;
+      if constexpr (MODEL == EUCM) {
+        const double nb = (0.5 * alpha) * (r2 * irho);
+        au[C::KOFF + 1] = nbu * nb; av[C::KOFF + 1] = nbv * nb;
+      }
+      au[C::D + 0] = qy * du2 - qz * du1; au[C::D + 1] = qz * du0 - qx * du2; au[C::D + 2] = qx * du1 - qy * du0;
+      av[C::D + 0] = qy * dv2 - qz * dv1; av[C::D + 1] = qz * dv0 - qx * dv2; av[C::D + 2] = qx * dv1 - qy * dv0;
+      au[C::D + 3] = du0; au[C::D + 4] = du1; au[C::D + 5] = du2;
+      av[C::D + 3] = dv0; av[C::D + 4] = dv1; av[C::D + 5] = dv2;
+      au[C::N] = w * ru; av[C::N] = w * rv;
+    }
+    return s * (w * w);
+  } else {
   double m[2], dP[2][3], dk[2][kMaxNd];
   model_eval<MODEL, WITH_J>(ip + 4, X, Y, Z, m, dP, dk);   // project_one (factors.rs:165)
   const double ru = fma(fx, m[0], cx) - ou;                 // - p2d (factors.rs:167-171)
@@ -156,6 +211,7 @@ CCRS_D double obs_rows(const double* __restrict__ ip /* full intrinsics */, cons
     au[C::N] = w * ru; av[C::N] = w * rv;
   }
   return s * w * w;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -321,7 +377,7 @@ CCRS_D void slices_reduce_store(double (&acc)[C::NACC], bool active, int lane, i
   });
 }
 
-template <int MODEL, bool OF, bool BATCH, bool COST_ONLY>
+template <int MODEL, bool OF, bool BATCH, bool COST_ONLY, bool F32>
 __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const __grid_constant__ LinParams prm) {
   using C = Cfg<MODEL, OF>;
   extern __shared__ double smem[];
@@ -364,7 +420,7 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   auto fetch = [&](int kk, int stage) {
     if (kk < end) {
       double* dst = ring + stage * (5 * 32);
-      if (pb.f32) {
+      if constexpr (F32) {
         const float *fx = (const float*)pb.x, *fy = (const float*)pb.y, *fz = (const float*)pb.z, *fu = (const float*)pb.u, *fv = (const float*)pb.v;
         cp_async4(dst, fx + kk); cp_async4(dst + 32, fy + kk); cp_async4(dst + 64, fz + kk);
         cp_async4(dst + 96, fu + kk); cp_async4(dst + 128, fv + kk);
@@ -455,15 +511,14 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   for (int i = 0; i < (COST_ONLY ? 1 : C::NACC); ++i) acc[i] = 0.0;
 
   if (active) {
-    const int f32 = pb.f32;
-    // rows of [J | r] for the observation in ring slot `stage` (branch-free: both widths are read and selected)
+    // rows of [J | r] for the observation in ring slot `stage` (f32 -> f64 widening as factors.rs:141-143)
     auto rows_of = [&](int stage, double* __restrict__ au, double* __restrict__ av) -> double {
       const double* src = ring + stage * (5 * 32);
-      const double px = f32 ? (double)*(const float*)(src) : src[0];
-      const double py = f32 ? (double)*(const float*)(src + 32) : src[32];
-      const double pz = f32 ? (double)*(const float*)(src + 64) : src[64];
-      const double ou = f32 ? (double)*(const float*)(src + 96) : src[96];
-      const double ov = f32 ? (double)*(const float*)(src + 128) : src[128];
+      auto ld = [&](int a) -> double {
+        if constexpr (F32) return (double)*reinterpret_cast<const float*>(src + a * 32);
+        else return src[a * 32];
+      };
+      const double px = ld(0), py = ld(1), pz = ld(2), ou = ld(3), ov = ld(4);
       return obs_rows<MODEL, OF, !COST_ONLY>(ip, fc, px, py, pz, ou, ov, pb.huber_delta, au, av);
     };
     if constexpr (COST_ONLY) {
@@ -1003,9 +1058,9 @@ static size_t lin_smem_bytes(int FPW, bool batch, bool cost_only) {
   return (size_t)kLinWarps * lin_warp_smem_doubles(FPW, batch, cost_only) * sizeof(double);
 }
 
-template <int MODEL, bool OF, bool BATCH, bool COST>
+template <int MODEL, bool OF, bool BATCH, bool COST, bool F32>
 static cudaError_t launch_lin_t(const LinParams& prm, int n_ctas, cudaStream_t s) {
-  auto kern = k_linearize<MODEL, OF, BATCH, COST>;
+  auto kern = k_linearize<MODEL, OF, BATCH, COST, F32>;
   const size_t smem = lin_smem_bytes(prm.FPW, BATCH, COST);
   static bool configured = false;  // per instantiation
   if (!configured) {
@@ -1022,8 +1077,9 @@ cudaError_t launch_linearize(int model, int one_focal, bool batch, bool cost_onl
   return dispatch_model(model, one_focal, [&](auto M, auto OF) {
     constexpr int m = decltype(M)::value;
     constexpr bool of = decltype(OF)::value;
-    if (batch) return cost_only ? launch_lin_t<m, of, true, true>(prm, n_ctas, s) : launch_lin_t<m, of, true, false>(prm, n_ctas, s);
-    return cost_only ? launch_lin_t<m, of, false, true>(prm, n_ctas, s) : launch_lin_t<m, of, false, false>(prm, n_ctas, s);
+    if (batch) return cost_only ? launch_lin_t<m, of, true, true, false>(prm, n_ctas, s) : launch_lin_t<m, of, true, false, false>(prm, n_ctas, s);
+    if (prm.pb.f32) return cost_only ? launch_lin_t<m, of, false, true, true>(prm, n_ctas, s) : launch_lin_t<m, of, false, false, true>(prm, n_ctas, s);
+    return cost_only ? launch_lin_t<m, of, false, true, false>(prm, n_ctas, s) : launch_lin_t<m, of, false, false, false>(prm, n_ctas, s);
   });
 }
 
