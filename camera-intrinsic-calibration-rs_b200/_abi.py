@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("CCRS_B200_LIB") or os.path.join(_HERE, "libccrs_b200.
 SYMBOLS = [
     "ccrs_model_nparams", "ccrs_last_error", "ccrs_problem_create", "ccrs_problem_create_f32", "ccrs_batch_create", "ccrs_problem_destroy", "ccrs_release_cached_memory",
     "ccrs_problem_dim", "ccrs_problem_nblk", "ccrs_problem_n_frames", "ccrs_problem_n_obs", "ccrs_problem_n_problems",
-    "ccrs_set_poses", "ccrs_get_poses", "ccrs_eval_rj", "ccrs_linearize", "ccrs_get_frame_blocks",
+    "ccrs_set_poses", "ccrs_get_poses", "ccrs_eval_rj", "ccrs_validation", "ccrs_linearize", "ccrs_get_frame_blocks",
     "ccrs_compute_scale", "ccrs_set_intr_scale", "ccrs_reduce", "ccrs_backsub", "ccrs_eval_cost", "ccrs_accept",
     "ccrs_comm_unique_id", "ccrs_comm_init", "ccrs_comm_finalize", "ccrs_comm_set_deterministic", "ccrs_comm_uses_peer_memory", "ccrs_default_options",
     "ccrs_solve_gn", "ccrs_solve_lm", "ccrs_controller_gn", "ccrs_controller_lm", "ccrs_calib_camera",
@@ -97,6 +97,7 @@ def load():
     lib.ccrs_set_poses.argtypes = [vp, _dp]
     lib.ccrs_get_poses.argtypes = [vp, _dp]
     lib.ccrs_eval_rj.argtypes = [vp, _dp, _dp, C.c_int, _dp, _dp]
+    lib.ccrs_validation.argtypes = [vp, _dp, _dp, _dp, _dp, _dp]
     lib.ccrs_linearize.argtypes = [vp, _dp, C.c_int, _dp]
     lib.ccrs_get_frame_blocks.argtypes = [vp, C.c_int, _dp]
     lib.ccrs_compute_scale.argtypes = [vp, C.c_int, _dp]

@@ -150,6 +150,15 @@ class Problem:
         check(self.lib.ccrs_eval_rj(self.h, _dp(intr), _dp(pp), int(apply_loss), _dp(r), _dp(J)))
         return r, J
 
+    def validation(self, intr, poses=None, want_errors=False):
+        """util::validation on the device: (median, mean of the best 99 %[, per-point errors])."""
+        intr = _f64(intr)
+        pp = _f64(poses).reshape(-1) if poses is not None else None
+        med, avg = C.c_double(0.0), C.c_double(0.0)
+        e = np.empty(self.n_obs) if want_errors else None
+        check(self.lib.ccrs_validation(self.h, _dp(intr), _dp(pp), C.byref(med), C.byref(avg), _dp(e)))
+        return (med.value, avg.value, e) if want_errors else (med.value, avg.value)
+
     def linearize(self, intr, which=0) -> np.ndarray:
         intr = _f64(intr).reshape(-1)
         sq = np.empty(self.n_problems)
@@ -309,6 +318,27 @@ def calib_camera(frame_feature_list: Sequence[Optional[FrameFeature]], generic_c
     cam = GenericModel(generic_camera.model, params, generic_camera.width, generic_camera.height)
     rt = {i: RvecTvec(tuple(poses[k, :3]), tuple(poses[k, 3:])) for k, i in enumerate(valid)}
     return cam, rt
+
+
+def validation(cam_idx: int, final_result: GenericModel, rtvec_list: Dict[int, RvecTvec],
+               detected_feature_frames: Sequence[Optional[FrameFeature]], recording_option=None,
+               device: int = 0) -> Tuple[float, float]:
+    """Mirror of util::validation (src/util.rs:721-795): (median reprojection error, mean of the best 99 %) in px over
+    every feature of every frame that has a pose. cam_idx / recording_option only label the reference's rerun logging
+    (out of scope here) and are accepted for signature parity."""
+    offs, xs, ys, zs, us, vs, poses = [0], [], [], [], [], [], []
+    for i, rt in rtvec_list.items():
+        ff = detected_feature_frames[i]
+        if ff is None:                                   # util.rs:730
+            continue
+        for fp in ff.features.values():
+            xs.append(fp.p3d[0]); ys.append(fp.p3d[1]); zs.append(fp.p3d[2]); us.append(fp.p2d[0]); vs.append(fp.p2d[1])
+        offs.append(len(xs))
+        poses.append(rt.as_array())
+    f32 = lambda a: np.asarray(a, dtype=np.float32)      # FeaturePoint stores f32 (detected_points.rs:6-9)
+    with Problem(final_result.model, final_result.width, final_result.height, offs, f32(xs), f32(ys), f32(zs), f32(us),
+                 f32(vs), huber_delta=0.0, device=device) as gp:
+        return gp.validation(final_result.params, _f64(poses))
 
 
 class JointProblem:

@@ -815,6 +815,20 @@ int ccrs_get_poses(ccrs_problem* p, double* poses) {
   return 0;
 }
 
+// frame index of every observation (thread-per-observation kernels K1 / K6), built on first use
+static int ensure_obs_frame(ccrs_problem* p) {
+  if (p->have_obs_frame) return 0;
+  const size_t N = (size_t)p->n_obs;
+  std::vector<int32_t> of(N);
+  for (int f = 0; f < p->n_frames; ++f)
+    for (int k = p->h_frame_offsets[f]; k < p->h_frame_offsets[f + 1]; ++k) of[k] = f;
+  CK(p->obs_frame.alloc(N));
+  CK(cudaMemcpyAsync(p->obs_frame.p, of.data(), N * 4, cudaMemcpyHostToDevice, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  p->have_obs_frame = true;
+  return 0;
+}
+
 int ccrs_eval_rj(ccrs_problem* p, const double* intr, const double* poses, int apply_loss, double* r, double* J) {
   if (!p || !intr || !r) return fail(CCRS_ERR_INVALID, "null");
   if (p->batch) return fail(CCRS_ERR_INVALID, "ccrs_eval_rj is for single-problem handles");
@@ -822,15 +836,8 @@ int ccrs_eval_rj(ccrs_problem* p, const double* intr, const double* poses, int a
   int st = flush_pending(p);
   if (st) return st;
   const size_t N = (size_t)p->n_obs;
-  if (!p->have_obs_frame) {
-    std::vector<int32_t> of(N);
-    for (int f = 0; f < p->n_frames; ++f)
-      for (int k = p->h_frame_offsets[f]; k < p->h_frame_offsets[f + 1]; ++k) of[k] = f;
-    CK(p->obs_frame.alloc(N));
-    CK(cudaMemcpyAsync(p->obs_frame.p, of.data(), N * 4, cudaMemcpyHostToDevice, p->stream));
-    CK(cudaStreamSynchronize(p->stream));
-    p->have_obs_frame = true;
-  }
+  st = ensure_obs_frame(p);
+  if (st) return st;
   const int n = p->D + 6;
   DevBuf<double> d_r, d_J, d_pose;
   CK(d_r.alloc(2 * N));
@@ -850,6 +857,62 @@ int ccrs_eval_rj(ccrs_problem* p, const double* intr, const double* poses, int a
   if (J) CK(cudaMemcpyAsync(J, d_J.p, 2 * N * n * 8, cudaMemcpyDeviceToHost, p->stream));
   CK(cudaStreamSynchronize(p->stream));
   d_r.release(); d_J.release(); d_pose.release();
+  return 0;
+}
+
+// validation (src/util.rs:721-795): K6 per-observation errors, then two order statistics and a masked sum by radix
+// select on the device; only 3 x 48 bytes of state + the per-CTA partial sums come back.
+int ccrs_validation(ccrs_problem* p, const double* intr, const double* poses, double* median, double* avg99,
+                    double* errors) {
+  if (!p || !intr || !median || !avg99) return fail(CCRS_ERR_INVALID, "null");
+  if (p->batch) return fail(CCRS_ERR_INVALID, "ccrs_validation is for single-problem handles");
+  CK(cudaSetDevice(p->device));
+  int st = flush_pending(p);
+  if (st) return st;
+  const size_t N = (size_t)p->n_obs;
+  if (N == 0) return fail(CCRS_ERR_INVALID, "no observations");
+  st = ensure_obs_frame(p);
+  if (st) return st;
+  st = upload_intr(p, intr);
+  if (st) return st;
+  DevBuf<double> d_err, d_pose, d_part;
+  DevBuf<unsigned int> d_hist;
+  DevBuf<unsigned long long> d_state;
+  const int n_ctas = p->n_sms * 4;
+  CK(d_err.alloc(N)); CK(d_part.alloc(n_ctas)); CK(d_hist.alloc(2 * kSelBins)); CK(d_state.alloc(6));
+  const double* pose_ptr = p->poses[p->cur_val].p;
+  if (poses) {
+    CK(d_pose.alloc((size_t)p->n_frames * 6));
+    CK(cudaMemcpyAsync(d_pose.p, poses, (size_t)p->n_frames * 48, cudaMemcpyHostToDevice, p->stream));
+    pose_ptr = d_pose.p;
+  }
+  // reprojection_errors[len / 2]; mean of the first len * 99 / 100 sorted errors (util.rs:771-781)
+  const unsigned long long len99 = (unsigned long long)N * 99ull / 100ull;
+  SelectState h_st{};
+  h_st.rank[0] = (unsigned long long)(N / 2);
+  h_st.rank[1] = len99 > 0 ? len99 - 1 : 0;
+  CK(cudaMemcpyAsync(d_state.p, &h_st, sizeof(h_st), cudaMemcpyHostToDevice, p->stream));
+  CK(cudaMemsetAsync(d_hist.p, 0, 2 * kSelBins * sizeof(unsigned int), p->stream));
+  CK(launch_reproj_err(p->model, p->one_focal, p->dev(), p->intr_dev.p, pose_ptr, d_err.p, p->n_obs, p->stream));
+  p->launches++;
+  CK(launch_select(d_err.p, (int64_t)N, reinterpret_cast<SelectState*>(d_state.p), d_hist.p, d_part.p, n_ctas, p->stream,
+                   &p->launches));
+  std::vector<double> part(n_ctas);
+  CK(cudaMemcpyAsync(&h_st, d_state.p, sizeof(h_st), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaMemcpyAsync(part.data(), d_part.p, (size_t)n_ctas * 8, cudaMemcpyDeviceToHost, p->stream));
+  if (errors) CK(cudaMemcpyAsync(errors, d_err.p, N * 8, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  d_err.release(); d_pose.release(); d_part.release(); d_hist.release(); d_state.release();
+  double med, t99;
+  std::memcpy(&med, &h_st.prefix[0], 8);
+  std::memcpy(&t99, &h_st.prefix[1], 8);
+  *median = med;
+  if (len99 == 0) { *avg99 = 0.0; return 0; }
+  double sum_below = 0.0;
+  for (int c = 0; c < n_ctas; ++c) sum_below += part[c];      // CTA order: fixed
+  const double copies = (double)(len99 - h_st.below[1]);      // elements equal to the 99 % threshold that are kept
+  *avg99 = (sum_below + copies * t99) / (double)len99;
+  if (std::isnan(*median) || std::isnan(*avg99)) return fail(CCRS_ERR_NUMERIC, "NaN reprojection error");
   return 0;
 }
 
@@ -1244,6 +1307,13 @@ int ccrs_bench_lm_steps(ccrs_problem* p, const double* intr0, const double* pose
       if (!S) { st = fail(CCRS_ERR_CUDA, "lm_begin failed (%d)", sum.status); break; }
     }
     if (flush_l2) CK(launch_l2_flush(p->l2_flush.p, flush_n, p->stream));
+    if (p->comm && p->world > 1) {
+      // rendezvous outside the event bracket: without it a rank's timed step absorbs its peers' flush / reset skew
+      // (every step waits for all ranks' partial systems)
+      if (!p->l2_flush.p) CK(p->l2_flush.alloc(flush_n));
+      if (nccl().AllReduce(p->l2_flush.p, p->l2_flush.p, 1, kNcclFloat64, kNcclSum, p->comm, p->stream) != 0)
+        return fail(CCRS_ERR_COMM, "bench rendezvous all-reduce failed");
+    }
     CK(cudaStreamSynchronize(p->stream));
     const int64_t l0 = p->launches;
     int done = 0;

@@ -661,6 +661,28 @@ __global__ void __launch_bounds__(128) k_eval_rj(ProblemDev pb, const double* __
   }
 }
 
+// K6 (validation): per-observation reprojection error without the robust loss,
+// sqrt(dx^2 + dy^2) of project_one(T * p3d) - p2d  (src/util.rs:733-745). 48 B/obs: HBM-bound.
+template <int MODEL, bool OF>
+__global__ void __launch_bounds__(128) k_reproj_err(ProblemDev pb, const double* __restrict__ intr_dev,
+                                                    const double* __restrict__ poses, double* __restrict__ err, int64_t n_obs) {
+  using C = Cfg<MODEL, OF>;
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_obs) return;
+  const int f = pb.obs_frame[k];
+  double ip[kMaxFull];
+  if constexpr (OF) { ip[0] = intr_dev[0]; ip[1] = intr_dev[0]; for (int i = 1; i < C::D; ++i) ip[i + 1] = intr_dev[i]; }
+  else { for (int i = 0; i < C::D; ++i) ip[i] = intr_dev[i]; }
+  FramePose fp;
+  pose_from_rvec_tvec(poses + 6 * (size_t)f, fp);
+  double fc[12];
+  for (int i = 0; i < 9; ++i) fc[i] = fp.R[i];
+  for (int i = 0; i < 3; ++i) fc[9 + i] = fp.t[i];
+  const double s = obs_rows<MODEL, OF, false>(ip, fc, ld_obs(pb.x, k, pb.f32), ld_obs(pb.y, k, pb.f32), ld_obs(pb.z, k, pb.f32),
+                                              ld_obs(pb.u, k, pb.f32), ld_obs(pb.v, k, pb.f32), 0.0, nullptr, nullptr);
+  err[k] = sqrt(s);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K3. One thread per frame: scale + damp C_f, Cholesky (registers), Y = L^-1 B'^T, S_f = A'_f - Y^T Y,
 // g_s = g'_a - Y^T L^-1 g'_p, X = L^-T Y and cg = C^-1 g'_p stored for the back-substitution.
@@ -1088,6 +1110,15 @@ cudaError_t launch_eval_rj(int model, int one_focal, const ProblemDev& pb, const
   return dispatch_model(model, one_focal, [&](auto M, auto OF) {
     const int nb = (int)((n_obs + 127) / 128);
     k_eval_rj<decltype(M)::value, decltype(OF)::value><<<nb, 128, 0, s>>>(pb, intr_dev, poses, apply_loss, r, J, n_obs);
+    return cudaGetLastError();
+  });
+}
+
+cudaError_t launch_reproj_err(int model, int one_focal, const ProblemDev& pb, const double* intr_dev, const double* poses,
+                              double* err, int64_t n_obs, cudaStream_t s) {
+  return dispatch_model(model, one_focal, [&](auto M, auto OF) {
+    const int nb = (int)((n_obs + 127) / 128);
+    k_reproj_err<decltype(M)::value, decltype(OF)::value><<<nb, 128, 0, s>>>(pb, intr_dev, poses, err, n_obs);
     return cudaGetLastError();
   });
 }

@@ -128,6 +128,16 @@ cudaError_t launch_trial_stats(const ProblemDev& pb, int rr_idx, int mode, const
 cudaError_t launch_flip_cur(int32_t* cur, const unsigned char* mask_dev, int n_problems, cudaStream_t s);
 // fill p[0..n) with the arming bit pattern (self-validating result slots)
 cudaError_t launch_arm(double* p, size_t n, cudaStream_t s);
+// K6: per-observation reprojection error sqrt(dx^2 + dy^2) without loss (validation, util.rs:733-745)
+cudaError_t launch_reproj_err(int model, int one_focal, const ProblemDev& pb, const double* intr_dev, const double* poses,
+                              double* err, int64_t n_obs, cudaStream_t s);
+// radix select (ccrs_select.cu): exact keys at two ranks of the non-negative doubles v[0..n) plus the sum of the values
+// below the second key. st: in {rank[2]} (prefix, below zeroed), out {prefix = key bits, below = #keys smaller};
+// hist: [2][kSelBins] zeroed; partial: [n_ctas] per-CTA sums of the values below key 1 (sum them in index order).
+constexpr int kSelBins = 2048;
+struct SelectState { unsigned long long prefix[2], rank[2], below[2]; };
+cudaError_t launch_select(const double* v, int64_t n, SelectState* st, unsigned* hist, double* partial, int n_ctas,
+                          cudaStream_t s, int64_t* launches);
 cudaError_t launch_fp64_peak(double* out, int n_ctas, int iters, cudaStream_t s);
 cudaError_t launch_l2_flush(double* buf, size_t n, cudaStream_t s);
 

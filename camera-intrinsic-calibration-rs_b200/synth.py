@@ -184,6 +184,20 @@ def make_calib(model: str = "eucm", n_frames: int = 100, seed: int = 0, noise_px
                           gt_params=gt, gt_poses=poses, init_params=init_params, init_poses=init_poses)
 
 
+def to_frame_features(s: SyntheticCalib, poses: np.ndarray | None = None):
+    """The problem as the reference's types: ([FrameFeature], {frame_idx: RvecTvec}) (detected_points.rs:6-17,
+    types.rs:13-17) with `poses` (default: the perturbed initial poses) as the per-frame initial guess."""
+    from .calib import FeaturePoint, FrameFeature, RvecTvec
+    poses = s.init_poses if poses is None else poses
+    frames, init = [], {}
+    for f in range(s.n_frames):
+        a, b = s.frame_offsets[f], s.frame_offsets[f + 1]
+        feats = {k: FeaturePoint((s.u[a + k], s.v[a + k]), (s.x[a + k], s.y[a + k], s.z[a + k])) for k in range(b - a)}
+        frames.append(FrameFeature(0, (s.width, s.height), feats))
+        init[f] = RvecTvec(tuple(poses[f, :3]), tuple(poses[f, 3:]))
+    return frames, init
+
+
 def intr_from_full(params: np.ndarray, xy_same_focal: bool) -> np.ndarray:
     """calib_camera's `params.remove_row(1)` when --one-focal (util.rs:391-395)."""
     p = np.asarray(params, dtype=np.float64)

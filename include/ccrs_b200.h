@@ -112,6 +112,15 @@ int ccrs_get_poses(ccrs_problem* p, double* poses);
  * poses may be NULL (use the device pose state). Single-problem handles only. */
 int ccrs_eval_rj(ccrs_problem* p, const double* intr, const double* poses, int apply_loss, double* r, double* J);
 
+/* ---- validation: replaces util::validation (src/util.rs:721-795) ----------------------------------------------
+ * Per-point reprojection error sqrt(dx^2 + dy^2) WITHOUT the robust loss at (intr, poses) (util.rs:733-745), then
+ * median = sorted_errors[N / 2] and avg99 = mean of the N * 99 / 100 smallest errors (util.rs:771-781), computed on
+ * the device by radix select (no sort, no per-observation transfer). poses NULL = the device pose state.
+ * errors (nullable, [N], observation order) receives the per-point errors the reference logs to rerun.
+ * Single-problem handles only. */
+int ccrs_validation(ccrs_problem* p, const double* intr, const double* poses, double* median, double* avg99,
+                    double* errors);
+
 /* ---- step-wise hot path: replaces Problem::compute_residual_and_jacobian + J^T J assembly + the
  * per-iteration sparse LLT of tiny-solver (call sites util.rs:455,463,670) ---------- */
 

@@ -377,6 +377,30 @@ void oracle_eval_r(const oracle_problem_t* pb, const double* intr, const double*
     }
 }
 
+// validation (src/util.rs:721-795): per-point error sqrt(dx^2 + dy^2) of project_one(T * p3d) - p2d WITHOUT loss
+// (:733-745); all errors sorted ascending (:771); median = sorted[len / 2] (:772); mean of the first len * 99 / 100
+// computed as sum(p / len99) in sorted order (:777-781). errors_out (nullable): per-point errors, observation order.
+void oracle_validation(const oracle_problem_t* pb, const double* intr, const double* poses, double* median, double* avg99,
+                       double* errors_out) {
+  const size_t N = (size_t)pb->frame_offsets[pb->n_frames];
+  std::vector<double> e(N);
+  set_threads(pb);
+#pragma omp parallel for schedule(static)
+  for (int f = 0; f < pb->n_frames; ++f)
+    for (int k = pb->frame_offsets[f]; k < pb->frame_offsets[f + 1]; ++k) {
+      double r[2];
+      residual_f64(pb, intr, poses + 6 * f, k, r);
+      e[k] = std::sqrt(r[0] * r[0] + r[1] * r[1]);
+    }
+  if (errors_out) std::copy(e.begin(), e.end(), errors_out);
+  std::sort(e.begin(), e.end());
+  *median = N ? e[N / 2] : 0.0;
+  const size_t len99 = N * 99 / 100;
+  double s = 0.0;
+  for (size_t i = 0; i < len99; ++i) s += e[i] / (double)len99;
+  *avg99 = s;
+}
+
 // Parity hook a3 (OtherCamReprojectionFactor, factors.rs:204-228): per observation k of camera i,
 // pose0 = T_0_b of its frame, pose1 = T_i_0. J: 2 x (d_eff + 12), columns [intr | rvec_0_b tvec_0_b | rvec_i_0 tvec_i_0].
 void oracle_othercam_rj(const oracle_problem_t* pb, const double* intr, const double* poses_0_b, const double* pose_i_0,

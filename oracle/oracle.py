@@ -95,6 +95,14 @@ class OracleProblem:
         lib().oracle_eval_r(C.byref(self.c), _dp(intr), _dp(poses), int(apply_loss), _dp(r))
         return r
 
+    def validation(self, intr, poses):
+        """util::validation (src/util.rs:721-795): (median, mean of the best 99 %, per-point errors)."""
+        intr, poses = _f64(intr), _f64(poses)
+        med, avg = C.c_double(0.0), C.c_double(0.0)
+        e = np.empty(self.n_obs)
+        lib().oracle_validation(C.byref(self.c), _dp(intr), _dp(poses), C.byref(med), C.byref(avg), _dp(e))
+        return med.value, avg.value, e
+
     def othercam_rj(self, intr, poses_0_b, pose_i_0, apply_loss=True):
         intr, poses_0_b, pose_i_0 = _f64(intr), _f64(poses_0_b), _f64(pose_i_0)
         r = np.empty(2 * self.n_obs)
