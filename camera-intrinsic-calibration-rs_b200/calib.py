@@ -320,6 +320,49 @@ def calib_camera(frame_feature_list: Sequence[Optional[FrameFeature]], generic_c
     return cam, rt
 
 
+def init_ucm(frame_feature0: FrameFeature, frame_feature1: FrameFeature, rtvec0: RvecTvec, rtvec1: RvecTvec,
+             init_f: float, init_alpha: float, fixed_focal: bool, options: Optional[Options] = None,
+             device: int = 0) -> Optional[GenericModel]:
+    """Mirror of init_ucm (src/util.rs:284-378): [f, alpha] fit on two frames, then the one-focal UCM calibration of
+    those two frames. Returns None where the reference returns None (optimiser failure in the first stage)."""
+    frames = [frame_feature0, frame_feature1]
+    _, offs, x, y, z, u, v, poses = pack_frames(frames, {0: rtvec0, 1: rtvec1})
+    if len(offs) != 3:
+        return None
+    w, h = frame_feature0.img_w_h
+    out = np.empty(5)
+    s = Summary()
+    o = options or default_options()
+    poses = poses.copy()
+    code = _abi.load().ccrs_init_ucm(int(w), int(h), 2, offs.ctypes.data_as(C.POINTER(C.c_int32)), _dp(x), _dp(y), _dp(z),
+                                     _dp(u), _dp(v), float(init_f), float(init_alpha), int(fixed_focal),
+                                     _dp(poses.reshape(-1)), _dp(out), C.byref(o), C.byref(s), int(device))
+    if code in (-4, -5):
+        return None
+    check(code)
+    return GenericModel("ucm", out, int(w), int(h))
+
+
+def convert_model(source_model: GenericModel, target_model: GenericModel, disabled_distortions: int,
+                  options: Optional[Options] = None, device: int = 0) -> None:
+    """Mirror of convert_model (src/util.rs:225-278): target_model.params is updated in place (`&mut GenericModel`)."""
+    from .models import conversion_grid, unproject
+    if int(round(source_model.width)) != int(round(target_model.width)):
+        raise ValueError("source width and target width are not the same.")      # factors.rs:28-29 (panic)
+    if int(round(source_model.height)) != int(round(target_model.height)):
+        raise ValueError("source height and target height are not the same.")    # factors.rs:30-31
+    rays, valid = unproject(source_model.model, source_model.params, conversion_grid(source_model.width, source_model.height))
+    p = np.ascontiguousarray(rays[valid].T)                                        # filter_map(Some) factors.rs:39-42
+    tgt = _f64(target_model.params).copy()
+    src = _f64(source_model.params)
+    s = Summary()
+    o = options or default_options()
+    check(_abi.load().ccrs_convert_model(source_model.model_id(), _dp(src), target_model.model_id(), _dp(tgt),
+                                         int(source_model.width), int(source_model.height), int(disabled_distortions),
+                                         p.shape[1], _dp(p[0]), _dp(p[1]), _dp(p[2]), C.byref(o), C.byref(s), int(device)))
+    target_model.params = tgt
+
+
 def validation(cam_idx: int, final_result: GenericModel, rtvec_list: Dict[int, RvecTvec],
                detected_feature_frames: Sequence[Optional[FrameFeature]], recording_option=None,
                device: int = 0) -> Tuple[float, float]:

@@ -185,6 +185,7 @@ struct ccrs_problem {
   DevBuf<unsigned int> tickets;   // [0] K2 statistics, [1] K3 reduction
   PinBuf<double> h_red, h_stat;   // mapped: single problem [NRED + 1] / [4] (last = sequence number); batch: plain D2H targets
   bool have_scale = false, have_obs_frame = false;
+  bool fixed_poses = false;       // poses are constants (ccrs_set_fixed_poses)
   std::vector<int32_t> h_frame_offsets, h_problem_frame_offsets;
   bool last_use_scale = false;    // state of the last reduce(), needed by the back-substitution
   int cur_val = 0;                // single problem: which state buffer is current (host-tracked, passed by value)
@@ -586,6 +587,7 @@ int do_reduce(ccrs_problem* p, int which, const double* u, int use_scale, double
   prm.intr_scale = use_scale ? p->scale_dev.p : nullptr;
   prm.pose_scale = use_scale ? p->pose_scale.p : nullptr;
   prm.min_diag = min_diag; prm.max_diag = max_diag;
+  prm.no_pose = p->fixed_poses ? 1 : 0;
   prm.elim = p->elim.p;
   prm.frame_red = p->frame_red.p;
   p->last_use_scale = use_scale != 0;
@@ -1242,6 +1244,87 @@ int ccrs_calib_camera(int model, int width, int height, int n_frames, const int3
     st = ccrs_get_poses(p, poses);
   }
   ccrs_problem_destroy(p);
+  return st;
+}
+
+int ccrs_set_fixed_poses(ccrs_problem* p, int fixed) {
+  if (!p) return fail(CCRS_ERR_INVALID, "null");
+  p->fixed_poses = fixed != 0;
+  return 0;
+}
+
+int ccrs_init_ucm(int width, int height, int n_frames, const int32_t* frame_offsets, const double* x, const double* y,
+                  const double* z, const double* u, const double* v, double init_f, double init_alpha, int fixed_focal,
+                  double* poses, double* params_out, const ccrs_options* opt, ccrs_summary* summary, int device_id) {
+  if (!poses || !params_out || !frame_offsets) return fail(CCRS_ERR_INVALID, "null");
+  const double half_w = width / 2.0, half_h = height / 2.0;          // util.rs:293-294
+  // stage 1: one-focal UCM [f, cx, cy, alpha]; cx, cy are constants of UCMInitFocalAlphaFactor -> mask 2
+  ccrs_problem* p = nullptr;
+  int st = ccrs_problem_create(&p, CCRS_UCM, width, height, 1, n_frames, frame_offsets, x, y, z, u, v, 1.0, device_id);
+  if (st) return st;
+  const double inf = std::numeric_limits<double>::infinity();
+  double intr[4] = {init_f, half_w, half_h, init_alpha};
+  const double lo[4] = {init_f / 3.0, -inf, -inf, 1e-6}, hi[4] = {init_f * 3.0, inf, inf, 1.0};   // util.rs:337-338
+  const unsigned char fixed[4] = {(unsigned char)(fixed_focal ? 1 : 0), 2, 2, 0};                  // util.rs:330-332
+  ccrs_summary s1{}, s2{};
+  st = ccrs_set_poses(p, poses);
+  if (!st) st = ccrs_solve_gn(p, intr, lo, hi, fixed, opt, &s1, nullptr);
+  if (!st) st = ccrs_get_poses(p, poses);
+  ccrs_problem_destroy(p);
+  if (st) { s1.status = st; if (summary) *summary = s1; return st; }
+  // stage 2: calib_camera(frames, UCM[f f w/2 h/2 alpha], one_focal = true, 0, fixed_focal)  (util.rs:358-372)
+  params_out[0] = intr[0]; params_out[1] = intr[0]; params_out[2] = half_w; params_out[3] = half_h; params_out[4] = intr[3];
+  st = ccrs_calib_camera(CCRS_UCM, width, height, n_frames, frame_offsets, x, y, z, u, v, params_out, poses, 1, 0,
+                         fixed_focal, 0, opt, &s2, device_id);
+  s2.iterations += s1.iterations; s2.device_ms += s1.device_ms;
+  if (summary) *summary = s2;
+  return st;
+}
+
+int ccrs_convert_model(int src_model, const double* src_params, int tgt_model, double* tgt_params, int width, int height,
+                       int disabled_distortions, int n_pts, const double* px, const double* py, const double* pz,
+                       const ccrs_options* opt_in, ccrs_summary* summary, int device_id) {
+  if (!src_params || !tgt_params || !px || !py || !pz || n_pts <= 0) return fail(CCRS_ERR_INVALID, "null / empty");
+  const int ns = ccrs_model_nparams(src_model), nt = ccrs_model_nparams(tgt_model);
+  if (ns < 0 || nt < 0) return fail(CCRS_ERR_INVALID, "bad model");
+  if (disabled_distortions < 0 || disabled_distortions > nt - 4) return fail(CCRS_ERR_INVALID, "disabled_distortions out of range");
+  ccrs_summary sum{};
+  if (src_model == CCRS_UCM && (tgt_model == CCRS_EUCM || tgt_model == CCRS_EUCMT)) {   // util.rs:230-243
+    for (int i = 0; i < 5; ++i) tgt_params[i] = src_params[i];
+    tgt_params[5] = 1.0;
+    if (tgt_model == CCRS_EUCMT) { tgt_params[6] = 0.0; tgt_params[7] = 0.0; }
+    if (summary) *summary = sum;
+    return 0;
+  }
+  const int32_t fo[2] = {0, n_pts};
+  std::vector<double> zeros((size_t)n_pts, 0.0), uv((size_t)2 * n_pts), u0(n_pts), v0(n_pts);
+  const double pose[6] = {0, 0, 0, 0, 0, 0};
+  // p2ds0 = source.project(p3ds) (factors.rs:59): residual of the source model against zero observations
+  ccrs_problem* ps = nullptr;
+  int st = ccrs_problem_create(&ps, src_model, width, height, 0, 1, fo, px, py, pz, zeros.data(), zeros.data(), 0.0, device_id);
+  if (st) return st;
+  st = ccrs_eval_rj(ps, src_params, pose, 0, uv.data(), nullptr);
+  ccrs_problem_destroy(ps);
+  if (st) return st;
+  for (int k = 0; k < n_pts; ++k) { u0[k] = uv[2 * k]; v0[k] = uv[2 * k + 1]; }
+  ccrs_problem* pt = nullptr;
+  st = ccrs_problem_create(&pt, tgt_model, width, height, 0, 1, fo, px, py, pz, u0.data(), v0.data(), 0.0, device_id);
+  if (st) return st;
+  std::vector<double> intr(tgt_params, tgt_params + nt), lo(nt), hi(nt);
+  for (int i = 0; i < 4; ++i) intr[i] = src_params[i];                                     // util.rs:253-255
+  std::vector<unsigned char> fixed(nt, 0);
+  ccrs_model_bounds(tgt_model, width, height, lo.data(), hi.data());                         // util.rs:262
+  for (int i = 0; i < disabled_distortions; ++i) { fixed[nt - 1 - i] = 1; intr[nt - 1 - i] = 0.0; }   // util.rs:263-270
+  ccrs_options opt;
+  if (opt_in) opt = *opt_in; else ccrs_default_options(&opt);
+  opt.block_huber_delta = 1.0;                                                               // util.rs:250
+  st = ccrs_set_fixed_poses(pt, 1);
+  if (!st) st = ccrs_set_poses(pt, pose);
+  if (!st) st = ccrs_solve_gn(pt, intr.data(), lo.data(), hi.data(), fixed.data(), &opt, &sum, nullptr);
+  ccrs_problem_destroy(pt);
+  sum.status = st;
+  if (summary) *summary = sum;
+  if (!st) for (int i = 0; i < nt; ++i) tgt_params[i] = intr[i];
   return st;
 }
 

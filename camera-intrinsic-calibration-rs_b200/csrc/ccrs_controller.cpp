@@ -19,6 +19,10 @@ constexpr bool kErrorIsL2Norm = true;   // optimisers compare ||r||, not ||r||^2
 constexpr double kLmRejectFactor0 = 2.0;
 
 inline double err_metric(double sq) { return kErrorIsL2Norm ? std::sqrt(sq) : sq; }
+// One HuberLoss over the WHOLE residual vector (ModelConvertFactor is a single residual block, util.rs:246-251):
+// the corrector scales r and J by the same w = sqrt(rho'(s)), s = ||r||^2, so the Gauss-Newton step is unchanged and
+// only the error the stop tests see becomes ||w r||^2 = delta sqrt(s) outside the quadratic region.
+inline double block_loss(double sq, double delta) { return (delta > 0.0 && sq > delta * delta) ? delta * std::sqrt(sq) : sq; }
 
 // in-place lower Cholesky of a dense n x n SPD matrix; false on a non-positive pivot
 bool chol_factor(double* A, int n) {
@@ -58,9 +62,9 @@ int solve_intrinsics(const Reduced& r, int d, double u, double min_diag, double 
     dd[i] = std::min(std::max(r.diag[i], min_diag), max_diag);
     S[i * d + i] += u * dd[i];
   }
-  if (fixed && fixed_mode == 1)
+  if (fixed)
     for (int i = 0; i < d; ++i)
-      if (fixed[i]) { for (int j = 0; j < d; ++j) { S[i * d + j] = 0; S[j * d + i] = 0; } S[i * d + i] = 1; g[i] = 0; }
+      if (fixed[i] == 2 || (fixed[i] && fixed_mode == 1)) { for (int j = 0; j < d; ++j) { S[i * d + j] = 0; S[j * d + i] = 0; } S[i * d + i] = 1; g[i] = 0; }
   for (int i = 0; i < d * d; ++i) if (std::isnan(S[i])) return CCRS_ERR_CHOLESKY;  // poisoned by a failed frame pivot
   if (!chol_factor(S.data(), d)) return CCRS_ERR_CHOLESKY;
   for (int i = 0; i < d; ++i) y[i] = g[i];
@@ -105,6 +109,7 @@ void ccrs_default_options(ccrs_options* o) {
   o->fixed_mode = 0;
   o->speculative = 1;
   o->verbose = 0;
+  o->block_huber_delta = 0.0;
 }
 
 int ccrs_controller_gn(const ccrs_backend* be, double* intr, const double* lo, const double* hi,
@@ -128,7 +133,7 @@ int ccrs_controller_gn(const ccrs_backend* be, double* intr, const double* lo, c
     for (int p = 0; p < P; ++p) {
       if (!active[p]) continue;
       const Reduced r = view(&out[(size_t)p * NOUT], d);
-      const double err = err_metric(r.sq_err);
+      const double err = err_metric(block_loss(r.sq_err, opt.block_huber_delta));
       if (p == 0) { if (err_hist) err_hist[it] = err; sum->final_error = err; }
       if (err < opt.min_error) { active[p] = 0; stop[p] = 1; continue; }
       if (std::isnan(err)) { active[p] = 0; worst = CCRS_ERR_NUMERIC; continue; }

@@ -724,13 +724,14 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(const __grid_constant__
     for (int a = 0; a < D; ++a) sa[a] = prm.intr_scale ? prm.intr_scale[prob * D + a] : 1.0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) sp[i] = prm.pose_scale ? prm.pose_scale[(size_t)i * Fs + f] : 1.0;
-    // C' (lower, in place Cholesky), damping
+    // C' (lower, in place Cholesky), damping. no_pose: the frame's pose is not a variable (intrinsics-only problems)
+    const bool np = prm.no_pose != 0;
     double L[6][6], gp[6], dd[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
 #pragma unroll
-      for (int j = 0; j <= i; ++j) L[i][j] = sp[i] * H(D + j, D + i) * sp[j];
-      gp[i] = -sp[i] * H(D + i, N);
+      for (int j = 0; j <= i; ++j) L[i][j] = np ? (i == j ? 1.0 : 0.0) : sp[i] * H(D + j, D + i) * sp[j];
+      gp[i] = np ? 0.0 : -sp[i] * H(D + i, N);
       dd[i] = fmin(fmax(L[i][i], prm.min_diag), prm.max_diag);
       L[i][i] = fma(u, dd[i], L[i][i]);
     }
@@ -757,7 +758,7 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(const __grid_constant__
     for (int a = 0; a < D; ++a) {
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        double s = sa[a] * H(a, D + i) * sp[i];
+        double s = np ? 0.0 : sa[a] * H(a, D + i) * sp[i];
 #pragma unroll
         for (int k = 0; k < i; ++k) s -= L[i][k] * Yv[a][k];
         Yv[a][i] = s * L[i][i];

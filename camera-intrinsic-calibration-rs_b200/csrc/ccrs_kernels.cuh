@@ -79,6 +79,7 @@ struct SchurParams {
   const double* pose_scale;     // [6][Fs] or nullptr
   double u_val;                 // single problem: damping by value (u_dev == nullptr)
   double min_diag, max_diag;
+  int no_pose;                  // poses are constants of the problem (ModelConvertFactor): B' = 0, g'_p = 0, C' = I
   double* elim;                 // [(6D+18)][Fs]: X (6xD), cg (6), g'_p (6), Dd (6)
   double* frame_red;            // batch: [NRED][Fs] per-frame contributions; single: [n_ctas][NRED] CTA partials
   // single problem: the last CTA sums the CTA partials in CTA order

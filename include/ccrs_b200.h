@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CCRS_ABI_VERSION 1
+#define CCRS_ABI_VERSION 2
 
 /* GenericModel variants of camera-intrinsic-model ^0.8 (CLI names: src/bin/camera_calibration.rs:35).
  * Parameter order:
@@ -190,6 +190,9 @@ typedef struct ccrs_options {
                                  (tiny-solver ParameterBlock::update_params); 1: eliminated */
   int speculative;            /* LM: 1 = linearise at the trial point instead of a residual-only pass (default) */
   int verbose;
+  double block_huber_delta;   /* GN only, 0 = off: ONE Huber loss over the whole residual vector (a problem that is a
+                                 single residual block, ModelConvertFactor util.rs:246-251): changes the error the stop
+                                 tests see, not the step. Use with a handle created with huber_delta <= 0. */
 } ccrs_options;
 void ccrs_default_options(ccrs_options* o);
 
@@ -203,7 +206,9 @@ typedef struct ccrs_summary {
 } ccrs_summary;
 
 /* intr[n_problems][d] in/out; lo/hi [d] nullable (set_variable_bounds, util.rs:29-49);
- * fixed[d] nullable (fix_variable, util.rs:50-71, :459-464). Poses are the device pose state.
+ * fixed[d] nullable: 1 = fix_variable (util.rs:50-71, :459-464; handled per fixed_mode), 2 = not a variable of the
+ * problem at all (always removed from the linear system; UCMInitFocalAlphaFactor's constant cx, cy).
+ * Poses are the device pose state.
  * err_hist nullable [max_iteration] (problem 0). */
 int ccrs_solve_gn(ccrs_problem* p, double* intr, const double* lo, const double* hi, const unsigned char* fixed,
                   const ccrs_options* opt, ccrs_summary* summary, double* err_hist);
@@ -248,6 +253,34 @@ int ccrs_calib_camera(int model, int width, int height, int n_frames, const int3
                       const double* x, const double* y, const double* z, const double* u, const double* v,
                       double* params, double* poses, int xy_same_focal, int disabled_distortions, int fixed_focal,
                       int use_lm, const ccrs_options* opt, ccrs_summary* summary, int device_id);
+
+/* Poses as constants: the per-frame pose blocks are not variables (K3 skips their elimination, K4 leaves them
+ * untouched). Intrinsics-only problems such as ModelConvertFactor (factors.rs:11-77). */
+int ccrs_set_fixed_poses(ccrs_problem* p, int fixed);
+
+/* ---- init_ucm (src/util.rs:284-378) ------------------------------------------------------------------------------
+ * Stage 1 (util.rs:295-357): Gauss-Newton over "params" = [f, alpha] of a UCM whose principal point is the image
+ * centre (UCMInitFocalAlphaFactor, factors.rs:83-120) and the poses of the given frames (two in the reference), Huber
+ * loss 1.0, f in [init_f / 3, 3 init_f], alpha in [1e-6, 1], fixed_focal = fix_variable("params", 0). It runs on the
+ * ReprojectionFactor kernels as a one-focal UCM problem whose cx, cy are removed from the linear system.
+ * Stage 2 (util.rs:358-372): calib_camera(frames, UCM[f, f, w/2, h/2, alpha], one_focal = true, 0, fixed_focal); the
+ * stage-1 poses are its initial poses (the reference re-runs SQPnP there; pose initialisation is an input here).
+ * params_out[5] = fx fy cx cy alpha; poses[n_frames][6] in/out. */
+int ccrs_init_ucm(int width, int height, int n_frames, const int32_t* frame_offsets,
+                  const double* x, const double* y, const double* z, const double* u, const double* v,
+                  double init_f, double init_alpha, int fixed_focal, double* poses, double* params_out,
+                  const ccrs_options* opt, ccrs_summary* summary, int device_id);
+
+/* ---- convert_model (src/util.rs:225-278) -------------------------------------------------------------------------
+ * Fit the target model to the source model on n_pts 3D points (px, py, pz: the source's unprojected pixel grid,
+ * ModelConvertFactor::new factors.rs:22-48 — unprojection belongs to the model crate and stays with the caller).
+ * UCM -> EUCM / EUCMT is the reference's closed form (util.rs:230-243). Otherwise: the source projections are evaluated
+ * on the device, the target's parameters start from tgt_params with fx fy cx cy taken from the source (util.rs:253-255),
+ * bounds and disabled distortions as util.rs:262-271, one Huber(1.0) over the whole block, Gauss-Newton on K2/K3 with
+ * the (identity) pose held constant. tgt_params[nparams(tgt)] in/out. */
+int ccrs_convert_model(int src_model, const double* src_params, int tgt_model, double* tgt_params, int width, int height,
+                       int disabled_distortions, int n_pts, const double* px, const double* py, const double* pz,
+                       const ccrs_options* opt, ccrs_summary* summary, int device_id);
 
 /* ---- joint multi-camera refinement: calib_all_camera_with_extrinsics (src/util.rs:567-715) ----------------------
  * Variables "params{c}" (d per camera), "rvec_{c}_0"/"tvec_{c}_0" (camera c <- camera 0, c > 0) and

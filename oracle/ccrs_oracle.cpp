@@ -675,3 +675,144 @@ int oracle_joint_gn(const oracle_joint_t* jp, double* intr, double* extr, double
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// N4: the two small optimisation problems of src/optimization that use other factors.
+// Restated directly from the reference (dense normal equations over the reference's own variable blocks), NOT through
+// the per-frame elimination machinery above, so that they check the product's reuse of its kernels independently.
+// =====================================================================================================================
+namespace {
+
+// generic dense Gauss-Newton step bookkeeping shared by the two problems below: tiny-solver semantics
+// (error = ||corrected r||, stop tests on successive errors, additive update, clamp, fixed indices reset)
+struct DenseGn {
+  int M;                                  // number of scalars
+  std::vector<double> x, lo, hi;          // lo > hi  <=> unbounded
+  std::vector<unsigned char> fixed;
+};
+
+template <class Lin>
+int dense_gn(DenseGn& P, const oracle_options_t* opt, oracle_result_t* res, double* err_hist, Lin&& linearize) {
+  const int M = P.M;
+  std::vector<double> H((size_t)M * M), g(M);
+  double last_err = 0.0;
+  res->iterations = 0; res->status = 0; res->stop_reason = 0; res->n_accepted = res->n_rejected = 0;
+  for (int it = 0; it < opt->max_iteration; ++it) {
+    std::fill(H.begin(), H.end(), 0.0); std::fill(g.begin(), g.end(), 0.0);
+    const double sq = linearize(P.x.data(), H.data(), g.data());   // H = J^T J, g = -J^T r (corrected), returns sum r'^2
+    const double err = err_metric(sq);
+    if (err_hist) err_hist[it] = err;
+    res->iterations = it + 1; res->final_error = err;
+    if (err < opt->min_error) { res->stop_reason = 1; break; }
+    if (std::isnan(err)) { res->status = -1; return -1; }
+    if (it > 0) {
+      if (std::fabs(last_err - err) < opt->min_abs_decrease) { res->stop_reason = 2; break; }
+      if (std::fabs(last_err - err) / last_err < opt->min_rel_decrease) { res->stop_reason = 3; break; }
+    }
+    last_err = err;
+    if (!chol_factor(H, M)) { res->status = -2; return -2; }
+    chol_solve(H, M, g.data());
+    for (int i = 0; i < M; ++i) {
+      double v = P.x[i] + g[i];
+      if (P.lo[i] <= P.hi[i]) v = std::min(std::max(v, P.lo[i]), P.hi[i]);
+      if (P.fixed[i]) v = P.x[i];
+      P.x[i] = v;
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// init_ucm, first stage (src/util.rs:284-357): variables "params" = [f, alpha], "rvec{0,1}", "tvec{0,1}";
+// one UCMInitFocalAlphaFactor block per feature of the two frames (factors.rs:101-120: cam = [f, f, cx, cy, alpha] with
+// cx, cy the constants of the target model), HuberLoss(1.0) per block; bounds f in [f0/3, 3 f0], alpha in [1e-6, 1];
+// fixed_focal fixes params[0]. Frame f owns observations [frame_offsets[f], frame_offsets[f+1]), n_frames == 2.
+// f_alpha[2] and poses[2][6] in/out.
+int oracle_init_ucm_gn(const oracle_problem_t* pb, double cx, double cy, double* f_alpha, double* poses, int fixed_focal,
+                       const oracle_options_t* opt, oracle_result_t* res, double* err_hist) {
+  const int F = pb->n_frames, M = 2 + 6 * F;
+  DenseGn P; P.M = M; P.x.resize(M); P.lo.assign(M, 1.0); P.hi.assign(M, 0.0); P.fixed.assign(M, 0);
+  P.x[0] = f_alpha[0]; P.x[1] = f_alpha[1];
+  for (int i = 0; i < 6 * F; ++i) P.x[2 + i] = poses[i];
+  P.lo[0] = f_alpha[0] / 3.0; P.hi[0] = f_alpha[0] * 3.0;     // util.rs:337
+  P.lo[1] = 1e-6; P.hi[1] = 1.0;                               // util.rs:338
+  if (fixed_focal) P.fixed[0] = 1;                             // util.rs:330-332
+  const int st = dense_gn(P, opt, res, err_hist, [&](const double* x, double* H, double* g) {
+    double sq = 0.0;
+    for (int f = 0; f < F; ++f)
+      for (int k = pb->frame_offsets[f]; k < pb->frame_offsets[f + 1]; ++k) {
+        const int n = 8;                                       // [f, alpha | rvec | tvec]
+        Dual fa[2] = {Dual::var(x[0], n, 0), Dual::var(x[1], n, 1)};
+        Dual prm[5] = {fa[0], fa[0], Dual(cx, n), Dual(cy, n), fa[1]};          // factors.rs:104-108
+        Dual rv[3], tv[3];
+        for (int i = 0; i < 3; ++i) { rv[i] = Dual::var(x[2 + 6 * f + i], n, 2 + i); tv[i] = Dual::var(x[2 + 6 * f + 3 + i], n, 5 + i); }
+        Dual p[3] = {Dual(pb->x[k], n), Dual(pb->y[k], n), Dual(pb->z[k], n)};
+        Dual Pc[3], uv[2];
+        isometry_apply<Dual>(rv, tv, p, Pc);
+        project_one<Dual>(UCM, prm, Pc, uv);
+        const Dual r0 = uv[0] - pb->u[k], r1 = uv[1] - pb->v[k];
+        const double w = huber_sqrt_rho1(r0.v * r0.v + r1.v * r1.v, pb->huber_delta);
+        const Dual* rr[2] = {&r0, &r1};
+        auto gi = [&](int c) { return c < 2 ? c : 2 + 6 * f + (c - 2); };
+        for (int q = 0; q < 2; ++q) {
+          const double rq = rr[q]->v * w;
+          sq += rq * rq;
+          for (int a = 0; a < n; ++a) {
+            const double ja = rr[q]->d[a] * w;
+            g[gi(a)] -= ja * rq;
+            for (int b = 0; b < n; ++b) H[(size_t)gi(a) * M + gi(b)] += ja * rr[q]->d[b] * w;
+          }
+        }
+      }
+    return sq;
+  });
+  f_alpha[0] = P.x[0]; f_alpha[1] = P.x[1];
+  for (int i = 0; i < 6 * F; ++i) poses[i] = P.x[2 + i];
+  return st;
+}
+
+// convert_model (src/util.rs:225-278) from the ModelConvertFactor onwards: ONE residual block of 2 n_pts residuals
+// source.project(p3d) - target.project(p3d) (factors.rs:56-77) under ONE HuberLoss(1.0) (util.rs:246-251: the loss sees
+// the squared norm of the whole block), variable "params" = the target's full parameter vector; lo/hi/fixed from
+// set_problem_parameter_bound / _disabled (util.rs:262-271). p3d[n_pts][3] are the unprojected grid points.
+int oracle_convert_model_gn(int src_model, const double* src_params, int tgt_model, double* tgt_params, int n_pts,
+                            const double* p3d, const double* lo, const double* hi, const unsigned char* fixed,
+                            double huber_delta, const oracle_options_t* opt, oracle_result_t* res, double* err_hist) {
+  const int M = model_nparams(tgt_model);
+  DenseGn P; P.M = M; P.x.assign(tgt_params, tgt_params + M); P.lo.assign(M, 1.0); P.hi.assign(M, 0.0); P.fixed.assign(M, 0);
+  for (int i = 0; i < M; ++i) { if (lo && hi) { P.lo[i] = lo[i]; P.hi[i] = hi[i]; } if (fixed) P.fixed[i] = fixed[i]; }
+  std::vector<double> uv0((size_t)2 * n_pts);
+  for (int k = 0; k < n_pts; ++k) project_one<double>(src_model, src_params, p3d + 3 * k, &uv0[2 * k]);
+  std::vector<double> r((size_t)2 * n_pts), J((size_t)2 * n_pts * M);
+  const int st = dense_gn(P, opt, res, err_hist, [&](const double* x, double* H, double* g) {
+    double s = 0.0;
+    for (int k = 0; k < n_pts; ++k) {
+      Dual prm[16];
+      for (int i = 0; i < M; ++i) prm[i] = Dual::var(x[i], M, i);
+      Dual Pc[3] = {Dual(p3d[3 * k], M), Dual(p3d[3 * k + 1], M), Dual(p3d[3 * k + 2], M)}, uv[2];
+      project_one<Dual>(tgt_model, prm, Pc, uv);
+      for (int q = 0; q < 2; ++q) {
+        const Dual rq = uv0[2 * k + q] - uv[q];                 // p0 - p1 (factors.rs:68)
+        r[2 * k + q] = rq.v; s += rq.v * rq.v;
+        for (int i = 0; i < M; ++i) J[(size_t)(2 * k + q) * M + i] = rq.d[i];
+      }
+    }
+    const double w = huber_sqrt_rho1(s, huber_delta);            // one corrector for the whole block
+    for (int row = 0; row < 2 * n_pts; ++row) {
+      const double rq = r[row] * w;
+      for (int a = 0; a < M; ++a) {
+        const double ja = J[(size_t)row * M + a] * w;
+        g[a] -= ja * rq;
+        for (int b = 0; b < M; ++b) H[(size_t)a * M + b] += ja * J[(size_t)row * M + b] * w;
+      }
+    }
+    return s * w * w;
+  });
+  for (int i = 0; i < M; ++i) tgt_params[i] = P.x[i];
+  return st;
+}
+
+}  // extern "C"

@@ -161,6 +161,34 @@ class OracleProblem:
         return self._run(lib().oracle_lm, intr, poses, lo, hi, fixed, options)
 
 
+def init_ucm_gn(op: "OracleProblem", cx: float, cy: float, f: float, alpha: float, poses, fixed_focal=False, options=None):
+    """init_ucm first stage (util.rs:295-357) on the frames of `op` (a UCM problem; only its observations are used)."""
+    fa = np.array([f, alpha], dtype=np.float64)
+    poses = _f64(poses).copy()
+    o = options or op.default_options()
+    res = Result()
+    hist = np.full(o.max_iteration, np.nan)
+    lib().oracle_init_ucm_gn(C.byref(op.c), C.c_double(cx), C.c_double(cy), _dp(fa), _dp(poses), int(fixed_focal),
+                             C.byref(o), C.byref(res), _dp(hist))
+    return fa, poses.reshape(-1, 6), res, hist[: res.iterations]
+
+
+def convert_model_gn(src_model: int, src_params, tgt_model: int, tgt_params, p3d, lo=None, hi=None, fixed=None,
+                     huber_delta: float = 1.0, options=None):
+    """convert_model's optimisation (util.rs:244-277) on given unprojected points p3d [n,3]."""
+    src = _f64(src_params); tgt = _f64(tgt_params).copy(); p3 = _f64(p3d).reshape(-1, 3)
+    if options is None:
+        options = Options(); lib().oracle_default_options(C.byref(options))
+    res = Result(); hist = np.full(options.max_iteration, np.nan)
+    lo_a = _f64(lo) if lo is not None else None
+    hi_a = _f64(hi) if hi is not None else None
+    fx = np.ascontiguousarray(fixed, dtype=np.uint8) if fixed is not None else None
+    lib().oracle_convert_model_gn(int(src_model), _dp(src), int(tgt_model), _dp(tgt), len(p3), _dp(p3), _dp(lo_a), _dp(hi_a),
+                                  fx.ctypes.data_as(C.POINTER(C.c_ubyte)) if fx is not None else None,
+                                  C.c_double(huber_delta), C.byref(options), C.byref(res), _dp(hist))
+    return tgt, res, hist[: res.iterations]
+
+
 def project(model: int, params, P):
     params, P = _f64(params), _f64(P)
     uv = np.empty(2)
