@@ -1,4 +1,4 @@
-//! Raw bindings to `include/ccrs_b200.h` (ABI version 1). SOURCE ONLY — never compiled in the build image.
+//! Raw bindings to `include/ccrs_b200.h` (ABI version 2). SOURCE ONLY — never compiled in the build image.
 #![allow(non_camel_case_types)]
 use libc::{c_char, c_double, c_int, c_uchar, c_void};
 
@@ -31,6 +31,7 @@ pub struct ccrs_options {
     pub fixed_mode: c_int,
     pub speculative: c_int,
     pub verbose: c_int,
+    pub block_huber_delta: c_double,
 }
 
 #[repr(C)]
@@ -70,6 +71,18 @@ extern "C" {
                              v: *const c_double, params: *mut c_double, poses: *mut c_double, xy_same_focal: c_int,
                              disabled_distortions: c_int, fixed_focal: c_int, use_lm: c_int, opt: *const ccrs_options,
                              summary: *mut ccrs_summary, device_id: c_int) -> c_int;
+    pub fn ccrs_validation(p: *mut ccrs_problem, intr: *const c_double, poses: *const c_double, median: *mut c_double,
+                           avg99: *mut c_double, errors: *mut c_double) -> c_int;
+    pub fn ccrs_set_fixed_poses(p: *mut ccrs_problem, fixed: c_int) -> c_int;
+    pub fn ccrs_init_ucm(width: c_int, height: c_int, n_frames: c_int, frame_offsets: *const i32, x: *const c_double,
+                         y: *const c_double, z: *const c_double, u: *const c_double, v: *const c_double,
+                         init_f: c_double, init_alpha: c_double, fixed_focal: c_int, poses: *mut c_double,
+                         params_out: *mut c_double, opt: *const ccrs_options, summary: *mut ccrs_summary,
+                         device_id: c_int) -> c_int;
+    pub fn ccrs_convert_model(src_model: c_int, src_params: *const c_double, tgt_model: c_int, tgt_params: *mut c_double,
+                              width: c_int, height: c_int, disabled_distortions: c_int, n_pts: c_int,
+                              px: *const c_double, py: *const c_double, pz: *const c_double, opt: *const ccrs_options,
+                              summary: *mut ccrs_summary, device_id: c_int) -> c_int;
     pub fn ccrs_comm_unique_id(unique_id_128: *mut c_void) -> c_int;
     pub fn ccrs_comm_init(p: *mut ccrs_problem, unique_id_128: *const c_void, rank: c_int, world_size: c_int) -> c_int;
     pub fn ccrs_release_cached_memory() -> c_int;
