@@ -226,7 +226,9 @@ void choose_slicing(ccrs_problem* p) {
   for (int f = 0; f < p->n_frames; ++f) max_cnt = std::max(max_cnt, p->h_frame_offsets[f + 1] - p->h_frame_offsets[f]);
   double best = 1e300;
   int bestG = 1;
+  const bool pairs = lin_uses_pairs(p->model, p->one_focal);   // lane-pair K2: the two lanes of a pair share a frame
   for (int G = 1; G <= 32; ++G) {
+    if (pairs && (G & 1)) continue;
     const int fpw = 32 / G;
     const int warps = (p->n_frames + fpw - 1) / fpw;
     const int ctas = (warps + kLinWarps - 1) / kLinWarps;
@@ -237,7 +239,7 @@ void choose_slicing(ccrs_problem* p) {
     const double cost = (double)waves * (per_lane + kLinOverheadIters);
     if (cost < best - 1e-12) { best = cost; bestG = G; }
   }
-  if (const char* e = getenv("CCRS_FORCE_G")) { const int g = atoi(e); if (g >= 1 && g <= 32) bestG = g; }
+  if (const char* e = getenv("CCRS_FORCE_G")) { const int g = atoi(e); if (g >= 1 && g <= 32 && !(pairs && (g & 1))) bestG = g; }
   p->G = bestG;
   p->FPW = 32 / bestG;
   const int warps = (p->n_frames + p->FPW - 1) / p->FPW;

@@ -61,7 +61,31 @@ struct Cfg {
     return k;
   }
   static constexpr int NACC = nacc();
+  // compact rows: the structurally non-zero columns of the u-row / v-row of [J | r], in column order. Both rows have
+  // the same shape [2 row intrinsics (fx cx | fy cy; one focal: f cx | f cy) | distortion | phi | t | r].
+  CCRS_HD static constexpr bool inu(int c) { return c >= D || nzu(c); }
+  CCRS_HD static constexpr bool inv(int c) { return c >= D || nzv(c); }
+  CCRS_HD static constexpr int count_u() { int n = 0; for (int c = 0; c < NA; ++c) n += inu(c) ? 1 : 0; return n; }
+  static constexpr int NU = count_u();     // == number of v-row columns
+  CCRS_HD static constexpr int ucol(int k) { int n = 0; for (int c = 0; c < NA; ++c) if (inu(c)) { if (n == k) return c; ++n; } return -1; }
+  CCRS_HD static constexpr int vcol(int k) { int n = 0; for (int c = 0; c < NA; ++c) if (inv(c)) { if (n == k) return c; ++n; } return -1; }
 };
+
+// Lane-pair variant of K2 for the models whose merged Gram block does not fit the register file (EUCMT, KB4, OPENCV5,
+// FTHETA: 104-132 FP64 accumulators = 208-264 registers, i.e. heavy local-memory spilling): the even lane of a pair
+// accumulates only the u-row products, the odd lane only the v-row products, of BOTH lanes' observations; the rows are
+// swapped with one shuffle per value. One compact row has the shape of a problem with NU columns:
+constexpr int kPairThreshold = 100;   // merged accumulators above which the pair variant is used
+template <class C>
+struct RowCfg {
+  static constexpr int NA = C::NU;
+  static constexpr int D = C::NU - 7;   // row intrinsics + distortion, then phi(3) t(3) r(1)
+  static constexpr int N = NA - 1;
+  static constexpr int NACC = NA * (NA + 1) / 2;
+  CCRS_HD static constexpr int kidx(int i, int j) { return tri_idx(NA, i, j); }
+};
+template <int MODEL, bool OF>
+constexpr bool lin_pair_v = Cfg<MODEL, OF>::NACC > kPairThreshold;
 
 // bit pattern that arms a result slot which validates itself (device partials, mapped host results): a NaN payload
 // no computation produces (the Cholesky-failure poison is the canonical quiet NaN)
@@ -224,7 +248,7 @@ CCRS_D double obs_rows(const double* __restrict__ ip /* full intrinsics */, cons
 // overlap with whatever phase the other resident warps are in.
 // ------------------------------------------------------------------------------------------------
 constexpr int kRedStride = 33;    // row stride of the reduction staging buffer (odd: no bank conflicts)
-constexpr int kA2bDoubles = 72;   // per-warp copy of the accumulator -> block-entry table (<= 144 int32)
+constexpr int kA2bDoubles = 112;  // per-warp copy of the accumulator -> block-entry table (<= 224 int32)
 CCRS_HD constexpr int lin_warp_smem_doubles(int FPW, bool batch, bool cost_only) {
   return FPW * kFrameConst + (batch ? FPW * kMaxFull : 0) + 2 * FPW + (cost_only ? 32 : kRedChunk * kRedStride) +
          kObsStages * 5 * 32 + kA2bDoubles;
@@ -322,6 +346,56 @@ CCRS_D void gram_accumulate(double (&acc)[C::NACC], const double* __restrict__ a
   });
 }
 
+// rank-1 update of one compact row's Gram block (pair variant: every entry is dense)
+template <class R>
+CCRS_D void gram_row(double (&acc)[R::NACC], const double* __restrict__ r) {
+  static_for<0, R::NA>([&](auto A) {
+    static_for<decltype(A)::value, R::NA>([&](auto B) {
+      constexpr int a = decltype(A)::value, b = decltype(B)::value;
+      acc[R::kidx(a, b)] = fma(r[a], r[b], acc[R::kidx(a, b)]);
+    });
+  });
+}
+
+// Pair variant of the frame reduction: compact entry e of the even lanes is a u-row product, of the odd lanes the
+// matching v-row product. Where both land on the same entry of the frame block (columns common to both rows) the G
+// slices are summed in lane order; otherwise the even and the odd lanes are summed separately into their two entries.
+// s_a2b = [dense index of the u-row entry | dense index of the v-row entry], NACC each.
+template <class R>
+CCRS_D void slices_reduce_store_pair(double (&acc)[R::NACC], bool active, int lane, int fl, int sl, int G,
+                                     double* __restrict__ s_red, const int* __restrict__ s_a2b, double* __restrict__ out, size_t Fs) {
+  constexpr int NCH = (R::NACC + kRedChunk - 1) / kRedChunk;
+  const double* const srow = s_red + fl * G;
+  static_for<0, NCH>([&](auto CH) {
+    constexpr int ch = decltype(CH)::value;
+    constexpr int cnt = (R::NACC - ch * kRedChunk) < kRedChunk ? (R::NACC - ch * kRedChunk) : kRedChunk;
+    if (ch > 0) __syncwarp();
+    if (active) {
+      static_for<0, cnt>([&](auto E) {
+        constexpr int e = decltype(E)::value;
+        s_red[e * kRedStride + lane] = acc[ch * kRedChunk + e];
+      });
+    }
+    __syncwarp();
+    if (active) {
+      for (int e = sl; e < cnt; e += G) {
+        const double* src = srow + e * kRedStride;
+        const int bu = s_a2b[ch * kRedChunk + e], bv = s_a2b[R::NACC + ch * kRedChunk + e];
+        if (bu == bv) {
+          double t = src[0];
+          for (int j = 1; j < G; ++j) t += src[j];
+          out[(size_t)bu * Fs] = t;
+        } else {
+          double tu = src[0], tv = src[1];
+          for (int j = 2; j < G; j += 2) { tu += src[j]; tv += src[j + 1]; }
+          out[(size_t)bu * Fs] = tu;
+          out[(size_t)bv * Fs] = tv;
+        }
+      }
+    }
+  });
+}
+
 // Sum the G slices of each frame of a warp in slice order (fixed order -> deterministic) and store the frame blocks SoA.
 // `out` = block buffer + this lane's frame.
 template <class C>
@@ -393,8 +467,11 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   double* s_red = s_stat + 2 * FPW;                      // [kRedChunk][kRedStride]
   double* s_obs = s_red + (COST_ONLY ? 32 : kRedChunk * kRedStride);  // [kObsStages][5][32] cp.async ring of x,y,z,u,v
   int* s_a2b = reinterpret_cast<int*>(s_obs + kObsStages * 5 * 32);  // [NACC] accumulator -> packed block entry
+  constexpr bool PAIR = !COST_ONLY && lin_pair_v<MODEL, OF>;
+  using R = RowCfg<C>;
+  constexpr int NACC_L = COST_ONLY ? 1 : (PAIR ? R::NACC : C::NACC);   // accumulators per lane
   if constexpr (!COST_ONLY) {
-    for (int i = lane; i < C::NACC; i += 32) s_a2b[i] = __ldg(prm.acc_to_blk + i);   // visible after the prologue's __syncwarp
+    for (int i = lane; i < (PAIR ? 2 * R::NACC : C::NACC); i += 32) s_a2b[i] = __ldg(prm.acc_to_blk + i);   // visible after the prologue's __syncwarp
   }
 
 #ifdef CCRS_K2_TIMING
@@ -506,9 +583,46 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   const double* ip = BATCH ? (s_intr + (active ? fl : 0) * kMaxFull) : prm.intr;
   const double* fc = s_fc + (active ? fl : 0) * kFrameConst;
 
-  double acc[COST_ONLY ? 1 : C::NACC];
+  double acc[NACC_L];
 #pragma unroll
-  for (int i = 0; i < (COST_ONLY ? 1 : C::NACC); ++i) acc[i] = 0.0;
+  for (int i = 0; i < NACC_L; ++i) acc[i] = 0.0;
+
+  if constexpr (PAIR) {
+    // every lane of a pair runs the pair's trip count (the even lane's: it owns the extra observation of a ragged
+    // slice); the row exchange below needs both lanes
+    const int n_mine = (active && beg < end) ? (end - beg + G - 1) / G : 0;
+    const int n_pair = max(n_mine, __shfl_xor_sync(0xffffffffu, n_mine, 1));
+    const unsigned pair_mask = 3u << (lane & 30);
+    const bool odd = (lane & 1) != 0;
+    int k = beg;
+    for (int it = 0; it < n_pair; ++it, k += G) {
+      fetch(k + (kObsStages - 1) * G, (it + kObsStages - 1) % kObsStages);
+      cp_async_wait<kObsStages - 1>();
+      const bool valid = it < n_mine;
+      const double* src = ring + (it % kObsStages) * (5 * 32);
+      auto ld = [&](int a) -> double {
+        if constexpr (F32) return (double)*reinterpret_cast<const float*>(src + a * 32);
+        else return src[a * 32];
+      };
+      double au[C::NA], av[C::NA];
+      obs_rows<MODEL, OF, true>(ip, fc, ld(0), ld(1), ld(2), ld(3), ld(4), pb.huber_delta, au, av);
+      // mine: the row this lane accumulates (even: u, odd: v); give: the row its partner accumulates. An exhausted
+      // slice contributes zeros (selected, not multiplied: stale ring data may hold anything).
+      double mine[R::NA], give[R::NA];
+      static_for<0, R::NA>([&](auto Cc) {
+        constexpr int c = decltype(Cc)::value;
+        const double a = au[C::ucol(c)], b = av[C::vcol(c)];
+        mine[c] = valid ? (odd ? b : a) : 0.0;
+        give[c] = valid ? (odd ? a : b) : 0.0;
+      });
+#pragma unroll
+      for (int c = 0; c < R::NA; ++c) give[c] = __shfl_xor_sync(pair_mask, give[c], 1);
+      gram_row<R>(acc, mine);
+      gram_row<R>(acc, give);
+    }
+    CCRS_TCK(2);
+    if (active) basis_change<R>(acc, fc + 12);
+  } else
 
   if (active) {
     // rows of [J | r] for the observation in ring slot `stage` (f32 -> f64 widening as factors.rs:141-143)
@@ -566,7 +680,7 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   //      reduction below, so it equals the stored entry bit for bit); shuffles: the G lanes of a frame are adjacent
   double fcost;
   {
-    const double v = active ? acc[COST_ONLY ? 0 : C::NACC - 1] : 0.0;
+    const double v = active ? acc[NACC_L - 1] : 0.0;
     fcost = v;
     for (int j = 1; j < G; ++j) fcost += __shfl_down_sync(0xffffffffu, v, j);   // valid in slice 0 of each frame
   }
@@ -598,7 +712,8 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
     }
   } else {
     double* const out = pb.blocks[(BATCH ? (active ? cur_of(pb, pb.frame_problem[f]) : 0) : cur_of(pb, 0)) ^ prm.which] + f;
-    slices_reduce_store<C>(acc, active, lane, fl, sl, G, s_red, s_a2b, out, (size_t)pb.Fs);
+    if constexpr (PAIR) slices_reduce_store_pair<R>(acc, active, lane, fl, sl, G, s_red, s_a2b, out, (size_t)pb.Fs);
+    else slices_reduce_store<C>(acc, active, lane, fl, sl, G, s_red, s_a2b, out, (size_t)pb.Fs);
   }
 
   CCRS_TCK(4);
@@ -1061,15 +1176,30 @@ int model_dims(int model, int one_focal, int* D, int* NA, int* NBLK, int* NACC) 
     if (D) *D = C::D;
     if (NA) *NA = C::NA;
     if (NBLK) *NBLK = C::NBLK;
-    if (NACC) *NACC = C::NACC;
+    // entries of the accumulator -> block-entry table: merged accumulators, or [u-row | v-row] for the pair variant
+    if (NACC) *NACC = (C::NACC > kPairThreshold) ? 2 * RowCfg<C>::NACC : C::NACC;
     return 0;
   });
+}
+
+bool lin_uses_pairs(int model, int one_focal) {
+  return dispatch_model(model, one_focal, [&](auto M, auto OF) { return Cfg<decltype(M)::value, decltype(OF)::value>::NACC > kPairThreshold; });
 }
 
 void fill_acc_to_blk(int model, int one_focal, int32_t* table) {
   dispatch_model(model, one_focal, [&](auto M, auto OF) {
     using C = Cfg<decltype(M)::value, decltype(OF)::value>;
     int k = 0;
+    if (C::NACC > kPairThreshold) {
+      using R = RowCfg<C>;
+      for (int a = 0; a < R::NA; ++a)
+        for (int b = a; b < R::NA; ++b) {
+          table[k] = tri_idx(C::NA, C::ucol(a), C::ucol(b));
+          table[R::NACC + k] = tri_idx(C::NA, C::vcol(a), C::vcol(b));
+          ++k;
+        }
+      return 0;
+    }
     for (int i = 0; i < C::NA; ++i)
       for (int j = i; j < C::NA; ++j)
         if (C::has(i, j)) table[k++] = tri_idx(C::NA, i, j);

@@ -107,6 +107,8 @@ inline int nred_of(int D) { return D * (D + 1) / 2 + 3 * D + 1; }
 
 int model_dims(int model, int one_focal, int* D, int* NA, int* NBLK, int* NACC);
 void fill_acc_to_blk(int model, int one_focal, int32_t* table);
+// K2 runs its lane-pair variant for this model (needs an even number of lanes per frame)
+bool lin_uses_pairs(int model, int one_focal);
 
 cudaError_t launch_linearize(int model, int one_focal, bool batch, bool cost_only, const LinParams& prm, int n_ctas,
                              cudaStream_t s);
