@@ -8,7 +8,7 @@ the root-level alias module `ccrs_b200`.
 from . import _abi
 from ._abi import CcrsError, Options, Summary, default_options, LIB_PATH, SYMBOLS
 from .calib import (MODELS, FeaturePoint, FrameFeature, GenericModel, JointProblem, Problem, RvecTvec,
-                    calib_all_camera_with_extrinsics, calib_camera, comm_unique_id, convert_model, init_ucm,
+                    calib_all_camera_with_extrinsics, calib_camera, comm_unique_id, convert_model, init_poses, init_ucm, initial_poses,
                     measure_fp64_peak, model_bounds, pack_frames, validation)
 from . import synth
 from . import models
@@ -16,4 +16,4 @@ from . import dist
 
 __all__ = ["CcrsError", "Options", "Summary", "default_options", "LIB_PATH", "SYMBOLS", "MODELS", "FeaturePoint",
            "FrameFeature", "GenericModel", "JointProblem", "calib_all_camera_with_extrinsics", "Problem", "RvecTvec", "calib_camera", "comm_unique_id", "measure_fp64_peak",
-           "model_bounds", "pack_frames", "validation", "convert_model", "init_ucm", "synth", "models", "dist"]
+           "model_bounds", "pack_frames", "validation", "convert_model", "init_poses", "initial_poses", "init_ucm", "synth", "models", "dist"]

@@ -320,6 +320,49 @@ def calib_camera(frame_feature_list: Sequence[Optional[FrameFeature]], generic_c
     return cam, rt
 
 
+def init_poses(frame_offsets, x, y, z, xn, yn, device: int = 0, want_cost: bool = False):
+    """All frames' initial board poses in one launch (ccrs_init_poses). Returns poses [F, 6] (rvec, tvec)."""
+    fo = np.ascontiguousarray(frame_offsets, dtype=np.int32)
+    xs, ys, zs, a, b = map(_f64, (x, y, z, xn, yn))
+    poses = np.empty((len(fo) - 1, 6))
+    cost = np.empty(len(fo) - 1)
+    check(_abi.load().ccrs_init_poses(len(fo) - 1, fo.ctypes.data_as(C.POINTER(C.c_int32)), _dp(xs), _dp(ys), _dp(zs), _dp(a),
+                                      _dp(b), _dp(poses.reshape(-1)), _dp(cost), int(device)))
+    return (poses, cost) if want_cost else poses
+
+
+def initial_poses(frame_feature_list: Sequence[Optional[FrameFeature]], generic_camera: GenericModel,
+                  device: int = 0) -> Dict[int, RvecTvec]:
+    """The pose-initialisation part of calib_camera (src/util.rs:401-441) for every frame at once: unproject the
+    detections with the current model (host, models.unproject), drop points outside its domain and frames left with
+    fewer than 10 points (util.rs:431-433), normalise to z = 1 rounded to f32 like `glam::Vec2::new(.. as f32, ..)`
+    (util.rs:425), and solve all frames in one launch. Returns {frame_idx: RvecTvec} for the valid frames."""
+    from .models import unproject
+    idx, offs, xs, ys, zs, xn, yn = [], [0], [], [], [], [], []
+    for i, ff in enumerate(frame_feature_list):
+        if ff is None:
+            continue
+        p2 = np.array([fp.p2d for fp in ff.features.values()], dtype=np.float32).astype(np.float64).reshape(-1, 2)
+        p3 = np.array([fp.p3d for fp in ff.features.values()], dtype=np.float32).astype(np.float64).reshape(-1, 3)
+        if len(p2) == 0:
+            continue
+        rays, valid = unproject(generic_camera.model, generic_camera.params, p2)
+        valid &= np.abs(rays[:, 2]) > 1e-12
+        if valid.sum() < MIN_POINTS_PER_FRAME:
+            continue
+        r = rays[valid]
+        xs.append(p3[valid, 0]); ys.append(p3[valid, 1]); zs.append(p3[valid, 2])
+        xn.append((r[:, 0] / r[:, 2]).astype(np.float32).astype(np.float64))
+        yn.append((r[:, 1] / r[:, 2]).astype(np.float32).astype(np.float64))
+        offs.append(offs[-1] + int(valid.sum()))
+        idx.append(i)
+    if not idx:
+        return {}
+    cat = np.concatenate
+    poses = init_poses(offs, cat(xs), cat(ys), cat(zs), cat(xn), cat(yn), device=device)
+    return {i: RvecTvec(tuple(poses[k, :3]), tuple(poses[k, 3:])) for k, i in enumerate(idx)}
+
+
 def init_ucm(frame_feature0: FrameFeature, frame_feature1: FrameFeature, rtvec0: RvecTvec, rtvec1: RvecTvec,
              init_f: float, init_alpha: float, fixed_focal: bool, options: Optional[Options] = None,
              device: int = 0) -> Optional[GenericModel]:

@@ -1249,6 +1249,38 @@ int ccrs_calib_camera(int model, int width, int height, int n_frames, const int3
   return st;
 }
 
+int ccrs_init_poses(int n_frames, const int32_t* frame_offsets, const double* x, const double* y, const double* z,
+                    const double* xn, const double* yn, double* poses_out, double* cost_out, int device_id) {
+  if (!frame_offsets || !x || !y || !z || !xn || !yn || !poses_out || n_frames <= 0) return fail(CCRS_ERR_INVALID, "null / empty");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { cudaGetLastError(); return fail(CCRS_ERR_NO_DEVICE, "no CUDA device"); }
+  CK(cudaSetDevice(device_id));
+  for (int f = 0; f < n_frames; ++f)
+    if (frame_offsets[f + 1] - frame_offsets[f] < 4) return fail(CCRS_ERR_INVALID, "frame %d has fewer than 4 points", f);
+  const size_t N = (size_t)frame_offsets[n_frames], F = (size_t)n_frames;
+  cudaStream_t s = nullptr;
+  CK(get_stream(device_id, &s));
+  DevBuf<double> dx, dy, dz, dxn, dyn, dpose, dcost;
+  DevBuf<int32_t> dfo;
+  CK(dx.alloc(N)); CK(dy.alloc(N)); CK(dz.alloc(N)); CK(dxn.alloc(N)); CK(dyn.alloc(N)); CK(dpose.alloc(6 * F)); CK(dcost.alloc(F));
+  CK(dfo.alloc(F + 1));
+  CK(cudaMemcpyAsync(dfo.p, frame_offsets, (F + 1) * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dx.p, x, N * 8, cudaMemcpyHostToDevice, s)); CK(cudaMemcpyAsync(dy.p, y, N * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dz.p, z, N * 8, cudaMemcpyHostToDevice, s)); CK(cudaMemcpyAsync(dxn.p, xn, N * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dyn.p, yn, N * 8, cudaMemcpyHostToDevice, s));
+  CK(launch_pnp(dfo.p, dx.p, dy.p, dz.p, dxn.p, dyn.p, n_frames, dpose.p, dcost.p, s));
+  std::vector<double> cost(F);
+  CK(cudaMemcpyAsync(poses_out, dpose.p, 6 * F * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(cost.data(), dcost.p, F * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  put_stream(device_id, s);
+  dx.release(); dy.release(); dz.release(); dxn.release(); dyn.release(); dpose.release(); dcost.release(); dfo.release();
+  if (cost_out) std::memcpy(cost_out, cost.data(), F * 8);
+  for (size_t f = 0; f < F; ++f)
+    if (std::isnan(cost[f])) return fail(CCRS_ERR_NUMERIC, "no pose with the board in front of the camera for frame %zu", f);
+  return 0;
+}
+
 int ccrs_set_fixed_poses(ccrs_problem* p, int fixed) {
   if (!p) return fail(CCRS_ERR_INVALID, "null");
   p->fixed_poses = fixed != 0;

@@ -141,6 +141,9 @@ constexpr int kSelBins = 2048;
 struct SelectState { unsigned long long prefix[2], rank[2], below[2]; };
 cudaError_t launch_select(const double* v, int64_t n, SelectState* st, unsigned* hist, double* partial, int n_ctas,
                           cudaStream_t s, int64_t* launches);
+// batched initial board poses (ccrs_pnp.cu): one warp per frame; poses_out [n_frames][6], cost_out [n_frames] nullable
+cudaError_t launch_pnp(const int32_t* frame_offsets, const double* x, const double* y, const double* z, const double* xn,
+                       const double* yn, int n_frames, double* poses_out, double* cost_out, cudaStream_t s);
 cudaError_t launch_fp64_peak(double* out, int n_ctas, int iters, cudaStream_t s);
 cudaError_t launch_l2_flush(double* buf, size_t n, cudaStream_t s);
 

@@ -73,6 +73,9 @@ extern "C" {
                              summary: *mut ccrs_summary, device_id: c_int) -> c_int;
     pub fn ccrs_validation(p: *mut ccrs_problem, intr: *const c_double, poses: *const c_double, median: *mut c_double,
                            avg99: *mut c_double, errors: *mut c_double) -> c_int;
+    pub fn ccrs_init_poses(n_frames: c_int, frame_offsets: *const i32, x: *const c_double, y: *const c_double,
+                           z: *const c_double, xn: *const c_double, yn: *const c_double, poses_out: *mut c_double,
+                           cost_out: *mut c_double, device_id: c_int) -> c_int;
     pub fn ccrs_set_fixed_poses(p: *mut ccrs_problem, fixed: c_int) -> c_int;
     pub fn ccrs_init_ucm(width: c_int, height: c_int, n_frames: c_int, frame_offsets: *const i32, x: *const c_double,
                          y: *const c_double, z: *const c_double, u: *const c_double, v: *const c_double,

@@ -254,6 +254,17 @@ int ccrs_calib_camera(int model, int width, int height, int n_frames, const int3
                       double* params, double* poses, int xy_same_focal, int disabled_distortions, int fixed_focal,
                       int use_lm, const ccrs_options* opt, ccrs_summary* summary, int device_id);
 
+/* ---- initial board poses: replaces the per-frame sqpnp_simple::sqpnp_solve_glam(&p3ds, &p2ds_z) of calib_camera
+ * (src/util.rs:418-439) and of init_pose (src/optimization/linear.rs:5-21) -----------------------------------------
+ * x, y, z: board points; xn, yn: the matching NORMALISED image points (p2.x / p2.z, p2.y / p2.z of
+ * generic_camera.unproject, util.rs:418-429, or init_pose's radial approximation) — unprojection belongs to the model
+ * crate and stays with the caller. All frames are solved in one launch (one warp per frame): minimiser over SO(3) x R^3
+ * of the SQPnP cost sum_i (R p_i + t)^T Q_i (R p_i + t) with the board in front of the camera.
+ * poses_out [n_frames][6] = rvec, tvec (RvecTvec, types.rs:13-17); cost_out [n_frames] nullable = the minimum.
+ * Every frame needs >= 4 points (the reference skips frames with fewer than 10, util.rs:431-433). */
+int ccrs_init_poses(int n_frames, const int32_t* frame_offsets, const double* x, const double* y, const double* z,
+                    const double* xn, const double* yn, double* poses_out, double* cost_out, int device_id);
+
 /* Poses as constants: the per-frame pose blocks are not variables (K3 skips their elimination, K4 leaves them
  * untouched). Intrinsics-only problems such as ModelConvertFactor (factors.rs:11-77). */
 int ccrs_set_fixed_poses(ccrs_problem* p, int fixed);
