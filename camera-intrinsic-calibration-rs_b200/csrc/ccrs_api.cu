@@ -186,6 +186,15 @@ struct ccrs_problem {
   PinBuf<double> h_red, h_stat;   // mapped: single problem [NRED + 1] / [4] (last = sequence number); batch: plain D2H targets
   bool have_scale = false, have_obs_frame = false;
   bool fixed_poses = false;       // poses are constants (ccrs_set_fixed_poses)
+  // Speculative K3 (single problem, speculative LM): launched right behind the trial-point K2, before its statistics
+  // are known, for the outcome that dominates a converging run — step accepted with gain ratio >= 0.937, i.e.
+  // u_next = u / 3 exactly. If the controller then asks for exactly that reduction the result is already in flight (the
+  // launch call, the launch latency and K3 itself leave the critical path); otherwise the speculative result is
+  // ignored and K3 is launched again with the right damping. The decision itself stays on the host.
+  struct SpecK3 { bool valid = false; double u = 0.0; int use_scale = 0; double mn = 0.0, mx = 0.0; int cur_after = 0, area = 0; } spec;
+  int red_area = 0;               // which half of h_red the last K3 publishes into (alternates per launch)
+  double last_mn = 0.0, last_mx = 0.0;
+  bool have_last_reduce = false;
   std::vector<int32_t> h_frame_offsets, h_problem_frame_offsets;
   bool last_use_scale = false;    // state of the last reduce(), needed by the back-substitution
   int cur_val = 0;                // single problem: which state buffer is current (host-tracked, passed by value)
@@ -291,7 +300,7 @@ int upload_problem(ccrs_problem* p, int n_problems, const int32_t* problem_frame
   CK(p->stat_out.alloc(P * 2));
   CK(p->intr_dev.alloc(P * p->D)); CK(p->ya_dev.alloc(P * p->D)); CK(p->u_dev.alloc(P)); CK(p->scale_dev.alloc(P * p->D));
   CK(p->mask_dev.alloc(P));
-  CK(p->h_red.alloc(P * p->NRED + 1)); CK(p->h_stat.alloc(P * 2 + 2));
+  CK(p->h_red.alloc(2 * (P * p->NRED + 1))); CK(p->h_stat.alloc(P * 2 + 2));
   p->h_red.p[p->NRED] = -1.0; p->h_stat.p[2] = -1.0; p->h_stat.p[3] = -1.0;
   CK(cudaMemsetAsync(p->cur.p, 0, P * sizeof(int32_t), s));
   CK(cudaMemsetAsync(p->u_dev.p, 0, P * sizeof(double), s));
@@ -380,6 +389,10 @@ struct StepTrace {
   void mark(int slot) { if (!on) return; const double t = now(); if (slot >= 0 && t_mark > 0.0) acc[slot] += t - t_mark; t_mark = t; }
 };
 StepTrace g_trace;
+
+// speculative K3 (see ccrs_problem::SpecK3): CCRS_SPEC_K3=0 disables it; counters for tests / tools
+const bool g_spec_enabled = [] { const char* e = getenv("CCRS_SPEC_K3"); return !(e && atoi(e) == 0); }();
+std::atomic<long> g_spec_launched{0}, g_spec_hits{0};
 
 // Results the host needs every iteration come back through mapped pinned host memory WITHOUT any device-side fence
 // (a system-scope fence costs ~2-3 us per use): before the launch the host arms the n result words with a sentinel
@@ -502,6 +515,7 @@ int flush_pending(ccrs_problem* p) {
 // K2 (or its cost-only variant K5). A deferred back-substitution that targets the same point is fused into the
 // prologue. Single problem: {model decrease, cost} are reduced in-kernel and published under sequence number *seq_out.
 int do_linearize(ccrs_problem* p, const double* intr, int which, bool cost_only, bool publish, double* seq_out) {
+  p->spec.valid = false;   // any new linearisation makes a speculative reduction of the previous one stale
   if (p->pend && (p->pend_in_place ? which != 0 : which != 1)) { int st = flush_pending(p); if (st) return st; }
   LinParams prm{};
   prm.pb = p->dev();
@@ -578,11 +592,11 @@ int reduce_frames(ccrs_problem* p, const double* in, int NV, double* out_dev) {
   return 0;
 }
 
-int do_reduce(ccrs_problem* p, int which, const double* u, int use_scale, double min_diag, double max_diag, double* out) {
-  const int D = p->D, P = p->n_problems;
-  if (use_scale && !p->have_scale) return fail(CCRS_ERR_INVALID, "use_scale without ccrs_compute_scale/ccrs_set_intr_scale");
-  int st = flush_pending(p);
-  if (st) return st;
+// payload area `a` of the single-problem K3 result in mapped host memory
+volatile double* red_area_ptr(ccrs_problem* p, int a) { return p->h_red.p + (size_t)a * (p->NRED + 1); }
+
+// single problem: enqueue K3 (+ the NCCL exchange when the peer path is off) publishing into payload area `area`
+int launch_k3_single(ccrs_problem* p, int which, double u, int use_scale, double min_diag, double max_diag, int area) {
   SchurParams prm{};
   prm.pb = p->dev();
   prm.which = which;
@@ -593,7 +607,52 @@ int do_reduce(ccrs_problem* p, int which, const double* u, int use_scale, double
   prm.elim = p->elim.p;
   prm.frame_red = p->frame_red.p;
   p->last_use_scale = use_scale != 0;
+  prm.u_dev = nullptr;
+  prm.u_val = u;
+  prm.ticket = p->tickets.p + 1;
+  prm.red_out = p->red_out.p;
+  p->seq = next_seq();
+  prm.seq = p->seq;
+  const bool peer = use_peer(p, (size_t)p->NRED);
+  volatile double* host = red_area_ptr(p, area);
+  prm.host_red = (p->comm && !peer) ? nullptr : host;
+  arm_payload(host, p->NRED);
+  if (peer) fill_peer(p, 0, &prm.px);
+#ifdef CCRS_K2_TIMING
+  if (!p->k3_dbg.p) CK(p->k3_dbg.alloc((size_t)8 * (p->n_frames / 32 + 8)));
+  prm.dbg = reinterpret_cast<long long*>(p->k3_dbg.p);
+#endif
+  CK(launch_schur(p->D, prm, p->stream));
+  p->launches++;
+  if (p->comm && !peer) { int st = exchange(p, p->red_out.p, (size_t)p->NRED, host, p->seq); if (st) return st; }
+  return 0;
+}
+
+// unpack one problem's K3 result: packed upper S -> full row-major, then g_s | g_a | diag_a | sq_err
+void unpack_reduced(const ccrs_problem* p, const volatile double* r, double* o) {
+  const int D = p->D, NS = D * (D + 1) / 2;
+  int e = 0;
+  for (int a = 0; a < D; ++a)
+    for (int b = a; b < D; ++b) { o[a * D + b] = r[e]; o[b * D + a] = r[e]; ++e; }
+  for (int i = 0; i < 3 * D + 1; ++i) o[D * D + i] = r[NS + i];
+}
+
+int do_reduce(ccrs_problem* p, int which, const double* u, int use_scale, double min_diag, double max_diag, double* out) {
+  const int D = p->D, P = p->n_problems;
+  if (use_scale && !p->have_scale) return fail(CCRS_ERR_INVALID, "use_scale without ccrs_compute_scale/ccrs_set_intr_scale");
+  int st = flush_pending(p);
+  if (st) return st;
   if (p->batch) {
+    SchurParams prm{};
+    prm.pb = p->dev();
+    prm.which = which;
+    prm.intr_scale = use_scale ? p->scale_dev.p : nullptr;
+    prm.pose_scale = use_scale ? p->pose_scale.p : nullptr;
+    prm.min_diag = min_diag; prm.max_diag = max_diag;
+    prm.no_pose = p->fixed_poses ? 1 : 0;
+    prm.elim = p->elim.p;
+    prm.frame_red = p->frame_red.p;
+    p->last_use_scale = use_scale != 0;
     if (u) CK(cudaMemcpyAsync(p->u_dev.p, u, (size_t)P * 8, cudaMemcpyHostToDevice, p->stream));
     else CK(cudaMemsetAsync(p->u_dev.p, 0, (size_t)P * 8, p->stream));
     prm.u_dev = p->u_dev.p;
@@ -605,41 +664,30 @@ int do_reduce(ccrs_problem* p, int which, const double* u, int use_scale, double
     if (st) return st;
     CK(cudaMemcpyAsync(p->h_red.p, p->red_out.p, (size_t)P * p->NRED * 8, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
+    for (int q = 0; q < P; ++q) unpack_reduced(p, p->h_red.p + (size_t)q * p->NRED, out + (size_t)q * p->NOUT);
+    return 0;
+  }
+  const double uv = u ? u[0] : 0.0;
+  int area;
+  const bool hit = p->spec.valid && which == 0 && p->spec.cur_after == p->cur_val && p->spec.u == uv &&
+                   p->spec.use_scale == use_scale && p->spec.mn == min_diag && p->spec.mx == max_diag;
+  p->spec.valid = false;
+  g_trace.mark(5);
+  if (hit) {
+    area = p->spec.area;   // the reduction the controller asks for is the one already in flight
+    g_spec_hits++;
   } else {
-    prm.u_dev = nullptr;
-    prm.u_val = u ? u[0] : 0.0;
-    prm.ticket = p->tickets.p + 1;
-    prm.red_out = p->red_out.p;
-    p->seq = next_seq();
-    prm.seq = p->seq;
-    const bool peer = use_peer(p, (size_t)p->NRED);
-    prm.host_red = (p->comm && !peer) ? nullptr : p->h_red.p;
-    if (prm.host_red) arm_payload(prm.host_red, p->NRED);
-    if (peer) fill_peer(p, 0, &prm.px);
-    g_trace.mark(5);
-#ifdef CCRS_K2_TIMING
-    if (!p->k3_dbg.p) CK(p->k3_dbg.alloc((size_t)8 * (p->n_frames / 32 + 8)));
-    prm.dbg = reinterpret_cast<long long*>(p->k3_dbg.p);
-#endif
-    CK(launch_schur(D, prm, p->stream));
-    p->launches++;
-    if (p->comm && !peer) { st = exchange(p, p->red_out.p, (size_t)p->NRED, p->h_red.p, p->seq); if (st) return st; }
-    g_trace.mark(0);
-    st = wait_payload(p, p->h_red.p, p->NRED);
+    area = (p->red_area ^= 1);
+    st = launch_k3_single(p, which, uv, use_scale, min_diag, max_diag, area);
     if (st) return st;
-    g_trace.mark(1);
-    if (g_trace.on) g_trace.n++;
   }
-  // unpack: packed upper S -> full row-major
-  const int NS = D * (D + 1) / 2;
-  for (int q = 0; q < P; ++q) {
-    const double* r = p->h_red.p + (size_t)q * p->NRED;
-    double* o = out + (size_t)q * p->NOUT;
-    int e = 0;
-    for (int a = 0; a < D; ++a)
-      for (int b = a; b < D; ++b) { o[a * D + b] = r[e]; o[b * D + a] = r[e]; ++e; }
-    for (int i = 0; i < 3 * D + 1; ++i) o[D * D + i] = r[NS + i];
-  }
+  p->last_mn = min_diag; p->last_mx = max_diag; p->have_last_reduce = true;
+  g_trace.mark(0);
+  st = wait_payload(p, red_area_ptr(p, area), p->NRED);
+  if (st) return st;
+  g_trace.mark(1);
+  if (g_trace.on) g_trace.n++;
+  unpack_reduced(p, red_area_ptr(p, area), out);
   return 0;
 }
 
@@ -659,8 +707,20 @@ int be_trial_stats(void* ctx, const double* intr_trial, int speculative, double*
   ccrs_problem* p = (ccrs_problem*)ctx;
   double seq = 0.0;
   g_trace.mark(2);
+  const double u_step = p->pend_u;   // damping of the step being tried (do_linearize consumes the deferred back-substitution)
   int st = do_linearize(p, intr_trial, 1, !speculative, true, &seq);
   if (st) return st;
+  if (speculative && !p->batch && g_spec_enabled && p->have_last_reduce && (!p->comm || use_peer(p, (size_t)p->NRED))) {
+    ccrs_problem::SpecK3& sp = p->spec;
+    sp.u = u_step * (1.0 / 3.0);     // controller: u *= max(1/3, 1 - (2 rho - 1)^3) on accept
+    sp.use_scale = p->last_use_scale ? 1 : 0; sp.mn = p->last_mn; sp.mx = p->last_mx;
+    sp.cur_after = p->cur_val ^ 1;   // valid once the controller has accepted the trial point
+    sp.area = (p->red_area ^= 1);
+    st = launch_k3_single(p, 1, sp.u, sp.use_scale, sp.mn, sp.mx, sp.area);
+    if (st) return st;
+    sp.valid = true;
+    g_spec_launched++;
+  }
   g_trace.mark(3);
   st = fetch_stats(p, speculative ? 1 : 0, seq, out);
   g_trace.mark(4);
@@ -783,6 +843,7 @@ int ccrs_set_poses(ccrs_problem* p, const double* poses) {
   // resetting the poses also resets the buffer selector and drops any deferred step
   p->pend = false;
   p->cur_val = 0;
+  p->spec.valid = false; p->have_last_reduce = false;
   if (p->batch) CK(cudaMemsetAsync(p->cur.p, 0, (size_t)p->n_problems * sizeof(int32_t), p->stream));
   CK(cudaMemcpyAsync(p->poses[0].p, poses, (size_t)p->n_frames * 6 * 8, cudaMemcpyHostToDevice, p->stream));
   CK(cudaStreamSynchronize(p->stream));
@@ -1279,6 +1340,12 @@ int ccrs_init_poses(int n_frames, const int32_t* frame_offsets, const double* x,
   for (size_t f = 0; f < F; ++f)
     if (std::isnan(cost[f])) return fail(CCRS_ERR_NUMERIC, "no pose with the board in front of the camera for frame %zu", f);
   return 0;
+}
+
+int ccrs_spec_k3_counters(int64_t* launched, int64_t* hits) {
+  if (launched) *launched = g_spec_launched.load();
+  if (hits) *hits = g_spec_hits.load();
+  return g_spec_enabled ? 1 : 0;
 }
 
 int ccrs_set_fixed_poses(ccrs_problem* p, int fixed) {

@@ -340,6 +340,11 @@ int ccrs_bench_lm_steps(ccrs_problem* p, const double* intr0, const double* pose
  *   [0] K3 launch call  [1] K3 execution + publish latency  [2] host: unpack, d x d solve, trial point
  *   [3] K2 launch call  [4] K2 execution + publish latency  [5] host: accept/reject, bookkeeping */
 int ccrs_step_trace(int enable, double* avg_us, int64_t* n_iterations);
+/* Speculative K3: in the speculative LM loop of a single problem the library launches the next reduction right behind
+ * the trial-point linearisation, for the outcome "accepted with gain ratio >= 0.937" (u_next = u / 3), so that launch
+ * and kernel leave the critical path; a different decision by the controller just launches K3 again. Process-wide
+ * counters (speculative launches, launches whose result was used); returns 1 if enabled (CCRS_SPEC_K3=0 disables). */
+int ccrs_spec_k3_counters(int64_t* launched, int64_t* hits);
 /* Kernel launches issued by this handle since creation. */
 int64_t ccrs_launch_count(const ccrs_problem* p);
 

@@ -314,3 +314,31 @@ def test_f32_observation_api_is_bit_identical(pkg):
     i32, s32, _ = g32.solve_lm(s.init_params)
     assert np.array_equal(i64, i32) and s64.iterations == s32.iterations
     g64.close(); g32.close()
+
+
+def test_speculative_k3_is_used_and_changes_nothing(pkg, oracle):
+    """the K3 launched behind the trial K2 (for 'accepted, u_next = u / 3') must be consumed on a converging run and the
+    trajectory must be bit-identical to the run without it (same kernels, same arguments, only launched earlier)."""
+    import ctypes as C, os, subprocess, sys, json
+    s, op, gp, intr0 = _setup(pkg, oracle, "eucm", 100, seed=1, noise_px=0.1)
+    lib = pkg._abi.load()
+    a0, h0 = C.c_int64(0), C.c_int64(0)
+    enabled = lib.ccrs_spec_k3_counters(C.byref(a0), C.byref(h0))
+    gp.set_poses(s.init_poses)
+    intr, summ, hist = gp.solve_lm(intr0)
+    poses = gp.get_poses()
+    a1, h1 = C.c_int64(0), C.c_int64(0)
+    lib.ccrs_spec_k3_counters(C.byref(a1), C.byref(h1))
+    assert enabled == 1 and a1.value - a0.value == summ.iterations and h1.value - h0.value >= 1
+    intr_ref, poses_ref, res, hist_ref = op.levenberg_marquardt(intr0, s.init_poses)
+    assert summ.iterations == res.iterations and np.max(np.abs(intr - intr_ref) / np.abs(intr_ref)) < TOL_INTR
+    gp.close()
+    # same solve in a process with CCRS_SPEC_K3=0: bitwise the same numbers
+    code = ("import importlib,json,numpy as np;pkg=importlib.import_module('camera-intrinsic-calibration-rs_b200');"
+            "s=pkg.synth.make_calib('eucm',100,seed=1,noise_px=0.1);gp=pkg.Problem.from_synth(s);gp.set_poses(s.init_poses);"
+            "intr,summ,hist=gp.solve_lm(s.init_params);print(json.dumps([intr.tolist(),hist.tolist(),gp.get_poses().tolist()]))")
+    env = dict(os.environ, CCRS_SPEC_K3="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, check=True).stdout
+    i2, h2, p2 = json.loads(out.strip().splitlines()[-1])
+    assert np.array_equal(intr, np.array(i2)) and np.array_equal(hist, np.array(h2)) and np.array_equal(poses, np.array(p2))
