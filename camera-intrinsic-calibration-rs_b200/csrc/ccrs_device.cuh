@@ -177,7 +177,7 @@ CCRS_D void model_eval(const double* __restrict__ k, double x, double y, double 
     }
   } else if constexpr (MODEL == KB4 || MODEL == FTHETA) {
     const double r2 = x * x + y * y;
-    const double r = sqrt(r2);
+    const double r = sqrt_fast(fmax(r2, 1e-300));   // branch-free; r2 = 0 lands in the pinhole-limit branch below
     if (r < kSmallR) {
       const double iz = 1.0 / z;
       m[0] = x * iz; m[1] = y * iz;
@@ -190,7 +190,7 @@ CCRS_D void model_eval(const double* __restrict__ k, double x, double y, double 
       return;
     }
     const double th = atan2(r, z);
-    const double ir = 1.0 / r;
+    const double ir = rcp_fast(r);
     double d, dd, pw[4];  // d(theta), d'(theta), d d/d k_i
     if constexpr (MODEL == KB4) {
       const double t2 = th * th;
@@ -205,7 +205,7 @@ CCRS_D void model_eval(const double* __restrict__ k, double x, double y, double 
     const double s = d * ir;  // m = s * (x, y)
     m[0] = x * s; m[1] = y * s;
     if constexpr (WITH_J) {
-      const double irho2 = 1.0 / (r2 + z * z);
+      const double irho2 = rcp_fast(r2 + z * z);
       // theta_x = x z / (r rho2), theta_y = y z / (r rho2), theta_z = -r / rho2
       const double cxy = (dd * z * irho2 - s) * ir * ir;  // (d' theta_x / r - d x / r^3) / x
       const double sz = -dd * irho2;                      // ds/dz = d' theta_z / r
