@@ -380,7 +380,7 @@ CCRS_D void slices_reduce_store_pair(double (&acc)[R::NACC], bool active, int la
     if (active) {
       for (int e = sl; e < cnt; e += G) {
         const double* src = srow + e * kRedStride;
-        const int bu = s_a2b[ch * kRedChunk + e], bv = s_a2b[R::NACC + ch * kRedChunk + e];
+        const int bu = __ldg(s_a2b + ch * kRedChunk + e), bv = __ldg(s_a2b + R::NACC + ch * kRedChunk + e);
         if (bu == bv) {
           double t = src[0];
           for (int j = 1; j < G; ++j) t += src[j];
@@ -432,7 +432,7 @@ CCRS_D void slices_reduce_store(double (&acc)[C::NACC], bool active, int lane, i
           } else {
             for (int j = 1; j < G; ++j) s += src[j];
           }
-          out[(size_t)s_a2b[ch * kRedChunk + e] * Fs] = s;
+          out[(size_t)__ldg(s_a2b + ch * kRedChunk + e) * Fs] = s;
         }
       }
     };
@@ -466,13 +466,10 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   double* s_stat = s_intr + (BATCH ? FPW * kMaxFull : 0);  // [2][FPW] per-frame md, cost
   double* s_red = s_stat + 2 * FPW;                      // [kRedChunk][kRedStride]
   double* s_obs = s_red + (COST_ONLY ? 32 : kRedChunk * kRedStride);  // [kObsStages][5][32] cp.async ring of x,y,z,u,v
-  int* s_a2b = reinterpret_cast<int*>(s_obs + kObsStages * 5 * 32);  // [NACC] accumulator -> packed block entry
+  const int* const s_a2b = prm.acc_to_blk;   // [NACC] accumulator -> packed block entry: read-only path, L1-resident
   constexpr bool PAIR = !COST_ONLY && lin_pair_v<MODEL, OF>;
   using R = RowCfg<C>;
   constexpr int NACC_L = COST_ONLY ? 1 : (PAIR ? R::NACC : C::NACC);   // accumulators per lane
-  if constexpr (!COST_ONLY) {
-    for (int i = lane; i < (PAIR ? 2 * R::NACC : C::NACC); i += 32) s_a2b[i] = __ldg(prm.acc_to_blk + i);   // visible after the prologue's __syncwarp
-  }
 
 #ifdef CCRS_K2_TIMING
   long long tck[8];
@@ -491,8 +488,46 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   // Observations are prefetched kObsStages-1 iterations ahead with 8-byte cp.async into a per-thread shared-memory
   // ring (each thread reads back only what it fetched: no barrier), so neither DRAM nor L2 latency sits at the
   // top of an iteration. The first stages are issued before the pose prologue so their latency overlaps it.
-  const int end = active ? pb.frame_offsets[f + 1] : 0;
-  const int beg = active ? pb.frame_offsets[f] + sl : 0;
+  // Every global load of the prologue is issued before anything waits on one of them: frame offsets, then the pose and
+  // (fused K4) the frame's elimination record — one memory round trip instead of three at the start of the kernel,
+  // when no other warp of the SM has work to hide it.
+  int fo_beg = 0, fo_end = 0, prob = 0, cur = 0;
+  bool moves = false;
+  double rt[6], X[6][C::D], cg[6], gp[6], dd[6], sp[6];
+  double* pose_dst = nullptr;
+  if (active) {
+    fo_end = __ldg(pb.frame_offsets + f + 1);
+    fo_beg = __ldg(pb.frame_offsets + f);
+    prob = BATCH ? pb.frame_problem[f] : 0;
+    cur = cur_of(pb, prob);
+    if (prm.backsub) {
+      const double* src = pb.poses[cur] + 6 * (size_t)f;
+      pose_dst = pb.poses[prm.backsub == 2 ? cur : (cur ^ 1)] + 6 * (size_t)f;
+      moves = !(BATCH && prm.active && !prm.active[prob]);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) rt[i] = src[i];
+      if (moves) {
+        const double* el = prm.elim + f;
+        const size_t Fs = pb.Fs;
+        // read-only path: none of these can alias the pose store below
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+          for (int a = 0; a < C::D; ++a) X[i][a] = __ldg(el + (size_t)(i * C::D + a) * Fs);
+          cg[i] = __ldg(el + (size_t)(6 * C::D + i) * Fs);
+          gp[i] = __ldg(el + (size_t)(6 * C::D + 6 + i) * Fs);
+          dd[i] = __ldg(el + (size_t)(6 * C::D + 12 + i) * Fs);
+          sp[i] = prm.pose_scale ? __ldg(prm.pose_scale + (size_t)i * Fs + f) : 1.0;
+        }
+      }
+    } else {
+      const double* src = pb.poses[cur ^ prm.which] + 6 * (size_t)f;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) rt[i] = src[i];
+    }
+  }
+  const int end = active ? fo_end : 0;
+  const int beg = active ? fo_beg + sl : 0;
   double* ring = s_obs + lane;
   auto fetch = [&](int kk, int stage) {
     if (kk < end) {
@@ -515,31 +550,10 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   //      slice 0 stores. Fused K4: y_p = cg - X y_a ; pose += D_p y_p ; model decrease y_p^T g'_p + u sum dd_i y_p,i^2
   double md = 0.0;   // model decrease of this lane's frame (same value in all lanes of the frame)
   if (active) {
-    const int prob = BATCH ? pb.frame_problem[f] : 0;
-    const int cur = cur_of(pb, prob);
-    double rt[6];
     if (prm.backsub) {
-      const double* src = pb.poses[cur] + 6 * (size_t)f;
-      double* dst = pb.poses[prm.backsub == 2 ? cur : (cur ^ 1)] + 6 * (size_t)f;
-      const bool moves = !(BATCH && prm.active && !prm.active[prob]);
-#pragma unroll
-      for (int i = 0; i < 6; ++i) rt[i] = src[i];
       if (moves) {
         const double* ya = BATCH ? prm.ya_dev + (size_t)prob * C::D : prm.y_a;
         const double u = BATCH ? (prm.u_dev ? prm.u_dev[prob] : 0.0) : prm.u;
-        const double* el = prm.elim + f;
-        const size_t Fs = pb.Fs;
-        // all loads first (read-only path: none of them can alias the pose store below)
-        double X[6][C::D], cg[6], gp[6], dd[6], sp[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-#pragma unroll
-          for (int a = 0; a < C::D; ++a) X[i][a] = __ldg(el + (size_t)(i * C::D + a) * Fs);
-          cg[i] = __ldg(el + (size_t)(6 * C::D + i) * Fs);
-          gp[i] = __ldg(el + (size_t)(6 * C::D + 6 + i) * Fs);
-          dd[i] = __ldg(el + (size_t)(6 * C::D + 12 + i) * Fs);
-          sp[i] = prm.pose_scale ? __ldg(prm.pose_scale + (size_t)i * Fs + f) : 1.0;
-        }
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
           double yp = cg[i];
@@ -551,13 +565,9 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
       }
       if (sl == 0) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) dst[i] = rt[i];
+        for (int i = 0; i < 6; ++i) pose_dst[i] = rt[i];
         if (BATCH && prm.frame_md) prm.frame_md[f] = md;
       }
-    } else {
-      const double* src = pb.poses[cur ^ prm.which] + 6 * (size_t)f;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) rt[i] = src[i];
     }
     FramePose fp;
     pose_from_rvec_tvec(rt, fp);
