@@ -55,9 +55,10 @@ CCRS_HD void pose_from_rvec_tvec(const double* rt, FramePose& fp) {
     const double th = sqrt(th2);
     double sh, ch;
     sincos(0.5 * th, &sh, &ch);
-    a = 2.0 * sh * ch / th;
-    b = 2.0 * sh * sh / th2;
-    c = (th - 2.0 * sh * ch) / (th2 * th);
+    const double ith = 1.0 / th, s2 = 2.0 * sh * ch;   // one division instead of three (each ~127 cycles of latency)
+    a = s2 * ith;
+    b = 2.0 * sh * sh * (ith * ith);
+    c = (th - s2) * (ith * ith * ith);
   }
   // K = [w]x, K^2 = w w^T - th2 I
   const double xx = wx * wx, yy = wy * wy, zz = wz * wz, xy = wx * wy, xz = wx * wz, yz = wy * wz;

@@ -700,10 +700,23 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   unsigned ticket_old = 0;
   const unsigned n_warps = gridDim.x * kLinWarps;
   if constexpr (!BATCH) {
+    // all shuffles first (independent), then the two fixed-order sums: a warp owns at most 32 frames, usually 4-8
     double wmd = 0.0, wcost = 0.0;
-    for (int i = 0; i < nf; ++i) {
-      wmd += __shfl_sync(0xffffffffu, md, i * G);
-      wcost += __shfl_sync(0xffffffffu, fcost, i * G);
+    if (FPW <= 8) {
+      double tm[8], tc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int srcl = min(i * G, 31);
+        tm[i] = __shfl_sync(0xffffffffu, md, srcl);
+        tc[i] = __shfl_sync(0xffffffffu, fcost, srcl);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (i < nf) { wmd += tm[i]; wcost += tc[i]; }
+    } else {
+      for (int i = 0; i < nf; ++i) {
+        wmd += __shfl_sync(0xffffffffu, md, i * G);
+        wcost += __shfl_sync(0xffffffffu, fcost, i * G);
+      }
     }
     if (lane == 0) {
       // no fence: the two partial words validate themselves (armed with kArmBits by the previous launch's last
