@@ -456,6 +456,8 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   using C = Cfg<MODEL, OF>;
   extern __shared__ double smem[];
   const ProblemDev& pb = prm.pb;
+  // a K3 enqueued behind this grid as a programmatic dependent may start launching now (it waits for our completion)
+  asm volatile("griddepcontrol.launch_dependents;");
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = prm.G, FPW = prm.FPW;
   const int gw = blockIdx.x * kLinWarps + wid;          // warp index in the grid
@@ -838,6 +840,8 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(const __grid_constant__
   constexpr int NRED = NS + 3 * D + 1;
   extern __shared__ double s_red[];  // [NRED][kSchurThreads+1]   (single problem only)
   const ProblemDev& pb = prm.pb;
+  // launched as a programmatic dependent of the K2 in front of it: wait until that grid has completed and flushed
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int f = blockIdx.x * kSchurThreads + threadIdx.x;
   const bool valid = f < pb.n_frames;
   double red[NRED];
@@ -1308,7 +1312,16 @@ cudaError_t launch_schur(int D, const SchurParams& prm, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         configured = true;
       }
-      kern<<<nb, kSchurThreads, smem, s>>>(prm, prm.frame_red);
+      // programmatic dependent launch: when K3 is enqueued behind a K2 that is still running (the speculative
+      // launch), its CTAs are scheduled as K2's drain and wait at griddepcontrol.wait, so the grid-launch ramp overlaps
+      // K2's tail; with nothing in front of it the wait returns at once
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(nb); cfg.blockDim = dim3(kSchurThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      return cudaLaunchKernelEx(&cfg, kern, prm, prm.frame_red);
     }
     return cudaGetLastError();
   });
