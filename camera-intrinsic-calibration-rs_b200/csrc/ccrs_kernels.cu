@@ -859,7 +859,16 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(const __grid_constant__
     const int prob = BATCH ? pb.frame_problem[f] : 0;
     const double* blk = pb.blocks[cur_of(pb, prob) ^ prm.which] + f;
     const size_t Fs = pb.Fs;
-    auto H = [&](int i, int j) { return blk[(size_t)tri_idx(NA, i, j) * Fs]; };
+    // The frame's whole packed block goes to shared memory in one burst of cp.async (each thread its own column: no
+    // barrier): one memory round trip for the kernel instead of one per dependent stage of the elimination, which
+    // with one warp per sub-partition nothing else would hide.
+    constexpr int NB = NA * (NA + 1) / 2;
+    double* const s_col = s_red + threadIdx.x;
+#pragma unroll
+    for (int e = 0; e < NB; ++e) cp_async8(s_col + e * kSchurThreads, blk + (size_t)e * Fs);
+    cp_async_commit();
+    cp_async_wait<0>();
+    auto H = [&](int i, int j) { return s_col[tri_idx(NA, i, j) * kSchurThreads]; };
     const double u = prm.u_dev ? prm.u_dev[prob] : prm.u_val;
     double sa[D], sp[6];
 #pragma unroll
@@ -979,6 +988,7 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(const __grid_constant__
   } else {
     constexpr int LD = kSchurThreads + 1;
     __shared__ int s_last;
+    __syncthreads();   // the block staging area becomes the reduction buffer
 #pragma unroll
     for (int i = 0; i < NRED; ++i) s_red[i * LD + threadIdx.x] = red[i];
     __syncthreads();
@@ -1301,14 +1311,22 @@ cudaError_t launch_schur(int D, const SchurParams& prm, cudaStream_t s) {
   return dispatch_d(D, [&](auto DD) {
     constexpr int d = decltype(DD)::value;
     constexpr int NRED = d * (d + 1) / 2 + 3 * d + 1;
+    constexpr size_t kStage = (size_t)(d + 7) * (d + 8) / 2 * kSchurThreads * sizeof(double);   // one packed block per thread
     if (batch) {
-      k_schur<d, true><<<nb, kSchurThreads, 0, s>>>(prm, nullptr);
+      auto kern = k_schur<d, true>;
+      static bool configured = false;
+      if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStage);
+        if (e != cudaSuccess) return e;
+        configured = true;
+      }
+      kern<<<nb, kSchurThreads, kStage, s>>>(prm, nullptr);
     } else {
-      const size_t smem = (size_t)NRED * (kSchurThreads + 1) * sizeof(double);
+      const size_t smem = std::max(kStage, (size_t)NRED * (kSchurThreads + 1) * sizeof(double));
       auto kern = k_schur<d, false>;
       static bool configured = false;
       if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
       }
