@@ -262,20 +262,21 @@ CCRS_D void stats_finalize(const LinParams& prm, unsigned n_parts, int lane) {
   // in flight per lane) until none still holds the arming pattern, sum in a fixed order, re-arm for the next launch
   double2* part = reinterpret_cast<double2*>(prm.cta_part);
   double a = 0.0, b = 0.0;
-  for (unsigned w0 = lane; w0 < n_parts; w0 += 32 * 16) {
-    double2 t[16];
+  constexpr int kBatch = 16;   // loads in flight per lane
+  for (unsigned w0 = lane; w0 < n_parts; w0 += 32 * kBatch) {
+    double2 t[kBatch];
     bool ok;
     do {
       ok = true;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
+      for (int q = 0; q < kBatch; ++q) {
         const unsigned w = w0 + 32 * q;
         t[q] = w < n_parts ? __ldcg(part + w) : make_double2(0.0, 0.0);
         ok = ok && (__double_as_longlong(t[q].x) != kArmBits) && (__double_as_longlong(t[q].y) != kArmBits);
       }
     } while (!ok);
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
+    for (int q = 0; q < kBatch; ++q) {
       a += t[q].x; b += t[q].y;
       const unsigned w = w0 + 32 * q;
       if (w < n_parts) part[w] = make_double2(__longlong_as_double(kArmBits), __longlong_as_double(kArmBits));
@@ -380,7 +381,7 @@ CCRS_D void slices_reduce_store_pair(double (&acc)[R::NACC], bool active, int la
     if (active) {
       for (int e = sl; e < cnt; e += G) {
         const double* src = srow + e * kRedStride;
-        const int bu = __ldg(s_a2b + ch * kRedChunk + e), bv = __ldg(s_a2b + R::NACC + ch * kRedChunk + e);
+        const int bu = s_a2b[ch * kRedChunk + e], bv = s_a2b[R::NACC + ch * kRedChunk + e];
         if (bu == bv) {
           double t = src[0];
           for (int j = 1; j < G; ++j) t += src[j];
@@ -432,7 +433,7 @@ CCRS_D void slices_reduce_store(double (&acc)[C::NACC], bool active, int lane, i
           } else {
             for (int j = 1; j < G; ++j) s += src[j];
           }
-          out[(size_t)__ldg(s_a2b + ch * kRedChunk + e) * Fs] = s;
+          out[(size_t)s_a2b[ch * kRedChunk + e] * Fs] = s;
         }
       }
     };
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   double* s_stat = s_intr + (BATCH ? FPW * kMaxFull : 0);  // [2][FPW] per-frame md, cost
   double* s_red = s_stat + 2 * FPW;                      // [kRedChunk][kRedStride]
   double* s_obs = s_red + (COST_ONLY ? 32 : kRedChunk * kRedStride);  // [kObsStages][5][32] cp.async ring of x,y,z,u,v
-  const int* const s_a2b = prm.acc_to_blk;   // [NACC] accumulator -> packed block entry: read-only path, L1-resident
+  int* s_a2b = reinterpret_cast<int*>(s_obs + kObsStages * 5 * 32);  // [NACC] accumulator -> packed block entry
   constexpr bool PAIR = !COST_ONLY && lin_pair_v<MODEL, OF>;
   using R = RowCfg<C>;
   constexpr int NACC_L = COST_ONLY ? 1 : (PAIR ? R::NACC : C::NACC);   // accumulators per lane
@@ -493,6 +494,11 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   // Every global load of the prologue is issued before anything waits on one of them: frame offsets, then the pose and
   // (fused K4) the frame's elimination record — one memory round trip instead of three at the start of the kernel,
   // when no other warp of the SM has work to hide it.
+  constexpr int kA2bN = COST_ONLY ? 0 : (PAIR ? 2 * R::NACC : C::NACC);
+  constexpr int kA2bPerLane = (kA2bN + 31) / 32;
+  int a2b_reg[kA2bPerLane > 0 ? kA2bPerLane : 1];
+#pragma unroll
+  for (int i = 0; i < kA2bPerLane; ++i) a2b_reg[i] = (lane + 32 * i < kA2bN) ? __ldg(prm.acc_to_blk + lane + 32 * i) : 0;
   int fo_beg = 0, fo_end = 0, prob = 0, cur = 0;
   bool moves = false;
   double rt[6], X[6][C::D], cg[6], gp[6], dd[6], sp[6];
@@ -589,6 +595,8 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
       }
     }
   }
+#pragma unroll
+  for (int i = 0; i < kA2bPerLane; ++i) if (lane + 32 * i < kA2bN) s_a2b[lane + 32 * i] = a2b_reg[i];   // loaded with the prologue's other loads
   __syncwarp();
   CCRS_TCK(1);
 
