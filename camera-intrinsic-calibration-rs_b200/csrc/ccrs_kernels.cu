@@ -663,30 +663,17 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
         acc[0] += rows_of(it % kObsStages, nullptr, nullptr);
       }
     } else {
-      // Software-pipelined by hand: the model chain of observation i+1 (rsqrt -> reciprocal -> Huber, one long
-      // dependent sequence) is issued in the same basic block as the NACC independent DFMAs that accumulate
-      // observation i, so ptxas interleaves them and the FP64 pipe stays busy with two warps per sub-partition.
-      auto accumulate = [&](const double* __restrict__ au, const double* __restrict__ av) { gram_accumulate<C>(acc, au, av); };
-      if (beg < end) {
-        double au0[C::NA], av0[C::NA], au1[C::NA], av1[C::NA];
-        cp_async_wait<kObsStages - 2>();
-        rows_of(0, au0, av0);
-        int it = 0, k = beg;
-        while (true) {
-          // slot (it+1) holds observation i+1 — or stale data when the slice is exhausted (result discarded)
-          fetch(k + (kObsStages - 1) * G, (it + kObsStages - 1) % kObsStages);
-          cp_async_wait<kObsStages - 2>();
-          rows_of((it + 1) % kObsStages, au1, av1);
-          accumulate(au0, av0);
-          k += G; ++it;
-          if (k >= end) break;
-          fetch(k + (kObsStages - 1) * G, (it + kObsStages - 1) % kObsStages);
-          cp_async_wait<kObsStages - 2>();
-          rows_of((it + 1) % kObsStages, au0, av0);
-          accumulate(au1, av1);
-          k += G; ++it;
-          if (k >= end) break;
-        }
+      // One observation per iteration: model chain, then the NACC independent Gram DFMAs. (A hand software-pipelined
+      // version that issued observation i+1's chain among observation i's DFMAs was 2-5 % slower once the chain had been
+      // shortened: its second row buffer cost 44 registers that the accumulators need; the other resident warp of the
+      // sub-partition covers the chain's latency instead.)
+      int it = 0;
+      for (int k = beg; k < end; k += G, ++it) {
+        double au[C::NA], av[C::NA];
+        fetch(k + (kObsStages - 1) * G, (it + kObsStages - 1) % kObsStages);
+        cp_async_wait<kObsStages - 1>();
+        rows_of(it % kObsStages, au, av);
+        gram_accumulate<C>(acc, au, av);
       }
     }
     CCRS_TCK(2);
