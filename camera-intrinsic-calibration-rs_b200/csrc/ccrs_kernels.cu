@@ -614,11 +614,13 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
     const int n_pair = max(n_mine, __shfl_xor_sync(0xffffffffu, n_mine, 1));
     const unsigned pair_mask = 3u << (lane & 30);
     const bool odd = (lane & 1) != 0;
-    int k = beg;
-    for (int it = 0; it < n_pair; ++it, k += G) {
+    int k = beg, it = 0;
+    // one pair iteration; CHECKED = the lane's slice may be exhausted (only the last iteration of a ragged pair)
+    auto pair_step = [&](auto CHECKED) {
+      constexpr bool checked = decltype(CHECKED)::value;
       fetch(k + (kObsStages - 1) * G, (it + kObsStages - 1) % kObsStages);
       cp_async_wait<kObsStages - 1>();
-      const bool valid = it < n_mine;
+      const bool valid = !checked || it < n_mine;
       const double* src = ring + (it % kObsStages) * (5 * 32);
       auto ld = [&](int a) -> double {
         if constexpr (F32) return (double)*reinterpret_cast<const float*>(src + a * 32);
@@ -632,14 +634,18 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
       static_for<0, R::NA>([&](auto Cc) {
         constexpr int c = decltype(Cc)::value;
         const double a = au[C::ucol(c)], b = av[C::vcol(c)];
-        mine[c] = valid ? (odd ? b : a) : 0.0;
-        give[c] = valid ? (odd ? a : b) : 0.0;
+        if constexpr (checked) { mine[c] = valid ? (odd ? b : a) : 0.0; give[c] = valid ? (odd ? a : b) : 0.0; }
+        else { mine[c] = odd ? b : a; give[c] = odd ? a : b; }
       });
 #pragma unroll
       for (int c = 0; c < R::NA; ++c) give[c] = __shfl_xor_sync(pair_mask, give[c], 1);
       gram_row<R>(acc, mine);
       gram_row<R>(acc, give);
-    }
+      ++it; k += G;
+    };
+    const int n_both = min(n_mine, __shfl_xor_sync(0xffffffffu, n_mine, 1));   // iterations in which both lanes hold an observation
+    while (it < n_both) pair_step(std::false_type{});
+    while (it < n_pair) pair_step(std::true_type{});
     CCRS_TCK(2);
     if (active) basis_change<R>(acc, fc + 12);
   } else
