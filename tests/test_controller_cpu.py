@@ -90,3 +90,39 @@ def test_cholesky_failure_is_reported(pkg, oracle):
     _, _, res, _ = op.gauss_newton(pkg.synth.GT_PARAMS["eucm"], np.array([[0.1, 0.0, 0.0, 0.0, 0.0, 0.5]]))
     assert res.status == -2
     assert code == -5 and summ.status == -5   # CCRS_ERR_CHOLESKY
+
+
+def test_mask_value_2_removes_the_variable_from_the_system(pkg, oracle):
+    """init_ucm's [f, alpha] problem (util.rs:295-357): a one-focal UCM whose cx, cy carry mask 2 must follow the
+    oracle's dense Gauss-Newton over the reference's own variables ([f, alpha] + two poses), iteration by iteration."""
+    gt = np.array([400.0, 400.0, 512.0, 512.0, 0.6])
+    s = pkg.synth.make_calib("ucm", 2, seed=12, gt_params=gt, noise_px=0.1)
+    fa, poses_ref, res, hist_ref = oracle.init_ucm_gn(oracle.OracleProblem.from_synth(s, 0), 512.0, 512.0, 350.0, 0.55, s.init_poses)
+    op1 = oracle.OracleProblem.from_synth(s, 0, xy_same_focal=True, n_threads=2)
+    be = OracleBackend(pkg, op1, s.init_poses)
+    inf = np.inf
+    code, intr, poses, summ, hist = be.run("gn", np.array([350.0, 512.0, 512.0, 0.55]), np.array([350.0 / 3, -inf, -inf, 1e-6]),
+                                           np.array([350.0 * 3, inf, inf, 1.0]), np.array([0, 2, 2, 0], dtype=np.uint8))
+    assert code == 0 and summ.iterations == res.iterations
+    assert intr[1] == 512.0 and intr[2] == 512.0
+    assert abs(intr[0] - fa[0]) <= 1e-8 * fa[0] and abs(intr[3] - fa[1]) <= 1e-8 * fa[1]
+    assert np.max(np.abs(poses - poses_ref)) < 1e-8
+    assert np.allclose(hist, hist_ref, rtol=1e-9)
+    # with fixed_mode = 0, mask 1 would have kept cx, cy in the linear system (a different step): mask 2 is not mask 1
+    be1 = OracleBackend(pkg, op1, s.init_poses)
+    _, intr1, _, _, hist1 = be1.run("gn", np.array([350.0, 512.0, 512.0, 0.55]), None, None, np.array([0, 1, 1, 0], dtype=np.uint8))
+    assert intr1[1] == 512.0 and not np.allclose(hist1[:3], hist[:3], rtol=1e-6)
+
+
+def test_block_huber_changes_the_error_not_the_step(pkg, oracle):
+    """ModelConvertFactor is ONE residual block under one HuberLoss (util.rs:246-251): the corrector scales r and J by
+    the same factor, so the GN iterates are those of the loss-free problem and only the reported error changes."""
+    s, _ = _mk(pkg, oracle, "eucm", 8, 6, noise_px=0.5)
+    op = oracle.OracleProblem(1, s.width, s.height, s.frame_offsets, s.x, s.y, s.z, s.u, s.v, huber_delta=0.0, n_threads=2)
+    o_plain = pkg.default_options(max_iteration=4, min_abs_decrease=-1.0, min_rel_decrease=-1.0)
+    o_block = pkg.default_options(max_iteration=4, min_abs_decrease=-1.0, min_rel_decrease=-1.0, block_huber_delta=1.0)
+    _, intr_a, poses_a, _, hist_a = OracleBackend(pkg, op, s.init_poses).run("gn", s.init_params, options=o_plain)
+    _, intr_b, poses_b, _, hist_b = OracleBackend(pkg, op, s.init_poses).run("gn", s.init_params, options=o_block)
+    assert np.array_equal(intr_a, intr_b) and np.array_equal(poses_a, poses_b)
+    # error seen by the stop tests: ||r|| without the loss, (delta^2 s)^(1/4) = sqrt(delta ||r||) with it (s > delta^2)
+    assert np.all(hist_a > 1.0) and np.allclose(hist_b, np.sqrt(hist_a), rtol=1e-12)
