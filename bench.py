@@ -242,7 +242,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "ours",
-            "config": {"workload": WORKLOAD, "model": MODEL, "frames_per_gpu": FRAMES_PER_GPU, "obs_total": int(n_total),
+            "config": {"workload": WORKLOAD, "camera_model": MODEL, "frames_per_gpu": FRAMES_PER_GPU, "obs_total": int(n_total),
                        "obs_per_gpu": int(n_local), "parallelism": f"frame-sharded x{world}", "exchange": exch,
                        "l2": "flushed (512 MB write) before every timed step, outside the event bracket", "loop": "speculative LM"},
             "lm_iterations_per_s": 1e3 / ms_per_step,
@@ -309,7 +309,7 @@ def run_reference(args):
         "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "impl": "reference",
-        "config": {"workload": WORKLOAD, "model": MODEL, "frames_per_gpu": FRAMES_PER_GPU, "obs_total": int(n),
+        "config": {"workload": WORKLOAD, "camera_model": MODEL, "frames_per_gpu": FRAMES_PER_GPU, "obs_total": int(n),
                    "note": "CPU arm runs ONE rank's 7000-frame problem on the host cores regardless of N"},
         "lm_iterations_per_s": 1e3 / ms, "cpu_baseline": base,
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
