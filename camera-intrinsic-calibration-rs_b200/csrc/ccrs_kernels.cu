@@ -975,9 +975,10 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(const __grid_constant__
       el[(size_t)(6 * D + 6 + i) * Fs] = gp[i];
       el[(size_t)(6 * D + 12 + i) * Fs] = dd[i];
     }
-    if (bad) {  // poison the reduced system so the host sees the Cholesky failure (tiny-solver returns None)
+    if (bad) {  // poison the reduced system so the host sees the Cholesky failure (tiny-solver returns None); the cost
+                // (last entry) stays valid: the failure is the factorisation's, not a NaN error
 #pragma unroll
-      for (int i = 0; i < NRED; ++i) red[i] = nan("");
+      for (int i = 0; i < NRED - 1; ++i) red[i] = nan("");
     }
   }
   CCRS_TK3(2);

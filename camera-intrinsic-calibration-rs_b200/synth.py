@@ -268,13 +268,20 @@ def make_rig(model: str = "eucm", n_frames: int = 200, n_cams: int = 2, seed: in
             us.append(uv[f, idx, 0]); vs.append(uv[f, idx, 1])
     cat = np.concatenate
     poses = cat([rvec, tvec], axis=1)
+    # a frame no camera detected is not a variable of the problem (util.rs:588-600 only creates "rvec_0_b_{f}" for
+    # frames with a detection): drop it and renumber
+    used = np.zeros(n_frames, dtype=bool); used[np.asarray(bf, dtype=np.int64)] = True
+    renum = np.cumsum(used) - 1
+    bf = [int(renum[f]) for f in bf]
+    poses = poses[used]
+    n_all, n_frames = n_frames, int(used.sum())
     init_params = gt_params * INIT_SCALE[model][None, :]
     init_extr = gt_extr.copy()
     init_extr[1:, :3] += rng.normal(scale=0.005, size=(n_cams - 1, 3))
     init_extr[1:, 3:] += rng.normal(scale=0.005, size=(n_cams - 1, 3))
     init_poses = poses.copy()
-    init_poses[:, :3] += rng.normal(scale=0.01, size=(n_frames, 3))
-    init_poses[:, 3:] += rng.normal(scale=0.005, size=(n_frames, 3))
+    init_poses[:, :3] += rng.normal(scale=0.01, size=(n_all, 3))[used]
+    init_poses[:, 3:] += rng.normal(scale=0.005, size=(n_all, 3))[used]
     return SyntheticRig(model=model, width=width, height=height, n_cams=n_cams, n_frames=n_frames,
                         block_cam=np.asarray(bc, dtype=np.int32), block_frame=np.asarray(bf, dtype=np.int32),
                         block_offsets=np.asarray(offs, dtype=np.int32), x=cat(xs), y=cat(ys), z=cat(zs), u=cat(us), v=cat(vs),

@@ -58,6 +58,15 @@ def test_oracle_joint_gn_recovers_ground_truth(pkg, oracle):
     assert np.all(e[0] == 0.0)
 
 
+def test_make_rig_keeps_only_detected_frames(pkg):
+    """a frame no camera detected is not a variable (util.rs:588-600): the generator drops it — with 200 frames and a
+    10 % miss rate per camera a couple of frames always go, which used to leave singular pose blocks behind."""
+    rig = pkg.synth.make_rig("kb4", 200, 2, seed=4)
+    assert rig.n_frames < 200
+    assert sorted(set(rig.block_frame.tolist())) == list(range(rig.n_frames))
+    assert rig.gt_poses.shape == (rig.n_frames, 6) and rig.init_poses.shape == (rig.n_frames, 6)
+
+
 # ----------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("one_focal", [False, True])
