@@ -195,73 +195,148 @@ __global__ void __launch_bounds__(32 * kJWarps) k_joint_linearize(JointDev jd, c
 
 // per frame: gather the blocks of every camera, eliminate T_0_b_f. Output per frame:
 // fs[f][NS + M + 1] = packed upper S_f (shared x shared), g_s (M), sum r^2 ; el[f][6*M + 6] = X (6 x M), C^-1 g_p
-__global__ void __launch_bounds__(64) k_joint_schur(JointDev jd, const double* __restrict__ jblk, int NAJ, int M,
-                                                    double u_damp, double* __restrict__ fs, double* __restrict__ el) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per frame (a thread per frame spent ~200 us in serial read-modify-write of its 250-entry system): the
+// frame's shared system lives in the warp's shared memory; the lanes scatter the packed entries of each camera block
+// into it (every entry of a block has its own target: no atomics; blocks in order: deterministic), all lanes factor the
+// 6x6 pose block redundantly in registers, then the columns of Y = L^-1 B^T and the entries of S -= Y^T Y are spread
+// over the lanes.
+constexpr int kJSchurWarps = 4;
+__host__ __device__ inline int jschur_warp_doubles(int M) { return M * (M + 1) / 2 + 7 * M + 48; }   // S | B (M x 6) | gs | L (36) gp (6) pad
+
+__global__ void __launch_bounds__(32 * kJSchurWarps) k_joint_schur(JointDev jd, const double* __restrict__ jblk,
+                                                                  const uint16_t* __restrict__ ij_table, int NAJ, int M,
+                                                                  double u_damp, double* __restrict__ fs, double* __restrict__ el) {
+  extern __shared__ double jsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = blockIdx.x * kJSchurWarps + warp;
   if (f >= jd.n_frames) return;
   const int d = jd.d, C = jd.n_cams, NBJ = NAJ * (NAJ + 1) / 2, NS = M * (M + 1) / 2, n = d + 12;
   const int off_e = C * d;
-  double* S = fs + (size_t)f * (NS + M + 1);
-  double* gs = S + NS;
-  for (int i = 0; i < NS + M + 1; ++i) S[i] = 0.0;
-  double B[kMaxShared][6];
-  for (int i = 0; i < M; ++i) for (int x = 0; x < 6; ++x) B[i][x] = 0.0;
-  double L[6][6], gp[6];
-  for (int i = 0; i < 6; ++i) { gp[i] = 0.0; for (int j = 0; j < 6; ++j) L[i][j] = 0.0; }
+  double* S = jsm + (size_t)warp * jschur_warp_doubles(M);
+  double* B = S + NS;          // [M][6]
+  double* gs = B + 6 * M;      // [M]
+  double* Lm = gs + M;         // [6][6] lower
+  double* gp = Lm + 36;        // [6]
+  for (int i = lane; i < NS + 7 * M + 42; i += 32) S[i] = 0.0;
+  __syncwarp();
   double sq = 0.0;
-  auto sidx = [&](int i, int j) { return i <= j ? tri_idx(M, i, j) : tri_idx(M, j, i); };
   for (int q = jd.frame_block_offsets[f]; q < jd.frame_block_offsets[f + 1]; ++q) {
     const int b = jd.frame_blocks[q], c = jd.block_cam[b];
     const double* Hb = jblk + (size_t)b * NBJ;
-    auto H = [&](int i, int j) { return i <= j ? Hb[tri_idx(NAJ, i, j)] : Hb[tri_idx(NAJ, j, i)]; };
     // shared index of block column i (theta: 0..d-1 ; extrinsic: d+6..d+11), -1 if not a shared column
     auto sh = [&](int i) { return i < d ? c * d + i : (i >= d + 6 && i < n && c > 0 ? off_e + 6 * (c - 1) + (i - d - 6) : -1); };
-    for (int i = 0; i < n; ++i) {
-      const int si = sh(i);
-      if (si < 0) continue;
-      for (int j = i; j < n; ++j) { const int sj = sh(j); if (sj >= 0) S[sidx(si, sj)] += H(i, j); }
-      for (int x = 0; x < 6; ++x) B[si][x] += H(i, d + x);
-      gs[si] -= H(i, n);
+    for (int e = lane; e < NBJ; e += 32) {
+      const uint16_t t = ij_table[e];
+      const int i = t >> 8, j = t & 255;      // i <= j
+      const double h = Hb[e];
+      const bool ip = i >= d && i < d + 6, jp = j >= d && j < d + 6;
+      if (j == n) {                            // the r column: gradient / cost
+        if (i == n) sq += h;
+        else if (ip) gp[i - d] -= h;
+        else { const int si = sh(i); if (si >= 0) gs[si] -= h; }
+      } else if (ip && jp) {
+        Lm[(j - d) * 6 + (i - d)] += h;        // lower triangle: row >= column
+      } else if (ip) {                         // pose x extrinsic column
+        const int sj = sh(j); if (sj >= 0) B[sj * 6 + (i - d)] += h;
+      } else if (jp) {                         // intrinsic x pose column
+        const int si = sh(i); if (si >= 0) B[si * 6 + (j - d)] += h;
+      } else {
+        const int si = sh(i), sj = sh(j);
+        if (si >= 0 && sj >= 0) S[si <= sj ? tri_idx(M, si, sj) : tri_idx(M, sj, si)] += h;
+      }
     }
-    for (int i = 0; i < 6; ++i) { for (int j = 0; j <= i; ++j) L[i][j] += H(d + j, d + i); gp[i] -= H(d + i, n); }
-    sq += H(n, n);
+    __syncwarp();
   }
-  gs[M] = sq;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  // 6x6 Cholesky of the (damped) pose block and L^-1 g_p: every lane, in registers
+  double L[6][6], yg[6];
   int bad = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) L[i][j] = Lm[i * 6 + j];
+#pragma unroll
   for (int i = 0; i < 6; ++i) L[i][i] += u_damp * L[i][i];
+#pragma unroll
   for (int j = 0; j < 6; ++j) {
-    double s = L[j][j];
-    for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
-    if (!(s > 0.0)) bad = 1;
-    const double il = 1.0 / sqrt(s);
+    double t = L[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) t -= L[j][k] * L[j][k];
+    if (!(t > 0.0)) bad = 1;
+    const double il = 1.0 / sqrt(t);
     L[j][j] = il;
+#pragma unroll
     for (int i = j + 1; i < 6; ++i) {
-      double t = L[i][j];
-      for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k];
-      L[i][j] = t * il;
+      double w = L[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) w -= L[i][k] * L[j][k];
+      L[i][j] = w * il;
     }
   }
-  double yg[6];
-  for (int i = 0; i < 6; ++i) { double s = gp[i]; for (int k = 0; k < i; ++k) s -= L[i][k] * yg[k]; yg[i] = s * L[i][i]; }
-  for (int a = 0; a < M; ++a) {   // Y[a] = L^-1 B[a]
-    for (int i = 0; i < 6; ++i) { double s = B[a][i]; for (int k = 0; k < i; ++k) s -= L[i][k] * B[a][k]; B[a][i] = s * L[i][i]; }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double t = gp[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) t -= L[i][k] * yg[k];
+    yg[i] = t * L[i][i];
   }
-  for (int a = 0; a < M; ++a) {
-    for (int b2 = a; b2 < M; ++b2) {
-      double s = 0.0;
-      for (int i = 0; i < 6; ++i) s += B[a][i] * B[b2][i];
-      S[tri_idx(M, a, b2)] -= s;
+  __syncwarp();
+  // Y[a] = L^-1 B[a] (columns over lanes), kept in B
+  for (int a = lane; a < M; a += 32) {
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double t = B[a * 6 + i];
+#pragma unroll
+      for (int k = 0; k < i; ++k) t -= L[i][k] * y[k];
+      y[i] = t * L[i][i];
     }
-    double s = 0.0;
-    for (int i = 0; i < 6; ++i) s += B[a][i] * yg[i];
-    gs[a] -= s;
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { B[a * 6 + i] = y[i]; t += y[i] * yg[i]; }
+    gs[a] -= t;
   }
-  double* e = el + (size_t)f * (6 * M + 6);
-  for (int a = 0; a < M; ++a) {   // X = L^-T Y
-    for (int i = 5; i >= 0; --i) { double s = B[a][i]; for (int k = i + 1; k < 6; ++k) s -= L[k][i] * B[a][k]; B[a][i] = s * L[i][i]; e[i * M + a] = B[a][i]; }
+  __syncwarp();
+  // S -= Y^T Y (entries over lanes) -> fs
+  double* So = fs + (size_t)f * (NS + M + 1);
+  const double poison = bad ? nan("") : 0.0;   // host reports the LLT failure (S and g_s poisoned, not the cost)
+  for (int e = lane; e < NS; e += 32) {
+    int a = 0, rem = e;                        // row a of the packed upper triangle holds M - a entries
+    while (rem >= M - a) { rem -= M - a; ++a; }
+    const int b2 = a + rem;
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) t += B[a * 6 + i] * B[b2 * 6 + i];
+    So[e] = S[e] - t + poison;
   }
-  for (int i = 5; i >= 0; --i) { double s = yg[i]; for (int k = i + 1; k < 6; ++k) s -= L[k][i] * yg[k]; yg[i] = s * L[i][i]; e[6 * M + i] = yg[i]; }
-  if (bad) for (int i = 0; i < NS + M; ++i) S[i] = nan("");   // poison S and g_s (not the cost): host reports the LLT failure
+  for (int a = lane; a < M; a += 32) So[NS + a] = gs[a] + poison;
+  if (lane == 0) So[NS + M] = sq;
+  // X = L^-T Y, C^-1 g_p -> el
+  double* eo = el + (size_t)f * (6 * M + 6);
+  for (int a = lane; a < M; a += 32) {
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] = B[a * 6 + i];
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+      double t = y[i];
+#pragma unroll
+      for (int k = i + 1; k < 6; ++k) t -= L[k][i] * y[k];
+      y[i] = t * L[i][i];
+      eo[i * M + a] = y[i];
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+      double t = yg[i];
+#pragma unroll
+      for (int k = i + 1; k < 6; ++k) t -= L[k][i] * yg[k];
+      yg[i] = t * L[i][i];
+      eo[6 * M + i] = yg[i];
+    }
+  }
 }
 
 // out[v] = sum_f fs[f][v], f ascending (fixed order)
@@ -273,15 +348,17 @@ __global__ void k_joint_sum(const double* __restrict__ fs, int F, int NV, double
   out[v] = s;
 }
 
-__global__ void k_joint_backsub(JointDev jd, const double* __restrict__ el, const double* __restrict__ y, int M) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per frame: lane (i, part) sums a strided part of row i of X y; five lanes per row, fixed combine order
+__global__ void __launch_bounds__(128) k_joint_backsub(JointDev jd, const double* __restrict__ el, const double* __restrict__ y, int M) {
+  const int f = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (f >= jd.n_frames) return;
   const double* e = el + (size_t)f * (6 * M + 6);
-  for (int i = 0; i < 6; ++i) {
-    double s = e[6 * M + i];
-    for (int a = 0; a < M; ++a) s -= e[i * M + a] * y[a];
-    jd.poses[6 * (size_t)f + i] += s;
-  }
+  const int i = lane / 5, part = lane - 5 * i;     // lanes 0..29: row i, part 0..4; lanes 30, 31 idle
+  double s = 0.0;
+  if (i < 6) for (int a = part; a < M; a += 5) s += e[i * M + a] * y[a];
+  const double s1 = __shfl_down_sync(0xffffffffu, s, 1), s2 = __shfl_down_sync(0xffffffffu, s, 2);
+  const double s3 = __shfl_down_sync(0xffffffffu, s, 3), s4 = __shfl_down_sync(0xffffffffu, s, 4);
+  if (i < 6 && part == 0) jd.poses[6 * (size_t)f + i] += e[6 * M + i] - ((((s + s1) + s2) + s3) + s4);
 }
 
 template <class F>
@@ -481,7 +558,15 @@ int ccrs_joint_solve_gn(ccrs_joint* p, double* intr, double* extr, double* poses
       return cudaGetLastError();
     });
     JCK(e);
-    k_joint_schur<<<(F + 63) / 64, 64, 0, p->stream>>>(jd, p->jblk, p->NAJ, M, 0.0, p->fs, p->el);
+    {
+      const size_t smem = (size_t)kJSchurWarps * jschur_warp_doubles(M) * sizeof(double);
+      static size_t configured = 0;
+      if (smem > 48 * 1024 && smem > configured) {
+        JCK(cudaFuncSetAttribute(k_joint_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+      }
+      k_joint_schur<<<(F + kJSchurWarps - 1) / kJSchurWarps, 32 * kJSchurWarps, smem, p->stream>>>(jd, p->jblk, p->ij_table, p->NAJ, M, 0.0, p->fs, p->el);
+    }
     JCK(cudaGetLastError());
     k_joint_sum<<<(NV + 127) / 128, 128, 0, p->stream>>>(p->fs, F, NV, p->red);
     JCK(cudaGetLastError());
@@ -514,7 +599,7 @@ int ccrs_joint_solve_gn(ccrs_joint* p, double* intr, double* extr, double* poses
     }
     for (int c = 1; c < C; ++c) for (int i = 0; i < 6; ++i) extr[6 * c + i] += y[C * d + 6 * (c - 1) + i];
     JCK(cudaMemcpyAsync(p->ydev, y.data(), (size_t)M * 8, cudaMemcpyHostToDevice, p->stream));
-    k_joint_backsub<<<(F + 63) / 64, 64, 0, p->stream>>>(jd, p->el, p->ydev, M);
+    k_joint_backsub<<<(F + 3) / 4, 128, 0, p->stream>>>(jd, p->el, p->ydev, M);
     JCK(cudaGetLastError());
     p->launches++;
     st = upload_state(p, intr, extr, nullptr);
