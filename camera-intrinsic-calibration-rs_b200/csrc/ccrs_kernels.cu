@@ -507,6 +507,33 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
     fo_end = __ldg(pb.frame_offsets + f + 1);
     fo_beg = __ldg(pb.frame_offsets + f);
     prob = BATCH ? pb.frame_problem[f] : 0;
+  }
+  int end = 0, beg = 0;
+  double* ring = s_obs + lane;
+  auto fetch = [&](int kk, int stage) {
+    if (kk < end) {
+      double* dst = ring + stage * (5 * 32);
+      if constexpr (F32) {
+        const float *fx = (const float*)pb.x, *fy = (const float*)pb.y, *fz = (const float*)pb.z, *fu = (const float*)pb.u, *fv = (const float*)pb.v;
+        cp_async4(dst, fx + kk); cp_async4(dst + 32, fy + kk); cp_async4(dst + 64, fz + kk);
+        cp_async4(dst + 96, fu + kk); cp_async4(dst + 128, fv + kk);
+      } else {
+        cp_async8(dst, pb.x + kk); cp_async8(dst + 32, pb.y + kk); cp_async8(dst + 64, pb.z + kk);
+        cp_async8(dst + 96, pb.u + kk); cp_async8(dst + 128, pb.v + kk);
+      }
+    }
+    cp_async_commit();
+  };
+  auto prefetch_first_stages = [&]() {
+    end = active ? fo_end : 0;
+    beg = active ? fo_beg + sl : 0;
+#pragma unroll
+    for (int i = 0; i < kObsStages - 1; ++i) fetch(beg + i * G, i);
+  };
+  // batch handles reach their pose through two more dependent loads (frame -> problem -> state selector): there the
+  // observation prefetch goes out as soon as the frame offsets are back; a single problem issues everything first
+  if constexpr (BATCH) prefetch_first_stages();
+  if (active) {
     cur = cur_of(pb, prob);
     if (prm.backsub) {
       const double* src = pb.poses[cur] + 6 * (size_t)f;
@@ -534,25 +561,7 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
       for (int i = 0; i < 6; ++i) rt[i] = src[i];
     }
   }
-  const int end = active ? fo_end : 0;
-  const int beg = active ? fo_beg + sl : 0;
-  double* ring = s_obs + lane;
-  auto fetch = [&](int kk, int stage) {
-    if (kk < end) {
-      double* dst = ring + stage * (5 * 32);
-      if constexpr (F32) {
-        const float *fx = (const float*)pb.x, *fy = (const float*)pb.y, *fz = (const float*)pb.z, *fu = (const float*)pb.u, *fv = (const float*)pb.v;
-        cp_async4(dst, fx + kk); cp_async4(dst + 32, fy + kk); cp_async4(dst + 64, fz + kk);
-        cp_async4(dst + 96, fu + kk); cp_async4(dst + 128, fv + kk);
-      } else {
-        cp_async8(dst, pb.x + kk); cp_async8(dst + 32, pb.y + kk); cp_async8(dst + 64, pb.z + kk);
-        cp_async8(dst + 96, pb.u + kk); cp_async8(dst + 128, pb.v + kk);
-      }
-    }
-    cp_async_commit();
-  };
-#pragma unroll
-  for (int i = 0; i < kObsStages - 1; ++i) fetch(beg + i * G, i);
+  if constexpr (!BATCH) prefetch_first_stages();
 
   // ---- prologue: every lane of a frame evaluates the frame's pose redundantly (same addresses: broadcast loads);
   //      slice 0 stores. Fused K4: y_p = cg - X y_a ; pose += D_p y_p ; model decrease y_p^T g'_p + u sum dd_i y_p,i^2
