@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(kPnpWarps * 32) k_pnp(const int32_t* __restric
   start_rotation(lane, R);
   double cost = quad_form(Om, R, w);
   double lam = 1e-3;
+  bool settled = false;   // sticky: this run has taken a step below rounding level, or damped itself to a standstill
   for (int it = 0; it < kPnpIters; ++it) {
     // tangent basis J_k = vec([e_k]x R): rows (0, -R2, R1), (R2, 0, -R0), (-R1, R0, 0)
     double J[3][9];
@@ -238,6 +239,8 @@ __global__ void __launch_bounds__(kPnpWarps * 32) k_pnp(const int32_t* __restric
     } else {
       lam = fmin(lam * 10.0, 1e15);
     }
+    settled = settled || (pd && dn < 1e-12) || lam >= 1e10;
+    if (__all_sync(0xffffffffu, settled)) break;   // warp-uniform exit: typically after 8-12 of the 40 iterations
   }
   // ---- t = P r; keep the cheapest solution that puts the board in front of the camera (mean depth > 0)
   double t[3];
