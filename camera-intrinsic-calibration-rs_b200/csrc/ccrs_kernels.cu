@@ -1085,24 +1085,20 @@ __global__ void k_sum_partials(const double* __restrict__ partials, int n_part, 
   }
 }
 
-// out[seg][v] = sum_{f in segment} in[v][f]; one CTA per segment; fixed strided order + fixed tree
+// out[seg][v] = sum_{f in segment} in[v][f]; one CTA per segment, one WARP per value (eight values in flight, no CTA
+// barrier): lane-strided partial sums in frame order, then a fixed butterfly — bit-reproducible.
 constexpr int kSegThreads = 256;
 __global__ void __launch_bounds__(kSegThreads) k_segreduce(const double* __restrict__ in, int NV, int Fs,
                                                            const int32_t* __restrict__ seg_off, double* __restrict__ out) {
-  __shared__ double sh[kSegThreads];
-  const int seg = blockIdx.x;
+  const int seg = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = seg_off[seg], e = seg_off[seg + 1];
-  for (int v = 0; v < NV; ++v) {
+  for (int v = warp; v < NV; v += kSegThreads / 32) {
+    const double* src = in + (size_t)v * Fs;
     double s = 0.0;
-    for (int f = b + threadIdx.x; f < e; f += kSegThreads) s += in[(size_t)v * Fs + f];
-    sh[threadIdx.x] = s;
-    __syncthreads();
-    for (int w = kSegThreads / 2; w > 0; w >>= 1) {
-      if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) out[(size_t)seg * NV + v] = sh[0];
-    __syncthreads();
+    for (int f = b + lane; f < e; f += 32) s += src[f];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[(size_t)seg * NV + v] = s;
   }
 }
 
