@@ -366,8 +366,9 @@ def initial_poses(frame_feature_list: Sequence[Optional[FrameFeature]], generic_
 def init_ucm(frame_feature0: FrameFeature, frame_feature1: FrameFeature, rtvec0: RvecTvec, rtvec1: RvecTvec,
              init_f: float, init_alpha: float, fixed_focal: bool, options: Optional[Options] = None,
              device: int = 0) -> Optional[GenericModel]:
-    """Mirror of init_ucm (src/util.rs:284-378): [f, alpha] fit on two frames, then the one-focal UCM calibration of
-    those two frames. Returns None where the reference returns None (optimiser failure in the first stage)."""
+    """Mirror of init_ucm (src/util.rs:284-378): [f, alpha] fit on two frames, then — from fresh PnP poses under that
+    model, like the reference — the one-focal UCM calibration of those two frames. Returns None where the reference
+    returns None (optimiser failure in the first stage)."""
     frames = [frame_feature0, frame_feature1]
     _, offs, x, y, z, u, v, poses = pack_frames(frames, {0: rtvec0, 1: rtvec1})
     if len(offs) != 3:

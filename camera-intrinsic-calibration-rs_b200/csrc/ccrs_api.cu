@@ -1375,6 +1375,40 @@ int ccrs_init_ucm(int width, int height, int n_frames, const int32_t* frame_offs
   if (st) { s1.status = st; if (summary) *summary = s1; return st; }
   // stage 2: calib_camera(frames, UCM[f f w/2 h/2 alpha], one_focal = true, 0, fixed_focal)  (util.rs:358-372)
   params_out[0] = intr[0]; params_out[1] = intr[0]; params_out[2] = half_w; params_out[3] = half_h; params_out[4] = intr[3];
+  // ... which starts from fresh poses: calib_camera unprojects every detection with the new model and solves the PnP
+  // per frame (util.rs:418-439); the stage-1 poses are dropped (util.rs:356). UCM unprojection is closed form:
+  // m = ((u - cx)/f, (v - cy)/f), mz = (1 - a^2 r^2) / (a sqrt(1 - (2a - 1) r^2) + 1 - a); normalised point m / mz as f32.
+  {
+    const double f = intr[0], a = intr[3];
+    std::vector<int32_t> fo2(1, 0), src_frame;
+    std::vector<double> x2, y2, z2, xn, yn;
+    for (int fr = 0; fr < n_frames; ++fr) {
+      const size_t before = x2.size();
+      for (int k = frame_offsets[fr]; k < frame_offsets[fr + 1]; ++k) {
+        const double mx = (u[k] - half_w) / f, my = (v[k] - half_h) / f, r2 = mx * mx + my * my;
+        const double disc = 1.0 - (2.0 * a - 1.0) * r2;
+        if (disc < 0.0) continue;                                     // outside the model's domain: unproject -> None
+        const double mz = (1.0 - a * a * r2) / (a * std::sqrt(disc) + 1.0 - a);
+        if (!(std::fabs(mz) > 1e-12)) continue;
+        x2.push_back(x[k]); y2.push_back(y[k]); z2.push_back(z[k]);
+        xn.push_back((double)(float)(mx / mz)); yn.push_back((double)(float)(my / mz));   // glam::Vec2 (util.rs:425)
+      }
+      if (x2.size() - before < 10) {                                  // util.rs:431-433: the frame keeps its stage-1 pose here
+        x2.resize(before); y2.resize(before); z2.resize(before); xn.resize(before); yn.resize(before);
+        continue;
+      }
+      fo2.push_back((int32_t)x2.size());
+      src_frame.push_back(fr);
+    }
+    if (!src_frame.empty()) {
+      std::vector<double> pnp(6 * src_frame.size());
+      st = ccrs_init_poses((int)src_frame.size(), fo2.data(), x2.data(), y2.data(), z2.data(), xn.data(), yn.data(), pnp.data(),
+                           nullptr, device_id);
+      if (st) { s1.status = st; if (summary) *summary = s1; return st; }
+      for (size_t i = 0; i < src_frame.size(); ++i)
+        for (int j = 0; j < 6; ++j) poses[6 * (size_t)src_frame[i] + j] = pnp[6 * i + j];
+    }
+  }
   st = ccrs_calib_camera(CCRS_UCM, width, height, n_frames, frame_offsets, x, y, z, u, v, params_out, poses, 1, 0,
                          fixed_focal, 0, opt, &s2, device_id);
   s2.iterations += s1.iterations; s2.device_ms += s1.device_ms;

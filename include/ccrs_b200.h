@@ -274,8 +274,9 @@ int ccrs_set_fixed_poses(ccrs_problem* p, int fixed);
  * centre (UCMInitFocalAlphaFactor, factors.rs:83-120) and the poses of the given frames (two in the reference), Huber
  * loss 1.0, f in [init_f / 3, 3 init_f], alpha in [1e-6, 1], fixed_focal = fix_variable("params", 0). It runs on the
  * ReprojectionFactor kernels as a one-focal UCM problem whose cx, cy are removed from the linear system.
- * Stage 2 (util.rs:358-372): calib_camera(frames, UCM[f, f, w/2, h/2, alpha], one_focal = true, 0, fixed_focal); the
- * stage-1 poses are its initial poses (the reference re-runs SQPnP there; pose initialisation is an input here).
+ * Stage 2 (util.rs:358-372): calib_camera(frames, UCM[f, f, w/2, h/2, alpha], one_focal = true, 0, fixed_focal), which
+ * like the reference starts from fresh poses: every detection is unprojected with the stage-1 model (UCM: closed form)
+ * and the PnP of each frame is solved by ccrs_init_poses (util.rs:418-439); the stage-1 poses are dropped.
  * params_out[5] = fx fy cx cy alpha; poses[n_frames][6] in/out. */
 int ccrs_init_ucm(int width, int height, int n_frames, const int32_t* frame_offsets,
                   const double* x, const double* y, const double* z, const double* u, const double* v,

@@ -60,15 +60,21 @@ def test_gpu_init_ucm_matches_oracle(pkg, oracle, fixed_focal):
     s = pkg.synth.make_calib("ucm", 2, seed=11, gt_params=gt, noise_px=0.05)
     op = oracle.OracleProblem.from_synth(s, 0)
     f0, a0 = 330.0, 0.5
-    # oracle: stage 1 directly restated, stage 2 = one-focal UCM Gauss-Newton (+ fixed-focal second pass) from the
-    # stage-1 result, with the stage-1 poses as initial poses (the product's documented convention)
+    # oracle: stage 1 directly restated; stage 2 = calib_camera of the two frames with the stage-1 model (util.rs:358-372):
+    # fresh PnP poses under that model (the CUDA pose initialisation, checked on its own in test_init_poses.py), then
+    # one-focal UCM Gauss-Newton (+ the fixed-focal second pass)
     fa, poses1, res1, _ = oracle.init_ucm_gn(op, 512.0, 512.0, f0, a0, s.init_poses, fixed_focal=fixed_focal)
     assert res1.status == 0
+    frames, _ = pkg.synth.to_frame_features(s)
+    cam1 = pkg.GenericModel("ucm", np.array([fa[0], fa[0], 512.0, 512.0, fa[1]]), s.width, s.height)
+    init = pkg.initial_poses(frames, cam1)
+    poses_pnp = np.array([init[f].as_array() for f in range(s.n_frames)])
+    assert np.max(np.abs(poses_pnp - s.gt_poses)) < 0.2          # rough (the stage-1 model is approximate) but sane
     op1 = oracle.OracleProblem.from_synth(s, 0, xy_same_focal=True)
     lo, hi = pkg.model_bounds("ucm", s.width, s.height)
     lo1, hi1 = np.delete(lo, 1), np.delete(hi, 1)
     intr = np.array([fa[0], 512.0, 512.0, fa[1]])
-    intr, poses2, _, _ = op1.gauss_newton(intr, poses1, lo1, hi1)
+    intr, poses2, _, _ = op1.gauss_newton(intr, poses_pnp, lo1, hi1)
     if fixed_focal:
         intr[0] = fa[0]
         intr, poses2, _, _ = op1.gauss_newton(intr, poses2, lo1, hi1, fixed=[1, 0, 0, 0])
