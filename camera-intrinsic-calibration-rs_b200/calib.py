@@ -296,11 +296,16 @@ def pack_frames(frame_feature_list: Sequence[Optional[FrameFeature]], initial_po
 
 def calib_camera(frame_feature_list: Sequence[Optional[FrameFeature]], generic_camera: GenericModel,
                  xy_same_focal: bool, disabled_distortions: int, fixed_focal: bool,
-                 initial_poses: Dict[int, RvecTvec], use_lm: bool = False, options: Optional[Options] = None,
+                 initial_poses: Optional[Dict[int, RvecTvec]] = None, use_lm: bool = False,
+                 options: Optional[Options] = None,
                  device: int = 0) -> Optional[Tuple[GenericModel, Dict[int, RvecTvec]]]:
-    """Mirror of calib_camera (src/util.rs:384-490). Returns None where the reference returns None
-    (optimiser failure: NaN error or Cholesky failure)."""
+    """Mirror of calib_camera (src/util.rs:384-490). With the reference's own five arguments the initial pose of every
+    frame comes from the pose-initialisation step (unproject + PnP per frame, util.rs:418-439; here one launch for all
+    frames); `initial_poses` overrides it. Returns None where the reference returns None (optimiser failure: NaN error
+    or Cholesky failure)."""
     lib = _abi.load()
+    if initial_poses is None:
+        initial_poses = globals()["initial_poses"](frame_feature_list, generic_camera, device=device)
     valid, offs, x, y, z, u, v, poses = pack_frames(frame_feature_list, initial_poses)
     if not valid:
         return None

@@ -95,3 +95,6 @@ def test_initial_poses_feed_calib_camera(pkg):
     out = pkg.calib_camera(frames, cam0, False, 0, False, init)
     assert out is not None
     assert np.max(np.abs(out[0].params - s.gt_params) / np.abs(s.gt_params)) < 1e-3
+    # the reference's own signature (no poses passed): the mirror runs the same initialisation itself
+    out2 = pkg.calib_camera(frames, cam0, False, 0, False)
+    assert out2 is not None and np.array_equal(out2[0].params, out[0].params)
