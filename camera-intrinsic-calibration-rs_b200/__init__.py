@@ -11,9 +11,10 @@ from .calib import (MODELS, FeaturePoint, FrameFeature, GenericModel, JointProbl
                     calib_all_camera_with_extrinsics, calib_camera, comm_unique_id, convert_model, init_poses, init_ucm, initial_poses,
                     measure_fp64_peak, model_bounds, pack_frames, validation)
 from . import synth
+from . import io
 from . import models
 from . import dist
 
 __all__ = ["CcrsError", "Options", "Summary", "default_options", "LIB_PATH", "SYMBOLS", "MODELS", "FeaturePoint",
            "FrameFeature", "GenericModel", "JointProblem", "calib_all_camera_with_extrinsics", "Problem", "RvecTvec", "calib_camera", "comm_unique_id", "measure_fp64_peak",
-           "model_bounds", "pack_frames", "validation", "convert_model", "init_poses", "initial_poses", "init_ucm", "synth", "models", "dist"]
+           "model_bounds", "pack_frames", "validation", "convert_model", "init_poses", "initial_poses", "init_ucm", "synth", "models", "io", "dist"]
