@@ -54,4 +54,4 @@ def test_poses_and_report(pkg, tmp_path):
     pkg.io.write_report(str(r), True, [(0.123456, 0.1), (1.0, 0.987654)])
     assert r.read_text() == ("Calibrate with extrinsics: true\n\ncam0:\n    average reprojection error: 0.12346 px\n"
                              "    median  reprojection error: 0.10000 px\n\ncam1:\n    average reprojection error: 1.00000 px\n"
-                             "    median  reprojection error: 0.98765 px\n\n").replace("\\\n", "\n")
+                             "    median  reprojection error: 0.98765 px\n\n")
