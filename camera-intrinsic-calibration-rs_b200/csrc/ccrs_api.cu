@@ -183,6 +183,7 @@ struct ccrs_problem {
   DevBuf<double> red_out, stat_out, gather, intr_dev, ya_dev, u_dev, scale_dev, l2_flush;
   DevBuf<unsigned char> mask_dev;
   DevBuf<unsigned int> tickets;   // [0] K2 statistics, [1] K3 reduction
+  PinBuf<double> h_colsq;         // mapped: single problem [D] squared intrinsic column norms (Jacobi scaling)
   PinBuf<double> h_red, h_stat;   // mapped: single problem [NRED + 1] / [4] (last = sequence number); batch: plain D2H targets
   bool have_scale = false, have_obs_frame = false;
   bool fixed_poses = false;       // poses are constants (ccrs_set_fixed_poses)
@@ -300,7 +301,7 @@ int upload_problem(ccrs_problem* p, int n_problems, const int32_t* problem_frame
   CK(p->stat_out.alloc(P * 2));
   CK(p->intr_dev.alloc(P * p->D)); CK(p->ya_dev.alloc(P * p->D)); CK(p->u_dev.alloc(P)); CK(p->scale_dev.alloc(P * p->D));
   CK(p->mask_dev.alloc(P));
-  CK(p->h_red.alloc(2 * (P * p->NRED + 1))); CK(p->h_stat.alloc(P * 2 + 2));
+  CK(p->h_red.alloc(2 * (P * p->NRED + 1))); CK(p->h_stat.alloc(P * 2 + 2)); CK(p->h_colsq.alloc(P * p->D));
   p->h_red.p[p->NRED] = -1.0; p->h_stat.p[2] = -1.0; p->h_stat.p[3] = -1.0;
   CK(cudaMemsetAsync(p->cur.p, 0, P * sizeof(int32_t), s));
   CK(cudaMemsetAsync(p->u_dev.p, 0, P * sizeof(double), s));
@@ -784,7 +785,7 @@ int ccrs_problem_destroy(ccrs_problem* p) {
   p->elim.release(); p->frame_red.release(); p->pose_scale.release(); p->frame_md.release(); p->cta_part.release();
   p->red_out.release(); p->stat_out.release(); p->gather.release(); p->intr_dev.release(); p->ya_dev.release();
   p->u_dev.release(); p->scale_dev.release(); p->l2_flush.release(); p->mask_dev.release();
-  p->h_red.release(); p->h_stat.release();
+  p->h_red.release(); p->h_stat.release(); p->h_colsq.release();
   if (p->stream) put_stream(p->device, p->stream);
   delete p;
   return 0;
@@ -1019,6 +1020,17 @@ int ccrs_compute_scale(ccrs_problem* p, int which, double* col_sq) {
   // frame_red is free between reduce() calls: use it for the per-frame A_aa diagonals [D][Fs]
   CK(launch_compute_scale(p->D, p->dev(), which, p->pose_scale.p, p->frame_red.p, p->stream));
   p->launches++;
+  if (!p->batch && !p->comm) {
+    // single problem, single GPU: the frame-order sums go straight to mapped host memory (armed words, no memcpy, no
+    // stream synchronise) like every other per-iteration result
+    arm_payload(p->h_colsq.p, p->D);
+    CK(launch_segreduce(p->frame_red.p, p->D, p->Fs, p->problem_frame_offsets.p, 1, p->h_colsq.p, p->stream));
+    p->launches++;
+    int st1 = wait_payload(p, p->h_colsq.p, p->D);
+    if (st1) return st1;
+    for (int i = 0; i < p->D; ++i) col_sq[i] = p->h_colsq.p[i];
+    return 0;
+  }
   int st = reduce_frames(p, p->frame_red.p, p->D, p->red_out.p);
   if (st) return st;
   st = exchange(p, p->red_out.p, (size_t)p->n_problems * p->D, nullptr, 0.0);
