@@ -2,22 +2,29 @@
 """bench.py — BASELINE.json's metric on its quoted configuration.
 
 metric   : residual+Jacobian evals/s (and LM iterations/s) at ~1M corner observations, EUCM
-workload : configs[3] — EUCM, 7,000 frames x 144 corners (1,007,999 obs after the image-bounds filter) PER GPU,
-           synthetic (SURVEY.md §8(d) generator, seed 3), frames sharded across ranks, one exchange of the reduced
-           intrinsic system per linearisation (fused into K3/K2: peer-memory stores over NVLink + rank-order sum in
-           the kernel's last CTA; NCCL all-gather + rank-order sum when peer memory is unavailable). Weak scaling: every
-           rank owns 7,000 frames, the job is one calibration problem of N x 7,000 frames.
-step     : one Levenberg-Marquardt iteration of that problem = K3 reduce (+exchange) -> host d x d solve -> K4
-           back-substitution -> K2 linearisation of the trial point (speculative LM: the trial cost comes from the
-           linearisation itself) -> exchange of (model decrease, cost) -> accept/reject. Stop tests are disabled so
-           each of the K timed steps does the full work; every step evaluates residual+Jacobian once per observation.
-           Every 4 steps the state returns (untimed) to the perturbed start, so the timed steps are LM iterations 1-4
-           of the problem (iteration 1 has the Huber loss active on ~99% of the observations).
+workload : configs[3] — ONE EUCM calibration problem of 7,000 frames x 144 corners (1,007,999 obs after the
+           image-bounds filter), synthetic (SURVEY.md §8(d) generator, seed 3). At N > 1 the SAME problem is
+           frame-sharded over the N ranks ("scaling": "strong", 7000/N frames per GPU), one exchange of the reduced
+           intrinsic system per linearisation (fused into the kernels over peer memory; NCCL all-gather + rank-order
+           sum when peer memory is unavailable). The weak-scaling figure of round 1 (7,000 frames PER GPU) is kept as
+           the extra key `weak_scaling`.
+step     : one Levenberg-Marquardt iteration of that problem = reduce (+exchange) -> d x d solve -> pose
+           back-substitution -> linearisation of the trial point (speculative LM: the trial cost comes from the
+           linearisation itself) -> accept/reject. Stop tests are disabled so each of the K timed steps does the full
+           work; every step evaluates residual+Jacobian once per observation. Every 4 steps the state returns
+           (untimed) to the perturbed start, so the timed steps are LM iterations 1-4 of the problem (iteration 1
+           has the Huber loss active on ~99% of the observations).
 value    : total observations over all ranks / time per step, inputs resident in HBM, L2 flushed (512 MB write)
            before every timed step outside the CUDA-event bracket; max over ranks.
 e2e      : the same metric through the C-ABI entry point a user calls with HOST buffers: per step one complete
-           ccrs_problem_create_f32 (H2D of the f32 observation arrays from pinned memory) + ccrs_set_poses + ccrs_solve_lm
-           to convergence + ccrs_get_poses (D2H) + destroy; evals = observations x linearisations performed.
+           ccrs_problem_create_f32 (H2D of the f32 observation arrays from pinned memory) + ccrs_set_poses +
+           ccrs_solve_lm to convergence + ccrs_get_poses (D2H) + destroy; evals = observations x linearisations.
+multi_gpu_check (N > 1, same run): intrinsics bitwise-identical across ranks, equal iteration count and <= 1e-6
+           relative difference against a single-rank solve of the same problem on rank 0 — for the peer-memory
+           exchange AND for CCRS_P2P=0 (NCCL all-gather + rank-order sum).
+batch    : BASELINE configs[4] — independent KB4 calibrations (200 frames each), 512 problems per rank, no
+           communication (4,096 problems at N = 8). Extra key `batch` of the default line; `--workload batch` prints
+           it as a line of its own.
 
 `--impl reference` times the reference arm: the CPU oracle (oracle/, a restatement of the reference's num-dual +
 tiny-solver path: the Rust reference cannot be built here) running the same LM iteration on the host cores.
@@ -25,6 +32,7 @@ tiny-solver path: the Rust reference cannot be built here) running the same LM i
 from __future__ import annotations
 
 import argparse
+import hashlib
 import importlib
 import json
 import os
@@ -38,14 +46,39 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "EUCM 7000 frames x 144 corners per GPU (~1.008M obs/GPU), 1024x1024, synthetic seed 3, Huber(1.0), LM iteration"
-METRIC = "residual+Jacobian evals/s at 1M corner obs (EUCM LM iteration)"
-FRAMES_PER_GPU = 7000
+FRAMES_TOTAL = 7000
 MODEL = "eucm"
+WORKLOAD = ("EUCM, one calibration problem of 7000 frames x 144 corners (~1.008M obs), 1024x1024, synthetic seed 3, "
+            "Huber(1.0), LM iteration; frame-sharded over the GPUs")
+METRIC = "residual+Jacobian evals/s at 1M corner obs (EUCM LM iteration)"
+BATCH_PER_RANK = 512
+BATCH_FRAMES = 200
+BATCH_MODEL = "kb4"
+# FP64 work per observation of K2: SURVEY §8(d)'s nominal figure and the count from the kernel's SASS
+FLOP_PER_OBS_NOMINAL = 560.0
+FLOP_PER_OBS_COUNTED = 382.0
 
 
 def load_pkg():
     return importlib.import_module("camera-intrinsic-calibration-rs_b200")
+
+
+def workload_config(n_total: int):
+    """Identical in both arms (ours / reference): only what defines the workload."""
+    return {"workload": WORKLOAD, "camera_model": MODEL, "frames_total": FRAMES_TOTAL, "obs_total": int(n_total),
+            "seed": 3, "loop": "LM iteration (speculative: trial cost from the trial linearisation)",
+            "l2": "GPU arm: flushed (512 MB write) before every timed step, outside the event bracket"}
+
+
+def kernel_source_hash() -> str:
+    """sha256 over the kernel sources: ties profiles/k2_dram_bytes_per_launch.json to the build that ran."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "camera-intrinsic-calibration-rs_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh")):
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def measured_peaks():
@@ -75,7 +108,6 @@ class ClockSampler:
             t0 = time.time()
             while not self.rows and time.time() - t0 < 3.0:   # nvidia-smi needs ~0.5 s to produce its first row
                 time.sleep(0.01)
-            self.n_before = len(self.rows)
         except Exception:
             self.proc = None
 
@@ -115,92 +147,276 @@ def pinned(a: np.ndarray):
     return n, t
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    pkg = load_pkg()
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    dev = local
+class Ranks:
+    """torch.distributed plumbing: barrier, max over ranks, gather of small arrays."""
 
-    # ---- synthetic problem: N x 7000 frames, this rank's contiguous shard -------------------------------
-    s = pkg.synth.make_calib(MODEL, FRAMES_PER_GPU * world, seed=3)
-    lo, hi = pkg.dist.shard_frames(s.frame_offsets, rank, world)
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0")); self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+        torch.cuda.set_device(self.local)
+        self.dev = self.local
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max(self, x: float) -> float:
+        if not self.dist:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=f"cuda:{self.dev}")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, x: float) -> float:
+        if not self.dist:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=f"cuda:{self.dev}")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def gather_bits(self, a: np.ndarray) -> np.ndarray:
+        """[world, len(a)] int64 bit patterns of a float64 vector from every rank."""
+        bits = np.ascontiguousarray(a, dtype=np.float64).view(np.int64)
+        if not self.dist:
+            return bits[None, :].copy()
+        t = self.torch.from_numpy(bits.copy()).to(f"cuda:{self.dev}")
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return np.stack([o.cpu().numpy() for o in out])
+
+    def finish(self):
+        if self.dist:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def timed_lm_steps(R: Ranks, prob, intr0, poses0, steps, warmup, n_total, flush_l2=True):
+    R.barrier()
+    step_ms, launches = prob.bench_lm_steps(intr0, poses0, warmup=warmup, steps=steps, flush_l2=flush_l2)
+    R.barrier()
+    ms = R.max(float(step_ms.sum())) / steps
+    return ms, n_total / (ms * 1e-3), launches
+
+
+def sharded_problem(pkg, R: Ranks, s, model=MODEL):
+    lo, hi = pkg.dist.shard_frames(s.frame_offsets, R.rank, R.world)
     sh = pkg.dist.slice_problem(s, lo, hi)
+    prob = pkg.Problem(model, s.width, s.height, sh["frame_offsets"], sh["x"], sh["y"], sh["z"], sh["u"], sh["v"], device=R.dev)
+    return prob, sh, lo, hi
+
+
+def multi_gpu_check(pkg, R: Ranks, s):
+    """Same run, same problem: every rank's converged intrinsics bitwise identical, equal iteration count and
+    <= 1e-6 relative difference vs a single-rank solve on rank 0 — peer-memory exchange, then CCRS_P2P=0 (NCCL)."""
+    out = {"ok": True, "tolerance_rel": 1e-6, "modes": {}}
+    ref = {}
+    if R.rank == 0:     # single-rank solves of the whole problem (no communicator attached)
+        q = pkg.Problem.from_synth(s, device=R.dev)
+        for loop in ("lm", "gn"):
+            q.set_poses(s.init_poses)
+            intr, summ, _ = (q.solve_lm if loop == "lm" else q.solve_gn)(s.init_params)
+            ref[loop] = (intr.copy(), int(summ.iterations), int(summ.status))
+        q.close()
+    for mode in ("peer", "nccl"):
+        os.environ["CCRS_P2P"] = "1" if mode == "peer" else "0"
+        prob, sh, lo, hi = sharded_problem(pkg, R, s)
+        pkg.dist.init_comm(prob, R.rank, R.world)        # new communicator: peer setup honours CCRS_P2P
+        uses_peer = int(pkg._abi.load().ccrs_comm_uses_peer_memory())
+        res = {"uses_peer_memory": uses_peer}
+        for loop in (("lm", "gn") if mode == "peer" else ("lm",)):
+            prob.set_poses(s.init_poses[lo:hi])
+            intr, summ, _ = (prob.solve_lm if loop == "lm" else prob.solve_gn)(s.init_params)
+            bits = R.gather_bits(intr)
+            iters = R.gather_bits(np.array([float(summ.iterations), float(summ.status)]))
+            bitwise = bool(np.all(bits == bits[0:1]))
+            same_iters = bool(np.all(iters == iters[0:1]))
+            r = {"bitwise_identical_across_ranks": bitwise, "iterations": int(summ.iterations), "same_iterations_on_all_ranks": same_iters,
+                 "status": int(summ.status)}
+            if R.rank == 0:
+                ri, rit, rst = ref[loop]
+                r["iterations_single_rank"] = rit
+                r["max_rel_diff_vs_single_rank"] = float(np.max(np.abs(intr - ri) / np.abs(ri)))
+                r["ok"] = bool(bitwise and same_iters and rit == int(summ.iterations) and summ.status == 0 and rst == 0 and
+                               r["max_rel_diff_vs_single_rank"] <= 1e-6)
+            else:
+                r["ok"] = bool(bitwise and same_iters)
+            res[loop] = r
+        expect_peer = 1 if mode == "peer" else 0
+        res["ok"] = all(res[k]["ok"] for k in res if isinstance(res[k], dict)) and (mode == "peer" or uses_peer == expect_peer)
+        out["modes"][mode] = res
+        prob.close()
+    os.environ["CCRS_P2P"] = "1"
+    ok = R.sum(0.0 if all(m["ok"] for m in out["modes"].values()) else 1.0) == 0.0
+    out["ok"] = bool(ok)
+    return out
+
+
+def make_batch(pkg, n_problems: int, first: int = 0, n_distinct: int = 16):
+    """n_problems independent KB4 calibrations (200 frames each) concatenated; 16 distinct synthetic problems tiled."""
+    probs = [pkg.synth.make_calib(BATCH_MODEL, BATCH_FRAMES, seed=100 + i) for i in range(n_distinct)]
+    fo, pfo = [np.zeros(1, dtype=np.int64)], [0]
+    xs, ys, zs, us, vs, poses, intr0 = [], [], [], [], [], [], []
+    for b in range(first, first + n_problems):
+        s = probs[b % n_distinct]
+        fo.append(fo[-1][-1] + s.frame_offsets[1:].astype(np.int64))
+        pfo.append(pfo[-1] + s.n_frames)
+        xs.append(s.x); ys.append(s.y); zs.append(s.z); us.append(s.u); vs.append(s.v)
+        poses.append(s.init_poses); intr0.append(s.init_params)
+    cat = np.concatenate
+    return dict(fo=cat(fo).astype(np.int32), pfo=np.array(pfo, dtype=np.int32), x=cat(xs), y=cat(ys), z=cat(zs), u=cat(us),
+                v=cat(vs), poses=cat(poses), intr0=np.stack(intr0), probs=probs)
+
+
+def bench_batch(pkg, R: Ranks, steps: int, warmup: int):
+    """configs[4]: BATCH_PER_RANK independent KB4 calibrations per rank, no communication. A step = one LM solve of
+    the rank's batch to convergence (poses reset untimed)."""
+    b = make_batch(pkg, BATCH_PER_RANK, first=R.rank * BATCH_PER_RANK)
+    t0 = time.perf_counter()
+    gp = pkg.Problem(BATCH_MODEL, 1024, 1024, b["fo"], b["x"], b["y"], b["z"], b["u"], b["v"], problem_frame_offsets=b["pfo"], device=R.dev)
+    create_s = time.perf_counter() - t0
+    n_obs = int(gp.n_obs)
+    dev_ms, wall_ms, n_lin = [], [], 0
+    launches0 = 0
+    for i in range(warmup + steps):
+        gp.set_poses(b["poses"])
+        R.barrier()
+        if i == warmup:
+            launches0 = gp.launch_count()
+        t0 = time.perf_counter()
+        intr, summ, _ = gp.solve_lm(b["intr0"])
+        w = (time.perf_counter() - t0) * 1e3
+        if i >= warmup:
+            dev_ms.append(summ.device_ms); wall_ms.append(w)
+            n_lin = summ.iterations + 1
+    launches = gp.launch_count() - launches0
+    # a sample of problems against solving them on their own
+    worst = 0.0
+    for k in (0, 5, BATCH_PER_RANK - 1):
+        s = b["probs"][(R.rank * BATCH_PER_RANK + k) % len(b["probs"])]
+        q = pkg.Problem.from_synth(s, device=R.dev)
+        q.set_poses(s.init_poses)
+        ref, _, _ = q.solve_lm(s.init_params)
+        worst = max(worst, float(np.max(np.abs(intr[k] - ref) / np.abs(ref))))
+        q.close()
+    gp.close()
+    ms = R.max(float(np.median(dev_ms)))
+    wall = R.max(float(np.median(wall_ms)))
+    total_obs = R.sum(float(n_obs))
+    return {"workload": f"{BATCH_PER_RANK * R.world} independent {BATCH_MODEL.upper()} calibrations x {BATCH_FRAMES} frames x 144 corners, "
+                        f"{BATCH_PER_RANK} per GPU, no communication (BASELINE configs[4])",
+            "n_gpus": R.world, "problems": BATCH_PER_RANK * R.world, "obs_total": int(total_obs),
+            "lm_iterations_max": int(n_lin - 1), "linearisations": int(n_lin),
+            "ms_per_batch_solve": ms, "wall_ms_per_batch_solve": wall,
+            "evals_per_s": total_obs * n_lin / (ms * 1e-3), "calibrations_per_s": BATCH_PER_RANK * R.world / (ms * 1e-3),
+            "evals_per_s_wall": total_obs * n_lin / (wall * 1e-3), "gpu_launches": int(launches),
+            "max_rel_diff_vs_standalone_solve": R.max(worst), "create_s": create_s, "scaling": "weak (512 problems per GPU)"}
+
+
+def run_ours(args):
+    pkg = load_pkg()
+    R = Ranks()
+    rank, world, dev = R.rank, R.world, R.dev
+
+    if args.workload == "batch":
+        sampler = ClockSampler(dev)
+        if rank == 0:
+            sampler.start()
+        bt = bench_batch(pkg, R, steps=max(3, min(args.steps, 5)), warmup=1)
+        clocks = sampler.stop() if rank == 0 else None
+        if rank == 0:
+            print(json.dumps({"metric": "residual+Jacobian evals/s, batch of independent KB4 calibrations", "value": bt["evals_per_s"],
+                              "unit": "evals/s", "n_gpus": world, "steps": max(3, min(args.steps, 5)), "warmup": 1,
+                              "ms_per_step": bt["ms_per_batch_solve"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                              "dtype": "f64", "data": "synthetic", "impl": "ours", "config": {"workload": bt["workload"]},
+                              "batch": bt, "gpu_launches": bt["gpu_launches"], "clocks": clocks}))
+        R.finish()
+        return
+
+    # ---- the problem: 7000 frames in total, this rank's contiguous shard (strong scaling) ----------------------
+    s = pkg.synth.make_calib(MODEL, FRAMES_TOTAL, seed=3)
+    prob, sh, lo, hi = sharded_problem(pkg, R, s)
     poses0 = np.ascontiguousarray(s.init_poses[lo:hi])
     n_local = int(sh["frame_offsets"][-1]); n_total = s.n_obs
-    prob = pkg.Problem(MODEL, s.width, s.height, sh["frame_offsets"], sh["x"], sh["y"], sh["z"], sh["u"], sh["v"], device=dev)
     pkg.dist.init_comm(prob, rank, world)
     d = prob.d
-    exch = "none (single GPU)" if world == 1 else ("fused into K2/K3 over peer memory (NVLink P2P stores, rank-order sum)" if pkg._abi.load().ccrs_comm_uses_peer_memory()
-                                                 else "NCCL all-gather + rank-order sum")
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{dev}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    exch = "none (single GPU)" if world == 1 else ("fused into the kernels over peer memory (NVLink P2P stores, rank-order sum)"
+                                                 if pkg._abi.load().ccrs_comm_uses_peer_memory() else "NCCL all-gather + rank-order sum")
 
     # ---- device-resident steps (value) --------------------------------------------------------------------
     sampler = ClockSampler(dev)
-    barrier()
+    R.barrier()
     if rank == 0:
         sampler.start()
     t_wall0 = time.perf_counter()
-    step_ms, launches = prob.bench_lm_steps(s.init_params, poses0, warmup=args.warmup, steps=args.steps, flush_l2=True)
-    barrier()
+    ms_per_step, value, launches = timed_lm_steps(R, prob, s.init_params, poses0, args.steps, args.warmup, n_total, flush_l2=True)
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = max_over_ranks(float(step_ms.sum()))
-    ms_per_step = total_ms / args.steps
-    value = n_total / (ms_per_step * 1e-3)
 
     # L2-warm variant (what a real LM loop sees: the observation arrays stay L2-resident between iterations)
-    barrier()
-    warm_ms, _ = prob.bench_lm_steps(s.init_params, poses0, warmup=args.warmup, steps=args.steps, flush_l2=False)
-    warm_ms_per_step = max_over_ranks(float(warm_ms.sum())) / args.steps
+    warm_ms_per_step, warm_value, _ = timed_lm_steps(R, prob, s.init_params, poses0, args.steps, args.warmup, n_total, flush_l2=False)
 
-    # ---- the LM loop as a caller runs it: no synchronisation or flush between iterations, so the speculative K3 launch
-    #      overlaps the host's bookkeeping (the per-step figure above isolates every iteration between stream syncs)
+    # ---- the LM loop as a caller runs it: no synchronisation or flush between iterations
     prob.set_poses(poses0)
     o = pkg.default_options(max_iteration=40, min_abs_decrease=-1.0, min_rel_decrease=-1.0, min_error=-1.0)
     _, loop_summ, _ = prob.solve_lm(s.init_params, options=o)
-    loop_ms = max_over_ranks(loop_summ.device_ms) / max(loop_summ.iterations, 1)
+    loop_ms = R.max(loop_summ.device_ms) / max(loop_summ.iterations, 1)
+    # ... and the loop the reference actually runs (Gauss-Newton, src/util.rs:443-458)
+    prob.set_poses(poses0)
+    _, gn_summ, _ = prob.solve_gn(s.init_params, options=pkg.default_options(max_iteration=20, min_abs_decrease=-1.0, min_rel_decrease=-1.0, min_error=-1.0))
+    gn_ms = R.max(gn_summ.device_ms) / max(gn_summ.iterations, 1)
 
     # ---- dominant kernel K2 alone, timed live with CUDA events on the handle's stream ------------------
     prob.set_poses(poses0)
-    k2_ms = prob.time_linearize(s.init_params, reps=max(10, args.steps), flush_l2=True)
-    k2_ms_warm = prob.time_linearize(s.init_params, reps=max(10, args.steps), flush_l2=False)
+    k2_ms = R.max(prob.time_linearize(s.init_params, reps=max(10, args.steps), flush_l2=True))
+    k2_ms_warm = R.max(prob.time_linearize(s.init_params, reps=max(10, args.steps), flush_l2=False))
     peaks, peak_kind = measured_peaks()
     nblk = prob.nblk
     bytes_per_obs = 40.0 + (48.0 + 8.0 * nblk) / 144.0            # SURVEY §8(d): B_obs = 40 + (48 + 8 n_blk)/144
-    flop_per_obs = 560.0                                           # 360 (normal equations) + ~200 (model)
-    achieved_gbs = bytes_per_obs * n_local / (k2_ms * 1e-3) / 1e9
+    n_k2 = R.max(float(n_local))                                   # observations of the launch that was timed (largest shard)
+    achieved_gbs = bytes_per_obs * n_k2 / (k2_ms * 1e-3) / 1e9
     fp64_peak = pkg.measure_fp64_peak(dev)
-    achieved_tf = flop_per_obs * n_local / (k2_ms * 1e-3) / 1e12
-    roofline = {"kernel": "k_linearize<EUCM> (K2)", "bound": "hbm", "achieved": round(achieved_gbs, 1), "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": round(achieved_gbs / peaks["hbm_gbs"], 4), "traffic": None, "peak_source": f"{peak_kind} MEASURED_PEAKS.json hbm_gbs",
-                "k2_ms": round(k2_ms, 5), "k2_ms_l2_warm": round(k2_ms_warm, 5), "bytes_per_obs": round(bytes_per_obs, 2),
-                "note": "K2 is FP64-CUDA-core-bound by design (no dense contraction, no tensor cores): see fp64",
-                "fp64": {"achieved": round(achieved_tf, 2), "peak": round(fp64_peak, 2), "unit": "TFLOP/s",
-                         "frac": round(achieved_tf / fp64_peak, 4), "flop_per_obs": flop_per_obs,
-                         "peak_source": "ccrs_measure_fp64_peak DFMA microbenchmark, same run"}}
+    tf_nominal = FLOP_PER_OBS_NOMINAL * n_k2 / (k2_ms * 1e-3) / 1e12
+    tf_counted = FLOP_PER_OBS_COUNTED * n_k2 / (k2_ms * 1e-3) / 1e12
+    roofline = {"kernel": "k_linearize<EUCM> (K2)", "bound": "fp64", "achieved": round(tf_nominal, 2), "peak": round(fp64_peak, 2),
+                "unit": "TFLOP/s", "frac": round(tf_nominal / fp64_peak, 4), "traffic": None,
+                "flop_per_obs": FLOP_PER_OBS_NOMINAL, "flop_source": "SURVEY §8(d) nominal: 360 normal-equation + ~200 model",
+                "peak_source": "ccrs_measure_fp64_peak DFMA microbenchmark in this run (MEASURED_PEAKS.json has no FP64 entry; datasheet 37)",
+                "counted": {"flop_per_obs": FLOP_PER_OBS_COUNTED, "achieved": round(tf_counted, 2), "frac": round(tf_counted / fp64_peak, 4),
+                            "what": "FP64 instructions counted in the kernel's SASS (DFMA=2, DMUL/DADD=1), DESIGN §3"},
+                "k2_ms": round(k2_ms, 5), "k2_ms_l2_warm": round(k2_ms_warm, 5), "obs_per_launch": int(n_k2),
+                "hbm": {"achieved": round(achieved_gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(achieved_gbs / peaks["hbm_gbs"], 4),
+                        "bytes_per_obs": round(bytes_per_obs, 2), "peak_source": f"{peak_kind} MEASURED_PEAKS.json hbm_gbs (burst: kernel timed alone)"},
+                "note": "K2 is FP64-CUDA-core-bound (no dense contraction, no tensor cores); the HBM fraction is secondary"}
     traffic_file = os.path.join(ROOT, "profiles", "k2_dram_bytes_per_launch.json")
-    if os.path.exists(traffic_file):
+    if os.path.exists(traffic_file) and world == 1:
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get("bytes_per_launch")
+            tj = json.load(open(traffic_file))
+            if tj.get("kernel_src_sha256") == kernel_source_hash():     # only for the kernel build that was profiled
+                roofline["traffic"] = tj.get("bytes_per_launch")
+            else:
+                roofline["traffic_note"] = "ncu capture is of another kernel build (source hash differs): not reported"
         except Exception:
             pass
+
+    # ---- weak-scaling figure (7000 frames PER GPU, one problem of N x 7000 frames) ------------------------------
+    weak = None
+    if world > 1 and not args.no_weak:
+        sw = pkg.synth.make_calib(MODEL, FRAMES_TOTAL * world, seed=3)
+        pw, shw, low, hiw = sharded_problem(pkg, R, sw)
+        pw.comm_init(None)
+        w_ms, w_value, _ = timed_lm_steps(R, pw, sw.init_params, np.ascontiguousarray(sw.init_poses[low:hiw]), args.steps, args.warmup, sw.n_obs, flush_l2=True)
+        weak = {"frames_per_gpu": FRAMES_TOTAL, "obs_total": int(sw.n_obs), "ms_per_step": w_ms, "value": w_value, "lm_iterations_per_s": 1e3 / w_ms}
+        pw.close()
+        del sw, shw
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------------------
     # the reference's FeaturePoint holds f32 (src/detected_points.rs:6-9): the f32 entry point is the natural host format
@@ -213,7 +429,7 @@ def run_ours(args):
     evals = 0
     e2e_times = []
     for i in range(2 + e2e_steps):
-        barrier()
+        R.barrier()
         t0 = time.perf_counter()
         q = pkg.Problem(MODEL, s.width, s.height, hfo, hx, hy, hz, hu, hv, device=dev)
         if world > 1:
@@ -224,32 +440,42 @@ def run_ours(args):
         n_lin = 1 + summ.iterations          # initial linearisation + one (speculative) per iteration
         d2h_iter = summ.iterations * (prob.nout + 2) * 8
         q.close()
-        barrier()
+        R.barrier()
         if i >= 2:
             e2e_times.append(time.perf_counter() - t0)
             evals += n_total * n_lin
-    e2e_total = max_over_ranks(float(np.sum(e2e_times)))
+    e2e_total = R.max(float(np.sum(e2e_times)))
     e2e_value = evals / e2e_total
     rel_err = float(np.max(np.abs(intr - s.gt_params) / np.abs(s.gt_params)))
+    prob.close()
+
+    # ---- batch of independent KB4 calibrations (configs[4]), 512 per rank -------------------------------------
+    batch = None
+    if not args.no_batch:
+        batch = bench_batch(pkg, R, steps=3, warmup=1)
+
+    # ---- multi-GPU correctness in the same run ------------------------------------------------------------------
+    check = multi_gpu_check(pkg, R, s) if world > 1 else None
 
     # ---- CPU baseline (oracle port, bounded sample) on rank 0 at N=1 ---------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_lm_iteration_rate(pkg, s, sample_frames=FRAMES_PER_GPU, iters=2)
+        cpu = cpu_lm_iteration_rate(pkg, s, sample_frames=FRAMES_TOTAL, iters=3, solves=5)
 
     if rank == 0:
+        cfg = workload_config(n_total)
         line = {
             "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "impl": "ours",
-            "config": {"workload": WORKLOAD, "camera_model": MODEL, "frames_per_gpu": FRAMES_PER_GPU, "obs_total": int(n_total),
-                       "obs_per_gpu": int(n_local), "parallelism": f"frame-sharded x{world}", "exchange": exch,
-                       "l2": "flushed (512 MB write) before every timed step, outside the event bracket", "loop": "speculative LM"},
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "ours", "config": cfg,
+            "run": {"frames_per_gpu": int(hi - lo), "obs_per_gpu": int(n_local), "parallelism": f"frame-sharded x{world}", "exchange": exch},
             "lm_iterations_per_s": 1e3 / ms_per_step,
-            "l2_warm": {"ms_per_step": warm_ms_per_step, "value": n_total / (warm_ms_per_step * 1e-3), "lm_iterations_per_s": 1e3 / warm_ms_per_step},
+            "l2_warm": {"ms_per_step": warm_ms_per_step, "value": warm_value, "lm_iterations_per_s": 1e3 / warm_ms_per_step},
             "lm_loop_l2_warm": {"ms_per_iteration": loop_ms, "iterations": int(loop_summ.iterations), "lm_iterations_per_s": 1e3 / loop_ms,
                                 "value": n_total / (loop_ms * 1e-3),
                                 "what": "ccrs_solve_lm with the stop tests disabled, 40 back-to-back iterations incl. the initial linearisation and Jacobi scaling, CUDA events around the whole loop"},
+            "gn_loop_l2_warm": {"ms_per_iteration": gn_ms, "iterations": int(gn_summ.iterations),
+                                "what": "ccrs_solve_gn (the loop the reference runs, util.rs:443-458), stop tests disabled, 20 iterations, CUDA events around the whole loop"},
             "wall_ms_timed_region_incl_flush": wall_ms,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h + d2h_iter),
                     "ms_per_call": e2e_total / e2e_steps * 1e3, "lm_iterations_per_call": int(summ.iterations),
@@ -257,15 +483,19 @@ def run_ours(args):
                     "converged_rel_err_vs_gt": rel_err},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         }
+        if weak is not None:
+            line["weak_scaling"] = weak
+        if batch is not None:
+            line["batch"] = batch
+        if check is not None:
+            line["multi_gpu_check"] = check
         print(json.dumps(line))
-    prob.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    R.finish()
 
 
-def cpu_lm_iteration_rate(pkg, s, sample_frames: int, iters: int, threads: int | None = None):
-    """Oracle LM iterations on the host cores: the reference arm / cpu_baseline. Returns the cpu_baseline object."""
+def cpu_lm_iteration_rate(pkg, s, sample_frames: int, iters: int, solves: int = 5, threads: int | None = None):
+    """Oracle LM iterations on the host cores: the reference arm / cpu_baseline. Median over `solves` solves of `iters`
+    LM iterations each (after one warm-up solve). Returns the cpu_baseline object."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
     threads = threads or (os.cpu_count() or 1)
@@ -277,40 +507,37 @@ def cpu_lm_iteration_rate(pkg, s, sample_frames: int, iters: int, threads: int |
     opt = op.default_options(max_iteration=1, min_abs_decrease=-1.0, min_rel_decrease=-1.0, min_error=-1.0)
     op.levenberg_marquardt(s.init_params, poses, options=opt)          # warm-up (thread pool, page faults)
     opt = op.default_options(max_iteration=iters, min_abs_decrease=-1.0, min_rel_decrease=-1.0, min_error=-1.0)
-    t0 = time.perf_counter()
-    _, _, res, _ = op.levenberg_marquardt(s.init_params, poses, options=opt)
-    dt = time.perf_counter() - t0
-    # one oracle LM iteration = one dual-number linearisation + one residual-only pass; the initial cost pass is amortised
-    per_iter = dt / res.iterations
-    return {"value": n / per_iter, "unit": "evals/s", "cores": threads, "kind": "port",
-            "sample": f"{res.iterations} LM iterations of the same EUCM problem restricted to {sample_frames} frames ({n} obs), OpenMP {threads} threads",
-            "ms_per_lm_iteration": per_iter * 1e3, "lm_iterations_per_s": 1.0 / per_iter}
+    per_iter = []
+    for _ in range(solves):
+        t0 = time.perf_counter()
+        _, _, res, _ = op.levenberg_marquardt(s.init_params, poses, options=opt)
+        # one oracle LM iteration = one dual-number linearisation + one residual-only pass; the initial cost pass is amortised
+        per_iter.append((time.perf_counter() - t0) / res.iterations)
+    med = float(np.median(per_iter))
+    return {"value": n / med, "unit": "evals/s", "cores": threads, "kind": "port",
+            "sample": f"median of {solves} solves x {iters} LM iterations of the same EUCM problem restricted to {sample_frames} frames ({n} obs), OpenMP {threads} threads",
+            "ms_per_lm_iteration": med * 1e3, "ms_per_lm_iteration_min_max": [float(np.min(per_iter)) * 1e3, float(np.max(per_iter)) * 1e3],
+            "lm_iterations_per_s": 1.0 / med}
 
 
 def run_reference(args):
     """Reference arm: the reference's own algorithm for this path on the host cores. The Rust reference cannot be
     compiled here (no cargo/rustc; tiny-solver / camera-intrinsic-model / num-dual are not vendored), so this is the
-    oracle port (oracle/ccrs_oracle.cpp: dual-number autodiff + Huber corrector + Cholesky), all host threads."""
+    oracle port (oracle/ccrs_oracle.cpp: dual-number autodiff + Huber corrector + Cholesky), all host threads.
+    A step = one LM iteration (each timed solve runs 3 of them); the problem is the whole 7000-frame problem at every N."""
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     pkg = load_pkg()
-    s = pkg.synth.make_calib(MODEL, FRAMES_PER_GPU, seed=3)
-    times, base = [], None
-    for i in range(args.warmup + args.steps):
-        base = cpu_lm_iteration_rate(pkg, s, sample_frames=FRAMES_PER_GPU, iters=1)
-        if i >= args.warmup:
-            times.append(base["ms_per_lm_iteration"])
-    ms = float(np.mean(times))
+    s = pkg.synth.make_calib(MODEL, FRAMES_TOTAL, seed=3)
+    base = cpu_lm_iteration_rate(pkg, s, sample_frames=FRAMES_TOTAL, iters=3, solves=max(5, args.steps))
+    ms = base["ms_per_lm_iteration"]
     n = s.n_obs
     value = n / (ms * 1e-3)
-    base.update({"value": value, "ms_per_lm_iteration": ms, "lm_iterations_per_s": 1e3 / ms})
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "impl": "reference",
-        "config": {"workload": WORKLOAD, "camera_model": MODEL, "frames_per_gpu": FRAMES_PER_GPU, "obs_total": int(n),
-                   "note": "CPU arm runs ONE rank's 7000-frame problem on the host cores regardless of N"},
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "impl": "reference", "config": workload_config(n),
         "lm_iterations_per_s": 1e3 / ms, "cpu_baseline": base,
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -322,7 +549,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="lm", choices=["lm", "batch"], help="lm: configs[3] (headline); batch: configs[4] as a line of its own")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-batch", action="store_true", help="skip the batch (configs[4]) extra key")
+    ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling extra key at N > 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
