@@ -119,6 +119,10 @@ class Problem:
             self.h = None
 
     def __del__(self):
+        # never call into CUDA while the interpreter is shutting down (the runtime may already be tearing down)
+        import sys
+        if sys is None or sys.is_finalizing():
+            return
         try:
             self.close()
         except Exception:
@@ -468,6 +472,9 @@ class JointProblem:
             self.h = None
 
     def __del__(self):
+        import sys
+        if sys is None or sys.is_finalizing():
+            return
         try:
             self.close()
         except Exception:

@@ -2,6 +2,7 @@
 // the CUDA implementation of ccrs_backend, NCCL exchange of the reduced system, calib_camera entry point.
 #include "../../include/ccrs_b200.h"
 #include "ccrs_kernels.cuh"
+#include "ccrs_rule.h"
 
 #include <algorithm>
 #include <cmath>
@@ -64,13 +65,17 @@ struct GlobalComm { ncclComm_t comm = nullptr; int rank = 0, world = 1; } g_comm
 // cudaMalloc'd (not pooled: it is exported with cudaIpcGetMemHandle), armed, and every other rank's buffer opened with
 // cudaIpcOpenMemHandle. Areas: 0 = K3 reduced system, 1 = K2 {model decrease, cost}. Exchanges alternate parity per area
 // (all ranks issue the same sequence), so a rank that races ahead never overwrites a slot its peer has not consumed.
-constexpr int kXchgAreas = 2;
+constexpr int kXchgAreas = 3;   // 0: host-driven K3, 1: host-driven K2 statistics, 2: K3 of the device-driven loop
 struct GlobalPeer {
   bool ok = false;
   double* local = nullptr;
   double* peer[kXchgMaxRanks] = {};
   unsigned long count[kXchgAreas] = {};
+  // area 2 alternates its slot parity on a DEVICE-side count of executed exchanges (slots of the device-driven loop
+  // that find nothing to do exchange nothing): one 8-byte word behind the slot areas of the local buffer
+  unsigned int* dev_count() const { return reinterpret_cast<unsigned int*>(local + doubles()); }
   size_t doubles() const { return (size_t)kXchgAreas * 2 * kXchgMaxRanks * kXchgMaxVals; }
+  size_t bytes() const { return (doubles() + 2) * sizeof(double); }
 } g_peer;
 
 thread_local char g_err[512] = "";
@@ -181,6 +186,11 @@ struct ccrs_problem {
   DevBuf<double> k3_dbg;   // [n_warps][8]
 #endif
   DevBuf<double> red_out, stat_out, gather, intr_dev, ya_dev, u_dev, scale_dev, l2_flush;
+  DevBuf<double> ctl_dev;         // LoopCtl of the device-driven loop (single problem)
+  DevBuf<double> s2_part;         // K3 (k_schur2) per-CTA partials [n_ctas][NRED]: self-validating slots, armed
+  PinBuf<double> h_rec, h_ctl;    // mapped: record ring [kRecSlots][kRecStride]; staging copy of the control block
+  double h_scale[9] = {1, 1, 1, 1, 1, 1, 1, 1, 1};   // host copy of the Jacobi scaling of the intrinsic columns (single problem)
+  long loop_records = 0;          // records consumed from the ring since creation
   DevBuf<unsigned char> mask_dev;
   DevBuf<unsigned int> tickets;   // [0] K2 statistics, [1] K3 reduction
   PinBuf<double> h_colsq;         // mapped: single problem [D] squared intrinsic column norms (Jacobi scaling)
@@ -204,7 +214,7 @@ struct ccrs_problem {
   bool pend = false;
   int pend_in_place = 0;
   bool pend_active = false;
-  double pend_ya[9] = {0}, pend_u = 0.0;
+  double pend_ya[9] = {0}, pend_ya_step[9] = {0}, pend_u = 0.0;
   // communicator
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1, deterministic = 1;
@@ -302,6 +312,13 @@ int upload_problem(ccrs_problem* p, int n_problems, const int32_t* problem_frame
   CK(p->intr_dev.alloc(P * p->D)); CK(p->ya_dev.alloc(P * p->D)); CK(p->u_dev.alloc(P)); CK(p->scale_dev.alloc(P * p->D));
   CK(p->mask_dev.alloc(P));
   CK(p->h_red.alloc(2 * (P * p->NRED + 1))); CK(p->h_stat.alloc(P * 2 + 2)); CK(p->h_colsq.alloc(P * p->D));
+  if (!p->batch) {
+    CK(p->ctl_dev.alloc(sizeof(LoopCtl) / 8)); CK(p->h_ctl.alloc(sizeof(LoopCtl) / 8));
+    CK(p->h_rec.alloc((size_t)kRecSlots * kRecStride));
+    const size_t n_part = (size_t)schur2_ctas(n_frames) * p->NRED;
+    CK(p->s2_part.alloc(n_part));
+    CK(launch_arm(p->s2_part.p, n_part, s));
+  }
   p->h_red.p[p->NRED] = -1.0; p->h_stat.p[2] = -1.0; p->h_stat.p[3] = -1.0;
   CK(cudaMemsetAsync(p->cur.p, 0, P * sizeof(int32_t), s));
   CK(cudaMemsetAsync(p->u_dev.p, 0, P * sizeof(double), s));
@@ -468,7 +485,9 @@ int upload_intr(ccrs_problem* p, const double* intr) {
 // standalone K4 (used by the public ccrs_backsub and to flush a deferred back-substitution)
 int launch_backsub_now(ccrs_problem* p, int in_place, bool want_md) {
   if (!p->batch) {  // the single-problem hot path keeps y_a / u on the host (kernel arguments); upload them for K4
-    CK(cudaMemcpyAsync(p->ya_dev.p, p->pend_ya, (size_t)p->D * 8, cudaMemcpyHostToDevice, p->stream));
+    // K3 (k_schur2) leaves the elimination record WITHOUT the intrinsic Jacobi scaling: the step K4 applies is D_a y_a
+    for (int i = 0; i < p->D; ++i) p->pend_ya_step[i] = p->pend_ya[i] * (p->last_use_scale ? p->h_scale[i] : 1.0);
+    CK(cudaMemcpyAsync(p->ya_dev.p, p->pend_ya_step, (size_t)p->D * 8, cudaMemcpyHostToDevice, p->stream));
     CK(cudaMemcpyAsync(p->u_dev.p, &p->pend_u, 8, cudaMemcpyHostToDevice, p->stream));
   }
   BacksubParams prm{};
@@ -529,7 +548,8 @@ int do_linearize(ccrs_problem* p, const double* intr, int which, bool cost_only,
     prm.ya_dev = p->ya_dev.p; prm.u_dev = p->u_dev.p;
     prm.active = p->pend_active ? p->mask_dev.p : nullptr;
     prm.frame_md = p->frame_md.p;
-    for (int i = 0; i < p->D; ++i) prm.y_a[i] = p->pend_ya[i];
+    // single problem: K3 leaves the elimination record without the intrinsic Jacobi scaling, the step is D_a y_a
+    for (int i = 0; i < p->D; ++i) prm.y_a[i] = p->pend_ya[i] * ((!p->batch && p->last_use_scale) ? p->h_scale[i] : 1.0);
     prm.u = p->pend_u;
     p->pend = false;
   } else if (p->batch) {
@@ -598,32 +618,28 @@ volatile double* red_area_ptr(ccrs_problem* p, int a) { return p->h_red.p + (siz
 
 // single problem: enqueue K3 (+ the NCCL exchange when the peer path is off) publishing into payload area `area`
 int launch_k3_single(ccrs_problem* p, int which, double u, int use_scale, double min_diag, double max_diag, int area) {
-  SchurParams prm{};
+  Schur2Params prm{};
   prm.pb = p->dev();
+  prm.ctl = nullptr;
   prm.which = which;
   prm.intr_scale = use_scale ? p->scale_dev.p : nullptr;
-  prm.pose_scale = use_scale ? p->pose_scale.p : nullptr;
+  prm.use_pose_scale = use_scale ? 1 : 0;
+  prm.pose_scale = p->pose_scale.p;
   prm.min_diag = min_diag; prm.max_diag = max_diag;
   prm.no_pose = p->fixed_poses ? 1 : 0;
   prm.elim = p->elim.p;
-  prm.frame_red = p->frame_red.p;
+  prm.partials = p->s2_part.p;
   p->last_use_scale = use_scale != 0;
-  prm.u_dev = nullptr;
   prm.u_val = u;
   prm.ticket = p->tickets.p + 1;
   prm.red_out = p->red_out.p;
   p->seq = next_seq();
-  prm.seq = p->seq;
   const bool peer = use_peer(p, (size_t)p->NRED);
   volatile double* host = red_area_ptr(p, area);
   prm.host_red = (p->comm && !peer) ? nullptr : host;
   arm_payload(host, p->NRED);
   if (peer) fill_peer(p, 0, &prm.px);
-#ifdef CCRS_K2_TIMING
-  if (!p->k3_dbg.p) CK(p->k3_dbg.alloc((size_t)8 * (p->n_frames / 32 + 8)));
-  prm.dbg = reinterpret_cast<long long*>(p->k3_dbg.p);
-#endif
-  CK(launch_schur(p->D, prm, p->stream));
+  CK(launch_schur2(p->D, prm, p->n_frames, true, p->stream));
   p->launches++;
   if (p->comm && !peer) { int st = exchange(p, p->red_out.p, (size_t)p->NRED, host, p->seq); if (st) return st; }
   return 0;
@@ -713,7 +729,7 @@ int be_trial_stats(void* ctx, const double* intr_trial, int speculative, double*
   if (st) return st;
   if (speculative && !p->batch && g_spec_enabled && p->have_last_reduce && (!p->comm || use_peer(p, (size_t)p->NRED))) {
     ccrs_problem::SpecK3& sp = p->spec;
-    sp.u = u_step * (1.0 / 3.0);     // controller: u *= max(1/3, 1 - (2 rho - 1)^3) on accept
+    sp.u = u_step * ccrs_rule::kLmMinAcceptFactor;   // ccrs_rule::lm_decide: u *= max(1/3, 1 - (2 rho - 1)^3) on accept
     sp.use_scale = p->last_use_scale ? 1 : 0; sp.mn = p->last_mn; sp.mx = p->last_mx;
     sp.cur_after = p->cur_val ^ 1;   // valid once the controller has accepted the trial point
     sp.area = (p->red_area ^= 1);
@@ -736,6 +752,212 @@ ccrs_backend cuda_backend(ccrs_problem* p) {
   be.reduce = be_reduce; be.backsub = be_backsub; be.trial_stats = be_trial_stats; be.accept = be_accept;
   be.allreduce = nullptr;  // exchanged on the device (NCCL) inside reduce / compute_scale / trial_stats
   return be;
+}
+
+
+// Device-side phase trace of the device-driven loop (ccrs_loop_trace): globaltimer stamps carried by the records.
+//   0 K2 (first warp past its wait -> last warp done) | 1 K2 done -> K3's last CTA past its wait | 2 K3 per-frame work
+//   + CTA sums (last CTA) | 3 K3 tail: cross-CTA sum, exchange, controller rule | 4 record ready -> next K2 running
+struct LoopTrace {
+  bool on = false;
+  long n = 0;
+  double acc[5] = {0, 0, 0, 0, 0};
+  double prev_end = -1.0;
+  void add(const double* r) {
+    const double wrap = 1099511627776.0;   // 2^40 ns
+    auto d = [&](double a, double b) { double x = b - a; if (x < -wrap / 2) x += wrap; return x; };
+    if (r[REC_T_K2_END] <= 0.0) { prev_end = r[REC_T_END]; return; }
+    if (prev_end >= 0.0 && (int)r[REC_DECIDED]) {
+      acc[0] += d(r[REC_T_K2_BEGIN], r[REC_T_K2_END]);
+      acc[1] += d(r[REC_T_K2_END], r[REC_T_K3_BEGIN]);
+      acc[2] += d(r[REC_T_K3_BEGIN], r[REC_T_TAIL]);
+      acc[3] += d(r[REC_T_TAIL], r[REC_T_END]);
+      acc[4] += d(prev_end, r[REC_T_K2_BEGIN]);
+      ++n;
+    }
+    prev_end = r[REC_T_END];
+  }
+};
+LoopTrace g_loop_trace;
+
+// ---- device-driven loop (single problem) -----------------------------------------------------------------------------
+// The host enqueues K3, K2, K3, K2, ... a bounded distance ahead of the records it has consumed; every decision of the
+// iteration is taken by the last CTA of K3 with the rule of ccrs_rule.h (LoopCtl, ccrs_kernels.cuh). The host keeps
+// what north_star keeps on the host — it re-runs the same rule on every published reduced system and checks the
+// device's accept / reject decision, damping, solve and trial point bit for bit (audit), fills the summary, and stops
+// the loop — but it is no longer on the critical path between two kernels.
+const bool g_device_loop = [] { const char* e = getenv("CCRS_DEVICE_LOOP"); return !(e && atoi(e) == 0); }();
+const int g_loop_ahead = [] { const char* e = getenv("CCRS_LOOP_AHEAD"); const int v = e ? atoi(e) : 2; return v >= 1 && v <= 8 ? v : 2; }();
+std::atomic<long> g_loop_audited{0};
+
+bool device_loop_ok(const ccrs_problem* p, bool lm, const ccrs_options& opt) {
+  if (!g_device_loop || p->batch) return false;
+  if (p->comm && !use_peer(p, (size_t)p->NRED + 2)) return false;   // NCCL fallback: host-driven
+  if (lm && !opt.speculative) return false;                          // classical K5 sequence: host-driven
+  return true;
+}
+
+struct DeviceLoop {
+  ccrs_problem* p;
+  bool lm;
+  int D;
+  long enq = 0, got = 0;          // K3 slots enqueued / records consumed in this loop
+  double intr_host[9];            // the host's copy of the current intrinsics (audit of the GN update)
+  unsigned char fixed[16];
+  bool has_fixed = false, has_bounds = false;
+  double lo[9], hi[9];
+  ccrs_options opt;
+};
+
+volatile double* rec_slot(ccrs_problem* p, long r) { return p->h_rec.p + (size_t)(r % kRecSlots) * kRecStride; }
+
+int loop_begin(DeviceLoop& L, ccrs_problem* p, bool lm, const double* intr, const double* lo, const double* hi,
+               const unsigned char* fixed, const ccrs_options& opt) {
+  int st = flush_pending(p);
+  if (st) return st;
+  p->spec.valid = false; p->have_last_reduce = false;
+  L.p = p; L.lm = lm; L.D = p->D; L.opt = opt; L.enq = L.got = 0;
+  LoopCtl* c = reinterpret_cast<LoopCtl*>(p->h_ctl.p);
+  std::memset(c, 0, sizeof(LoopCtl));
+  c->mode = lm ? 1 : 0; c->D = p->D; c->max_iteration = opt.max_iteration; c->fixed_mode = opt.fixed_mode;
+  c->has_bounds = (lo && hi) ? 1 : 0; c->has_fixed = fixed ? 1 : 0;
+  c->min_abs = opt.min_abs_decrease; c->min_rel = opt.min_rel_decrease; c->min_error = opt.min_error;
+  c->min_diag = opt.lm_min_diag; c->max_diag = opt.lm_max_diag; c->block_huber = lm ? 0.0 : opt.block_huber_delta;
+  L.has_bounds = c->has_bounds != 0; L.has_fixed = c->has_fixed != 0;
+  for (int i = 0; i < p->D; ++i) {
+    c->lo[i] = L.lo[i] = c->has_bounds ? lo[i] : 0.0; c->hi[i] = L.hi[i] = c->has_bounds ? hi[i] : 0.0;
+    c->fixed[i] = L.fixed[i] = fixed ? fixed[i] : 0;
+    c->intr[i] = c->trial[i] = L.intr_host[i] = intr[i];
+    c->scale[i] = 1.0;
+  }
+  c->phase = PH_LIN0; c->cur = p->cur_val; c->first = lm ? 1 : 0;
+  c->u = 1.0 / opt.lm_initial_radius; c->v = ccrs_rule::kLmRejectFactor0;
+  CK(cudaMemcpyAsync(p->ctl_dev.p, c, sizeof(LoopCtl), cudaMemcpyHostToDevice, p->stream));
+  // records are consumed in order and a slot is re-armed when its record has been read; in flight <= ahead + 1 << ring
+  arm_payload(p->h_rec.p, kRecSlots * kRecStride);
+  p->last_use_scale = lm;
+  return 0;
+}
+
+int loop_launch_k2(DeviceLoop& L) {
+  ccrs_problem* p = L.p;
+  LinParams prm{};
+  prm.pb = p->dev();
+  prm.ctl = reinterpret_cast<LoopCtl*>(p->ctl_dev.p);
+  prm.G = p->G; prm.FPW = p->FPW;
+  prm.acc_to_blk = p->acc_to_blk.p;
+  prm.elim = p->elim.p;
+  prm.pose_scale = L.lm ? p->pose_scale.p : nullptr;
+  prm.frame_md = p->frame_md.p;
+  prm.cta_part = p->cta_part.p;
+  prm.ticket = p->tickets.p;
+  prm.stat_dev = p->stat_out.p;
+  CK(launch_linearize(p->model, p->one_focal, false, false, prm, p->n_lin_ctas, p->stream));
+  p->launches++;
+  return 0;
+}
+
+int loop_launch_k3(DeviceLoop& L) {
+  ccrs_problem* p = L.p;
+  Schur2Params prm{};
+  prm.pb = p->dev();
+  prm.ctl = reinterpret_cast<LoopCtl*>(p->ctl_dev.p);
+  prm.pose_scale = p->pose_scale.p;
+  prm.min_diag = L.opt.lm_min_diag; prm.max_diag = L.opt.lm_max_diag;
+  prm.no_pose = p->fixed_poses ? 1 : 0;
+  prm.elim = p->elim.p;
+  prm.partials = p->s2_part.p;
+  prm.ticket = p->tickets.p + 1;
+  prm.red_out = p->red_out.p;
+  prm.rec = p->h_rec.p;
+  if (p->comm && p->world > 1) {
+    for (int r = 0; r < kXchgMaxRanks; ++r) prm.px.peer[r] = g_peer.peer[r];
+    prm.px.world = p->world; prm.px.rank = p->rank;
+    prm.px.off = (int)((size_t)2 * 2 * kXchgMaxRanks * kXchgMaxVals);   // area 2, parity added on the device
+    prm.xchg_count = g_peer.dev_count();
+  }
+  CK(launch_schur2(p->D, prm, p->n_frames, true, p->stream));
+  p->launches++;
+  L.enq++;
+  return 0;
+}
+
+bool same_bits(double a, double b) { return std::memcmp(&a, &b, 8) == 0; }
+
+// Wait for the next record, audit it against the host rule, fold it into the summary. *done = 1 on the final record.
+int loop_consume(DeviceLoop& L, ccrs_summary* sum, double* err_hist, int* done, double* intr_out) {
+  ccrs_problem* p = L.p;
+  const int D = L.D;
+  volatile double* slot = rec_slot(p, L.got);
+  int st = wait_payload(p, slot, kRecStride);
+  if (st) return st;
+  double r[kRecStride];
+  for (int i = 0; i < kRecStride; ++i) r[i] = slot[i];
+  arm_payload(slot, kRecStride);
+  L.got++; p->loop_records++;
+  static const bool dbg = getenv("CCRS_LOOP_DEBUG") != nullptr;
+  if (dbg)
+    fprintf(stderr, "[loop] rec %ld seq %.0f phase %.0f it %.0f iters %.0f acc %.0f rho %.6g u %.6g err %.9g solved %.0f status %.0f stop %.0f cur %.0f\n",
+            L.got, r[REC_SEQ], r[REC_PHASE], r[REC_IT], r[REC_ITERATIONS], r[REC_ACCEPTED], r[REC_RHO], r[REC_U], r[REC_CUR_ERR], r[REC_SOLVED],
+            r[REC_STATUS], r[REC_STOP], r[REC_CUR]);
+  if ((long)r[REC_SEQ] != L.got) return fail(CCRS_ERR_CUDA, "loop record out of sequence (%ld, expected %ld)", (long)r[REC_SEQ], L.got);
+  // ---- audit: the device's decisions reproduced with the host build of the same rule ---------------------------------
+  using namespace ccrs_rule;
+  if (L.lm && r[REC_DECIDED] != 0.0) {
+    LmState stt{r[REC_U_BEFORE], r[REC_V_BEFORE], r[REC_CUR_ERR_BEFORE]};
+    double rho;
+    const int acc = lm_decide(r[REC_SQ_CUR_BEFORE], r[REC_SQ_NEW], r[REC_MD_A_BEFORE] + r[REC_MD_POSE], &stt, &rho);
+    if (acc != (int)r[REC_ACCEPTED] || !same_bits(stt.u, r[REC_U]) || !same_bits(stt.v, r[REC_V]) || (!same_bits(rho, r[REC_RHO]) && !(is_nan(rho) && is_nan(r[REC_RHO]))))
+      return fail(CCRS_ERR_NUMERIC, "device LM decision differs from the host rule at record %ld (accepted %d vs %d, u %.17g vs %.17g)",
+                  L.got, (int)r[REC_ACCEPTED], acc, r[REC_U], stt.u);
+    if (acc) for (int i = 0; i < D; ++i) L.intr_host[i] = r[REC_INTR + i];
+  }
+  if (r[REC_SOLVED] != 0.0) {
+    double y[kMaxD], dx[kMaxD], trial[kMaxD], md_a = 0.0;
+    const Reduced rv = view(r + REC_OUT, D);
+    const int sst = solve_intrinsics(rv, D, r[REC_U_SOLVE], L.opt.lm_min_diag, L.opt.lm_max_diag, L.has_fixed ? L.fixed : nullptr,
+                                     L.opt.fixed_mode, y, &md_a);
+    bool ok = sst == 0 && same_bits(md_a, r[REC_MD_A]);
+    if (ok) {
+      for (int i = 0; i < D; ++i) dx[i] = r[REC_SCALE + i] * y[i];
+      update_intr(D, L.intr_host, dx, L.has_bounds ? L.lo : nullptr, L.has_bounds ? L.hi : nullptr, L.has_fixed ? L.fixed : nullptr, trial);
+      for (int i = 0; i < D; ++i) ok = ok && same_bits(y[i], r[REC_Y + i]) && same_bits(trial[i], r[REC_TRIAL + i]);
+    }
+    if (!ok) return fail(CCRS_ERR_NUMERIC, "device intrinsic solve differs from the host rule at record %ld", L.got);
+    if (!L.lm) for (int i = 0; i < D; ++i) L.intr_host[i] = trial[i];
+    g_loop_audited++;
+  }
+  // ---- summary -----------------------------------------------------------------------------------------------------------
+  sum->iterations = (int)r[REC_ITERATIONS];
+  sum->final_error = r[REC_FINAL_ERR];
+  sum->n_accepted = (int)r[REC_N_ACC]; sum->n_rejected = (int)r[REC_N_REJ];
+  if (err_hist && r[REC_HIST_IDX] >= 0.0 && (int)r[REC_HIST_IDX] < L.opt.max_iteration) err_hist[(int)r[REC_HIST_IDX]] = r[REC_HIST_VAL];
+  *done = (int)r[REC_PHASE] == PH_DONE;
+  if (*done) {
+    sum->status = (int)r[REC_STATUS];
+    sum->stop_reason = (int)r[REC_STOP];
+    p->cur_val = (int)r[REC_CUR];
+    for (int i = 0; i < D; ++i) { intr_out[i] = r[REC_INTR + i]; p->h_scale[i] = r[REC_SCALE + i]; }
+  }
+  if (g_loop_trace.on) g_loop_trace.add(r);
+  return 0;
+}
+
+int run_device_loop(ccrs_problem* p, bool lm, double* intr, const double* lo, const double* hi, const unsigned char* fixed,
+                    const ccrs_options& opt, ccrs_summary* sum, double* err_hist) {
+  std::memset(sum, 0, sizeof(*sum));
+  if (opt.max_iteration <= 0) return 0;
+  DeviceLoop L;
+  int st = loop_begin(L, p, lm, intr, lo, hi, fixed, opt);
+  if (st) return st;
+  st = loop_launch_k2(L);                       // linearise the start point
+  int done = 0;
+  while (!st && !done) {
+    while (!st && L.enq - L.got < g_loop_ahead) { st = loop_launch_k3(L); if (!st) st = loop_launch_k2(L); }
+    if (!st) st = loop_consume(L, sum, err_hist, &done, intr);
+  }
+  if (st) { sum->status = st; cudaStreamSynchronize(p->stream); return st; }
+  return sum->status;
 }
 
 }  // namespace
@@ -786,6 +1008,7 @@ int ccrs_problem_destroy(ccrs_problem* p) {
   p->red_out.release(); p->stat_out.release(); p->gather.release(); p->intr_dev.release(); p->ya_dev.release();
   p->u_dev.release(); p->scale_dev.release(); p->l2_flush.release(); p->mask_dev.release();
   p->h_red.release(); p->h_stat.release(); p->h_colsq.release();
+  p->ctl_dev.release(); p->h_rec.release(); p->h_ctl.release(); p->s2_part.release();
   if (p->stream) put_stream(p->device, p->stream);
   delete p;
   return 0;
@@ -1046,6 +1269,7 @@ int ccrs_set_intr_scale(ccrs_problem* p, const double* intr_scale) {
   if (!p) return fail(CCRS_ERR_INVALID, "null");
   CK(cudaSetDevice(p->device));
   if (!intr_scale) { p->have_scale = false; return 0; }
+  if (!p->batch) for (int i = 0; i < p->D; ++i) p->h_scale[i] = intr_scale[i];
   CK(cudaMemcpyAsync(p->scale_dev.p, intr_scale, (size_t)p->n_problems * p->D * 8, cudaMemcpyHostToDevice, p->stream));
   p->have_scale = true;
   return 0;
@@ -1127,9 +1351,9 @@ static int peer_setup(int rank, int world, cudaStream_t s) {
   if (const char* e = getenv("CCRS_P2P")) if (atoi(e) == 0) return 0;
   if (world < 2 || world > kXchgMaxRanks) return 0;
   NcclApi& n = nccl();
-  const size_t bytes = g_peer.doubles() * sizeof(double);
-  if (cudaMalloc((void**)&g_peer.local, bytes) != cudaSuccess) { cudaGetLastError(); g_peer.local = nullptr; return 0; }
+  if (cudaMalloc((void**)&g_peer.local, g_peer.bytes()) != cudaSuccess) { cudaGetLastError(); g_peer.local = nullptr; return 0; }
   if (launch_arm(g_peer.local, g_peer.doubles(), s) != cudaSuccess) return 0;
+  if (cudaMemsetAsync(g_peer.dev_count(), 0, 2 * sizeof(double), s) != cudaSuccess) return 0;
   cudaIpcMemHandle_t mine;
   int have = cudaIpcGetMemHandle(&mine, g_peer.local) == cudaSuccess ? 1 : 0;
   if (!have) cudaGetLastError();
@@ -1232,8 +1456,12 @@ static int timed_solve(ccrs_problem* p, bool lm, double* intr, const double* lo,
   ccrs_backend be = cuda_backend(p);
   ccrs_summary local;
   if (!summary) summary = &local;
-  int st = lm ? ccrs_controller_lm(&be, intr, lo, hi, fixed, opt, summary, err_hist)
-              : ccrs_controller_gn(&be, intr, lo, hi, fixed, opt, summary, err_hist);
+  ccrs_options o;
+  if (opt) o = *opt; else ccrs_default_options(&o);
+  int st;
+  if (device_loop_ok(p, lm, o)) st = run_device_loop(p, lm, intr, lo, hi, fixed, o, summary, err_hist);
+  else st = lm ? ccrs_controller_lm(&be, intr, lo, hi, fixed, opt, summary, err_hist)
+               : ccrs_controller_gn(&be, intr, lo, hi, fixed, opt, summary, err_hist);
   cudaEventRecord(e1, p->stream);
   cudaEventSynchronize(e1);
   float ms = 0.f;
@@ -1352,6 +1580,19 @@ int ccrs_init_poses(int n_frames, const int32_t* frame_offsets, const double* x,
   for (size_t f = 0; f < F; ++f)
     if (std::isnan(cost[f])) return fail(CCRS_ERR_NUMERIC, "no pose with the board in front of the camera for frame %zu", f);
   return 0;
+}
+
+int ccrs_loop_trace(int enable, double* avg_us /* [5] or NULL */, int64_t* n_iterations) {
+  if (avg_us) for (int i = 0; i < 5; ++i) avg_us[i] = g_loop_trace.n ? g_loop_trace.acc[i] * 1e-3 / g_loop_trace.n : 0.0;
+  if (n_iterations) *n_iterations = g_loop_trace.n;
+  g_loop_trace = LoopTrace{};
+  g_loop_trace.on = enable != 0;
+  return 0;
+}
+
+int ccrs_loop_counters(int64_t* audited_solves) {
+  if (audited_solves) *audited_solves = g_loop_audited.load();
+  return g_device_loop ? 1 : 0;
 }
 
 int ccrs_spec_k3_counters(int64_t* launched, int64_t* hits) {
@@ -1517,7 +1758,6 @@ int ccrs_bench_lm_steps(ccrs_problem* p, const double* intr0, const double* pose
   if (flush_l2 && !p->l2_flush.p) CK(p->l2_flush.alloc(flush_n));
   ccrs_options opt;
   ccrs_default_options(&opt);
-  opt.max_iteration = reset_every + 1;
   opt.min_abs_decrease = -1.0; opt.min_rel_decrease = -1.0; opt.min_error = -1.0;  // never stop: every step does full work
   ccrs_summary sum;
   ccrs_backend be = cuda_backend(p);
@@ -1527,14 +1767,26 @@ int ccrs_bench_lm_steps(ccrs_problem* p, const double* intr0, const double* pose
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   int st = 0;
   int64_t timed = 0;
+  const bool dev_loop = device_loop_ok(p, true, opt);
+  DeviceLoop L;
+  opt.max_iteration = 1 << 30;
   for (int i = 0; i < warmup + steps; ++i) {
     if (i % reset_every == 0) {  // back to the initial point: untimed (pose upload, first linearisation, Jacobi scaling)
       if (S) ccrs_lm_state_destroy(S);
       st = ccrs_set_poses(p, poses0);
       if (st) break;
       std::memcpy(intr.data(), intr0, intr.size() * sizeof(double));
-      S = ccrs_lm_state_create(&be, intr.data(), &opt, &sum);
-      if (!S) { st = fail(CCRS_ERR_CUDA, "lm_begin failed (%d)", sum.status); break; }
+      if (dev_loop) {
+        // device-driven loop: control block + linearisation of the start point; the first timed step is then
+        // K3 (first reduction incl. Jacobi scaling) + K2, every later one K3 (decision + reduction) + K2
+        std::memset(&sum, 0, sizeof(sum));
+        st = loop_begin(L, p, true, intr.data(), nullptr, nullptr, nullptr, opt);
+        if (!st) st = loop_launch_k2(L);
+        if (st) break;
+      } else {
+        S = ccrs_lm_state_create(&be, intr.data(), &opt, &sum);
+        if (!S) { st = fail(CCRS_ERR_CUDA, "lm_begin failed (%d)", sum.status); break; }
+      }
     }
     if (flush_l2) CK(launch_l2_flush(p->l2_flush.p, flush_n, p->stream));
     if (p->comm && p->world > 1) {
@@ -1548,10 +1800,16 @@ int ccrs_bench_lm_steps(ccrs_problem* p, const double* intr0, const double* pose
     const int64_t l0 = p->launches;
     int done = 0;
     CK(cudaEventRecord(e0, p->stream));
-    st = ccrs_lm_state_step(S, &done);
+    if (dev_loop) {
+      st = loop_launch_k3(L);
+      if (!st) st = loop_launch_k2(L);
+    } else {
+      st = ccrs_lm_state_step(S, &done);
+    }
     if (st) break;
     CK(cudaEventRecord(e1, p->stream));
     CK(cudaEventSynchronize(e1));
+    if (dev_loop) { st = loop_consume(L, &sum, nullptr, &done, intr.data()); if (st) break; }
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     if (i >= warmup) { step_ms[i - warmup] = ms; timed += p->launches - l0; }

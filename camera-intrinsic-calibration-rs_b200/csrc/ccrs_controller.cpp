@@ -6,6 +6,7 @@
 // (d x d) intrinsic solve, bounds clamp and fixed-variable reset (src/util.rs:29-71; tiny-solver
 // ParameterBlock::update_params). Everything per-observation / per-frame happens behind ccrs_backend.
 #include "../../include/ccrs_b200.h"
+#include "ccrs_rule.h"
 
 #include <algorithm>
 #include <cmath>
@@ -14,79 +15,10 @@
 
 namespace {
 
-// Restated tiny-solver constants (unverifiable here — see SURVEY App. B; mirrored in oracle/ccrs_oracle.hpp)
-constexpr bool kErrorIsL2Norm = true;   // optimisers compare ||r||, not ||r||^2
-constexpr double kLmRejectFactor0 = 2.0;
-
-inline double err_metric(double sq) { return kErrorIsL2Norm ? std::sqrt(sq) : sq; }
-// One HuberLoss over the WHOLE residual vector (ModelConvertFactor is a single residual block, util.rs:246-251):
-// the corrector scales r and J by the same w = sqrt(rho'(s)), s = ||r||^2, so the Gauss-Newton step is unchanged and
-// only the error the stop tests see becomes ||w r||^2 = delta sqrt(s) outside the quadratic region.
-inline double block_loss(double sq, double delta) { return (delta > 0.0 && sq > delta * delta) ? delta * std::sqrt(sq) : sq; }
-
-// in-place lower Cholesky of a dense n x n SPD matrix; false on a non-positive pivot
-bool chol_factor(double* A, int n) {
-  for (int j = 0; j < n; ++j) {
-    double s = A[j * n + j];
-    for (int k = 0; k < j; ++k) s -= A[j * n + k] * A[j * n + k];
-    if (!(s > 0.0)) return false;
-    const double l = std::sqrt(s);
-    A[j * n + j] = l;
-    for (int i = j + 1; i < n; ++i) {
-      double t = A[i * n + j];
-      for (int k = 0; k < j; ++k) t -= A[i * n + k] * A[j * n + k];
-      A[i * n + j] = t / l;
-    }
-  }
-  return true;
-}
-void chol_solve(const double* L, int n, double* b) {
-  for (int i = 0; i < n; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= L[i * n + k] * b[k]; b[i] = s / L[i * n + i]; }
-  for (int i = n - 1; i >= 0; --i) { double s = b[i]; for (int k = i + 1; k < n; ++k) s -= L[k * n + i] * b[k]; b[i] = s / L[i * n + i]; }
-}
-
-struct Reduced {  // view into one problem's slice of the reduce() output
-  const double *S, *gs, *ga, *diag;
-  double sq_err;
-};
-inline Reduced view(const double* out, int d) {
-  return Reduced{out, out + d * d, out + d * d + d, out + d * d + 2 * d, out[d * d + 3 * d]};
-}
-
-// Solve the damped intrinsic system of one problem. Returns 0 / CCRS_ERR_CHOLESKY / CCRS_ERR_NUMERIC.
-int solve_intrinsics(const Reduced& r, int d, double u, double min_diag, double max_diag, const unsigned char* fixed,
-                     int fixed_mode, double* y, double* model_dec_a) {
-  std::vector<double> S(r.S, r.S + d * d), g(r.gs, r.gs + d);
-  std::vector<double> dd(d);
-  for (int i = 0; i < d; ++i) {
-    dd[i] = std::min(std::max(r.diag[i], min_diag), max_diag);
-    S[i * d + i] += u * dd[i];
-  }
-  if (fixed)
-    for (int i = 0; i < d; ++i)
-      if (fixed[i] == 2 || (fixed[i] && fixed_mode == 1)) { for (int j = 0; j < d; ++j) { S[i * d + j] = 0; S[j * d + i] = 0; } S[i * d + i] = 1; g[i] = 0; }
-  for (int i = 0; i < d * d; ++i) if (std::isnan(S[i])) return CCRS_ERR_CHOLESKY;  // poisoned by a failed frame pivot
-  if (!chol_factor(S.data(), d)) return CCRS_ERR_CHOLESKY;
-  for (int i = 0; i < d; ++i) y[i] = g[i];
-  chol_solve(S.data(), d, y);
-  if (model_dec_a) {  // y_a^T g'_a + u * sum dd_i y_i^2 (intrinsic part of y^T(2g' - H'y), using H_reg y = g')
-    double md = 0.0;
-    for (int i = 0; i < d; ++i) md += y[i] * r.ga[i] + u * dd[i] * y[i] * y[i];
-    *model_dec_a = md;
-  }
-  return 0;
-}
-
-// ParameterBlock::update_params: new = old + dx ; clamp bounded indices ; fixed indices keep the old value
-void update_intr(int d, const double* intr, const double* dx, const double* lo, const double* hi,
-                 const unsigned char* fixed, double* out) {
-  for (int i = 0; i < d; ++i) {
-    double v = intr[i] + dx[i];
-    if (lo && hi) v = std::min(std::max(v, lo[i]), hi[i]);
-    if (fixed && fixed[i]) v = intr[i];
-    out[i] = v;
-  }
-}
+// The controller arithmetic (error metric, damped d x d solve, update_params, accept / reject rule, stop tests) lives in
+// ccrs_rule.h: one source, built here for the host and in ccrs_loop.cu for the device-driven loop.
+using namespace ccrs_rule;
+static_assert(kErrNumeric == CCRS_ERR_NUMERIC && kErrCholesky == CCRS_ERR_CHOLESKY, "ccrs_rule.h status codes out of sync with the ABI");
 
 #define BE(call)                         \
   do {                                   \
@@ -135,12 +67,10 @@ int ccrs_controller_gn(const ccrs_backend* be, double* intr, const double* lo, c
       const Reduced r = view(&out[(size_t)p * NOUT], d);
       const double err = err_metric(block_loss(r.sq_err, opt.block_huber_delta));
       if (p == 0) { if (err_hist) err_hist[it] = err; sum->final_error = err; }
-      if (err < opt.min_error) { active[p] = 0; stop[p] = 1; continue; }
-      if (std::isnan(err)) { active[p] = 0; worst = CCRS_ERR_NUMERIC; continue; }
-      if (it > 0) {
-        if (std::fabs(last_err[p] - err) < opt.min_abs_decrease) { active[p] = 0; stop[p] = 2; continue; }
-        if (std::fabs(last_err[p] - err) / last_err[p] < opt.min_rel_decrease) { active[p] = 0; stop[p] = 3; continue; }
-      }
+      int status = 0;
+      const int why = gn_stop(it, last_err[p], err, opt.min_error, opt.min_abs_decrease, opt.min_rel_decrease, &status);
+      if (status != 0) { active[p] = 0; worst = status; continue; }
+      if (why != 0) { active[p] = 0; stop[p] = why; continue; }
       last_err[p] = err;
       double* yp = &y[(size_t)p * d];
       const int st = solve_intrinsics(r, d, 0.0, opt.lm_min_diag, opt.lm_max_diag, fixed, opt.fixed_mode, yp, nullptr);
@@ -231,28 +161,23 @@ static int lm_iterate(ccrs_lm_state& S, int* done) {
     if (!S.active[p]) continue;
     const Reduced r = view(&S.out[(size_t)p * NOUT], d);
     const double new_sq = S.stats[2 * p + 1];
-    const double rho = (r.sq_err - new_sq) / (S.md_a[p] + S.stats[2 * p]);
     const double last_err = S.cur_err[p];
-    bool accepted = false;
-    if (rho > 0.0) {
-      accepted = true; S.acc_mask[p] = 1; any_accept = true;
+    LmState st{S.u[p], S.v[p], S.cur_err[p]};
+    double rho;
+    const bool accepted = lm_decide(r.sq_err, new_sq, S.md_a[p] + S.stats[2 * p], &st, &rho) != 0;
+    S.u[p] = st.u; S.v[p] = st.v; S.cur_err[p] = st.cur_err;
+    if (accepted) {
+      S.acc_mask[p] = 1; any_accept = true;
       std::memcpy(S.intr + (size_t)p * d, &S.trial[(size_t)p * d], d * sizeof(double));
-      const double t = 2.0 * rho - 1.0;
-      S.u[p] *= std::max(1.0 / 3.0, 1.0 - t * t * t);
-      S.v[p] = kLmRejectFactor0;
-      S.cur_err[p] = err_metric(new_sq);
       if (p == 0) sum->n_accepted++;
-    } else {
-      S.u[p] *= S.v[p]; S.v[p] *= 2.0;
-      if (p == 0) sum->n_rejected++;
+    } else if (p == 0) {
+      sum->n_rejected++;
     }
     if (p == 0) { if (S.err_hist) S.err_hist[it] = S.cur_err[p]; sum->final_error = S.cur_err[p]; }
-    if (S.cur_err[p] < opt.min_error) { S.active[p] = 0; S.stop[p] = 1; }
-    else if (std::isnan(S.cur_err[p]) || std::isnan(rho)) { S.active[p] = 0; S.worst = CCRS_ERR_NUMERIC; }
-    else if (accepted) {  // stop tests compare successive ACCEPTED errors
-      if (std::fabs(last_err - S.cur_err[p]) < opt.min_abs_decrease) { S.active[p] = 0; S.stop[p] = 2; }
-      else if (std::fabs(last_err - S.cur_err[p]) / last_err < opt.min_rel_decrease) { S.active[p] = 0; S.stop[p] = 3; }
-    }
+    int status = 0;   // the stop tests compare successive ACCEPTED errors
+    const int why = lm_stop(last_err, S.cur_err[p], rho, accepted ? 1 : 0, opt.min_error, opt.min_abs_decrease, opt.min_rel_decrease, &status);
+    if (status != 0) { S.active[p] = 0; S.worst = status; }
+    else if (why != 0) { S.active[p] = 0; S.stop[p] = why; }
   }
   if (any_accept) {
     BE(be->accept(be->ctx, S.acc_mask.data()));

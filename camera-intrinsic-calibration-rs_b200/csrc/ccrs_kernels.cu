@@ -9,8 +9,7 @@
 // ReprojectionFactor::residual_func, reference src/optimization/factors.rs:152-173), the sparse J^T J product and
 // the sparse LLT (call sites src/util.rs:455,463,670). No tensor cores: there is no dense contraction, the
 // per-frame blocks are 6x6 / 6xd. Determinism: no floating-point atomics anywhere; every sum has a fixed order.
-#include "ccrs_device.cuh"
-#include "ccrs_kernels.cuh"
+#include "ccrs_devutil.cuh"
 
 #include <type_traits>
 
@@ -87,34 +86,6 @@ struct RowCfg {
 template <int MODEL, bool OF>
 constexpr bool lin_pair_v = Cfg<MODEL, OF>::NACC > kPairThreshold;
 
-// bit pattern that arms a result slot which validates itself (device partials, mapped host results): a NaN payload
-// no computation produces (the Cholesky-failure poison is the canonical quiet NaN)
-constexpr long long kArmBits = 0x7ff8dead5e471e15LL;
-__global__ void k_arm(double* p, size_t n) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    p[i] = __longlong_as_double(kArmBits);
-}
-
-// value v of this rank's partial -> sum over ranks (see PeerXchg). Called by one thread per value.
-CCRS_D double peer_exchange(const PeerXchg& px, int v, double mine) {
-  const size_t slot = (size_t)px.off + v;
-  for (int r = 0; r < px.world; ++r)
-    *reinterpret_cast<volatile double*>(px.peer[r] + slot + (size_t)px.rank * kXchgMaxVals) = mine;
-  volatile double* loc = px.peer[px.rank] + slot;
-  double tot = 0.0;
-  const long long t0 = clock64();
-  for (int r = 0; r < px.world; ++r) {
-    double x = loc[(size_t)r * kXchgMaxVals];
-    while (__double_as_longlong(x) == kArmBits) {
-      if (clock64() - t0 > 4000000000LL) { x = nan(""); break; }   // ~2 s: a peer never arrived -> poison, not a hang
-      x = loc[(size_t)r * kXchgMaxVals];
-    }
-    tot += x;                                                       // rank order
-    loc[(size_t)r * kXchgMaxVals] = __longlong_as_double(kArmBits); // re-arm for the next use of this area
-  }
-  return tot;
-}
-
 CCRS_D int cur_of(const ProblemDev& pb, int prob) { return pb.cur ? pb.cur[prob] : pb.cur_val; }
 
 // publish n doubles to mapped host memory: plain stores, no fence — the host armed the n words with a sentinel and
@@ -123,22 +94,10 @@ CCRS_D void publish_host(volatile double* dst, const double* src, int n) {
   for (int i = 0; i < n; ++i) dst[i] = src[i];
 }
 
-CCRS_D void cp_async8(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
-}
-CCRS_D void cp_async4(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
-}
 // observation k of an SoA array that holds doubles or (f32 != 0) floats; f32 -> f64 widening as factors.rs:141-143
 CCRS_D double ld_obs(const double* base, int k, int f32) {
   return f32 ? (double)reinterpret_cast<const float*>(base)[k] : base[k];
 }
-// no "memory" clobber on the issue side: ordinary loads may be scheduled across the prefetch (the pose prologue's loads
-// then overlap it); the wait below is the barrier that orders the ring reads
-CCRS_D void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N>
-CCRS_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // One observation: weighted rows au, av of [J | r] in the LOCAL rotation basis (d/dphi, not d/drvec).
 // Returns the corrected squared residual. Structurally-zero entries of au/av are left untouched.
 template <int MODEL, bool OF, bool WITH_J>
@@ -250,19 +209,20 @@ CCRS_D double obs_rows(const double* __restrict__ ip /* full intrinsics */, cons
 constexpr int kRedStride = 33;    // row stride of the reduction staging buffer (odd: no bank conflicts)
 constexpr int kA2bDoubles = 112;  // per-warp copy of the accumulator -> block-entry table (<= 224 int32)
 CCRS_HD constexpr int lin_warp_smem_doubles(int FPW, bool batch, bool cost_only) {
-  return FPW * kFrameConst + (batch ? FPW * kMaxFull : 0) + 2 * FPW + (cost_only ? 32 : kRedChunk * kRedStride) +
+  return FPW * kFrameConst + (batch ? FPW * kMaxFull : kMaxFull + 1) + 2 * FPW + (cost_only ? 32 : kRedChunk * kRedStride) +
          kObsStages * 5 * 32 + kA2bDoubles;
 }
 
 // Executed by the whole warp that took the last ticket: every producer of a {model decrease, cost} partial has taken
 // its ticket, so every partial store has been issued. Sum the n_parts slots in a fixed order, exchange across GPUs,
 // publish.
-CCRS_D void stats_finalize(const LinParams& prm, unsigned n_parts, int lane) {
+CCRS_D void stats_finalize(const LinParams& prm, unsigned n_parts, int lane, int phase) {
   // every warp has taken its ticket, so every partial store has been issued: read the slots from L2 (16 loads
   // in flight per lane) until none still holds the arming pattern, sum in a fixed order, re-arm for the next launch
   double2* part = reinterpret_cast<double2*>(prm.cta_part);
   double a = 0.0, b = 0.0;
   constexpr int kBatch = 16;   // loads in flight per lane
+  const long long t_spin = clock64();
   for (unsigned w0 = lane; w0 < n_parts; w0 += 32 * kBatch) {
     double2 t[kBatch];
     bool ok;
@@ -273,6 +233,11 @@ CCRS_D void stats_finalize(const LinParams& prm, unsigned n_parts, int lane) {
         const unsigned w = w0 + 32 * q;
         t[q] = w < n_parts ? __ldcg(part + w) : make_double2(0.0, 0.0);
         ok = ok && (__double_as_longlong(t[q].x) != kArmBits) && (__double_as_longlong(t[q].y) != kArmBits);
+      }
+      if (!ok && clock64() - t_spin > 4000000000LL) {   // ~2 s: a partial never arrived -> poison the result, not a hang
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) t[q] = make_double2(nan(""), nan(""));
+        ok = true;
       }
     } while (!ok);
 #pragma unroll
@@ -286,6 +251,17 @@ CCRS_D void stats_finalize(const LinParams& prm, unsigned n_parts, int lane) {
   for (int o = 16; o >= 1; o >>= 1) {
     a += __shfl_xor_sync(0xffffffffu, a, o);
     b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (prm.ctl) {
+    // device-driven loop: this rank's sums stay on the device; the next K3 exchanges them together with the reduced
+    // system (one cross-GPU exchange per iteration) and takes the accept / reject decision
+    if (lane == 0) {
+      prm.ctl->stat[0] = a; prm.ctl->stat[1] = b;
+      prm.ctl->t_k2_end = stamp_ns();
+      prm.ctl->phase = (phase == PH_LIN0 && prm.ctl->mode == 1) ? PH_REDUCE : PH_DECIDE;
+      *prm.ticket = 0u;
+    }
+    return;
   }
   if (prm.px.world > 1) {
     const double mine = lane == 0 ? a : b;
@@ -530,47 +506,101 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
 #pragma unroll
     for (int i = 0; i < kObsStages - 1; ++i) fetch(beg + i * G, i);
   };
-  // batch handles reach their pose through two more dependent loads (frame -> problem -> state selector): there the
-  // observation prefetch goes out as soon as the frame offsets are back; a single problem issues everything first
-  if constexpr (BATCH) prefetch_first_stages();
-  if (active) {
-    cur = cur_of(pb, prob);
-    if (prm.backsub) {
+  // which point is linearised, and how the pending step is applied, come from the launch (host-driven) or from the
+  // device control block (device-driven loop)
+  int which = prm.which, backsub = prm.backsub, phase = -1;
+  double u_bs = prm.u;
+  double ya_bs[C::D];
+  double lin_intr[C::D];
+  if constexpr (BATCH) {
+    // batch handles reach their pose through two more dependent loads (frame -> problem -> state selector): there the
+    // observation prefetch goes out as soon as the frame offsets are back
+    prefetch_first_stages();
+    if (active) cur = cur_of(pb, prob);
+  } else if (prm.ctl) {
+    // Device-driven loop: this grid was launched as a programmatic dependent of the K3 in front of it. Everything
+    // above and the observation prefetch touch only immutable data; the control block, the poses and the elimination
+    // record are read after that K3 has completed — all of them issued together (both pose buffers: which one is
+    // current is only known once the control block is back), one memory round trip.
+    prefetch_first_stages();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const LoopCtl* ctl = prm.ctl;
+    const int ph = __ldcg(&ctl->phase), lm = __ldcg(&ctl->mode), cu = __ldcg(&ctl->cur);
+    u_bs = __ldcg(&ctl->u_used);
+#pragma unroll
+    for (int a = 0; a < C::D; ++a) { ya_bs[a] = __ldcg(&ctl->step[a]); lin_intr[a] = __ldcg(&ctl->trial[a]); }
+    double r0[6], r1[6];
+    if (active) {
+      const double *p0 = pb.poses[0] + 6 * (size_t)f, *p1 = pb.poses[1] + 6 * (size_t)f;
+      const double* el = prm.elim + f;
+      const size_t Fs = pb.Fs;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        r0[i] = __ldcg(p0 + i); r1[i] = __ldcg(p1 + i);
+#pragma unroll
+        for (int a = 0; a < C::D; ++a) X[i][a] = __ldcg(el + (size_t)(i * C::D + a) * Fs);
+        cg[i] = __ldcg(el + (size_t)(6 * C::D + i) * Fs);
+        gp[i] = __ldcg(el + (size_t)(6 * C::D + 6 + i) * Fs);
+        dd[i] = __ldcg(el + (size_t)(6 * C::D + 12 + i) * Fs);
+        sp[i] = prm.pose_scale ? __ldcg(prm.pose_scale + (size_t)i * Fs + f) : 1.0;
+      }
+    }
+    phase = ph;
+    if (phase != PH_LIN0 && phase != PH_TRIAL) {   // not this slot's turn (re-reduction pending, or the loop is done)
+      cp_async_wait<0>();
+      return;
+    }
+    if (gw == 0 && lane == 0) prm.ctl->t_k2_begin = stamp_ns();
+    cur = cu;
+    backsub = phase == PH_LIN0 ? 0 : (lm ? 1 : 2);
+    which = (phase == PH_TRIAL && lm) ? 1 : 0;
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) rt[i] = cur ? r1[i] : r0[i];
+      moves = backsub != 0;
+      pose_dst = pb.poses[backsub == 2 ? cur : (cur ^ 1)] + 6 * (size_t)f;
+    }
+  } else {
+    cur = pb.cur_val;
+#pragma unroll
+    for (int a = 0; a < C::D; ++a) ya_bs[a] = prm.y_a[a];
+  }
+  if (active && (BATCH || !prm.ctl)) {
+    if (backsub) {
       const double* src = pb.poses[cur] + 6 * (size_t)f;
-      pose_dst = pb.poses[prm.backsub == 2 ? cur : (cur ^ 1)] + 6 * (size_t)f;
+      pose_dst = pb.poses[backsub == 2 ? cur : (cur ^ 1)] + 6 * (size_t)f;
       moves = !(BATCH && prm.active && !prm.active[prob]);
 #pragma unroll
       for (int i = 0; i < 6; ++i) rt[i] = src[i];
       if (moves) {
         const double* el = prm.elim + f;
         const size_t Fs = pb.Fs;
-        // read-only path: none of these can alias the pose store below
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
 #pragma unroll
-          for (int a = 0; a < C::D; ++a) X[i][a] = __ldg(el + (size_t)(i * C::D + a) * Fs);
-          cg[i] = __ldg(el + (size_t)(6 * C::D + i) * Fs);
-          gp[i] = __ldg(el + (size_t)(6 * C::D + 6 + i) * Fs);
-          dd[i] = __ldg(el + (size_t)(6 * C::D + 12 + i) * Fs);
-          sp[i] = prm.pose_scale ? __ldg(prm.pose_scale + (size_t)i * Fs + f) : 1.0;
+          for (int a = 0; a < C::D; ++a) X[i][a] = __ldcg(el + (size_t)(i * C::D + a) * Fs);
+          cg[i] = __ldcg(el + (size_t)(6 * C::D + i) * Fs);
+          gp[i] = __ldcg(el + (size_t)(6 * C::D + 6 + i) * Fs);
+          dd[i] = __ldcg(el + (size_t)(6 * C::D + 12 + i) * Fs);
+          sp[i] = prm.pose_scale ? __ldcg(prm.pose_scale + (size_t)i * Fs + f) : 1.0;
         }
       }
     } else {
-      const double* src = pb.poses[cur ^ prm.which] + 6 * (size_t)f;
+      const double* src = pb.poses[cur ^ which] + 6 * (size_t)f;
 #pragma unroll
       for (int i = 0; i < 6; ++i) rt[i] = src[i];
     }
   }
-  if constexpr (!BATCH) prefetch_first_stages();
+  if constexpr (!BATCH) if (!prm.ctl) prefetch_first_stages();
 
   // ---- prologue: every lane of a frame evaluates the frame's pose redundantly (same addresses: broadcast loads);
   //      slice 0 stores. Fused K4: y_p = cg - X y_a ; pose += D_p y_p ; model decrease y_p^T g'_p + u sum dd_i y_p,i^2
   double md = 0.0;   // model decrease of this lane's frame (same value in all lanes of the frame)
   if (active) {
-    if (prm.backsub) {
+    if (backsub) {
       if (moves) {
-        const double* ya = BATCH ? prm.ya_dev + (size_t)prob * C::D : prm.y_a;
-        const double u = BATCH ? (prm.u_dev ? prm.u_dev[prob] : 0.0) : prm.u;
+        const double* ya = BATCH ? prm.ya_dev + (size_t)prob * C::D : ya_bs;
+        const double u = BATCH ? (prm.u_dev ? prm.u_dev[prob] : 0.0) : u_bs;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
           double yp = cg[i];
@@ -604,12 +634,24 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
       }
     }
   }
+  if constexpr (!BATCH) {
+    // the warp's copy of the full intrinsic vector (fy := fx inserted for one-focal problems, factors.rs:156-158)
+    if (lane == 0) {
+      if (prm.ctl) {
+        if constexpr (OF) { s_intr[0] = lin_intr[0]; s_intr[1] = lin_intr[0]; for (int i = 1; i < C::D; ++i) s_intr[i + 1] = lin_intr[i]; }
+        else { for (int i = 0; i < C::D; ++i) s_intr[i] = lin_intr[i]; }
+      } else {
+#pragma unroll
+        for (int i = 0; i < C::DFULL; ++i) s_intr[i] = prm.intr[i];
+      }
+    }
+  }
 #pragma unroll
   for (int i = 0; i < kA2bPerLane; ++i) if (lane + 32 * i < kA2bN) s_a2b[lane + 32 * i] = a2b_reg[i];   // loaded with the prologue's other loads
   __syncwarp();
   CCRS_TCK(1);
 
-  const double* ip = BATCH ? (s_intr + (active ? fl : 0) * kMaxFull) : prm.intr;
+  const double* ip = BATCH ? (s_intr + (active ? fl : 0) * kMaxFull) : s_intr;
   const double* fc = s_fc + (active ? fl : 0) * kFrameConst;
 
   double acc[NACC_L];
@@ -743,10 +785,10 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   if constexpr (COST_ONLY) {
     if (active && sl == 0) {
       const int prob = BATCH ? pb.frame_problem[f] : 0;
-      pb.frame_cost[cur_of(pb, prob) ^ prm.which][f] = fcost;
+      pb.frame_cost[(BATCH ? cur_of(pb, prob) : cur) ^ which][f] = fcost;
     }
   } else {
-    double* const out = pb.blocks[(BATCH ? (active ? cur_of(pb, pb.frame_problem[f]) : 0) : cur_of(pb, 0)) ^ prm.which] + f;
+    double* const out = pb.blocks[(BATCH ? (active ? cur_of(pb, pb.frame_problem[f]) : 0) : cur) ^ which] + f;
     if constexpr (PAIR) slices_reduce_store_pair<R>(acc, active, lane, fl, sl, G, s_red, s_a2b, out, (size_t)pb.Fs);
     else slices_reduce_store<C>(acc, active, lane, fl, sl, G, s_red, s_a2b, out, (size_t)pb.Fs);
   }
@@ -755,7 +797,7 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   if constexpr (!BATCH) {
     const unsigned last = __shfl_sync(0xffffffffu, (unsigned)(ticket_old == n_warps - 1), 0);
     if (last) {
-      stats_finalize(prm, n_warps, lane);
+      stats_finalize(prm, n_warps, lane, phase);
     }
   }
 #ifdef CCRS_K2_TIMING
@@ -1265,6 +1307,17 @@ static cudaError_t launch_lin_t(const LinParams& prm, int n_ctas, cudaStream_t s
     if (e != cudaSuccess) return e;
     configured = true;
   }
+  if (prm.ctl) {
+    // device-driven loop: programmatic dependent of the K3 in front of it — the CTAs are scheduled while that K3
+    // drains, run their observation prefetch and wait at griddepcontrol.wait for its control block
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_ctas); cfg.blockDim = dim3(kLinThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, prm);
+  }
   kern<<<n_ctas, kLinThreads, smem, s>>>(prm);
   return cudaGetLastError();
 }
@@ -1311,43 +1364,21 @@ static cudaError_t dispatch_d(int D, F&& f) {
   return cudaErrorInvalidValue;
 }
 
-// single problem: partials buffer = frame_red (reused as [n_ctas][NRED]); result summed into red_out by the caller
+// batch handles: one thread per frame, per-frame contributions reduced per problem by k_segreduce. (The single-problem
+// reduction is k_schur2, ccrs_loop.cu.)
 cudaError_t launch_schur(int D, const SchurParams& prm, cudaStream_t s) {
-  const bool batch = prm.pb.frame_problem != nullptr;
   const int nb = (prm.pb.n_frames + kSchurThreads - 1) / kSchurThreads;
   return dispatch_d(D, [&](auto DD) {
     constexpr int d = decltype(DD)::value;
-    constexpr int NRED = d * (d + 1) / 2 + 3 * d + 1;
     constexpr size_t kStage = (size_t)(d + 7) * (d + 8) / 2 * kSchurThreads * sizeof(double);   // one packed block per thread
-    if (batch) {
-      auto kern = k_schur<d, true>;
-      static bool configured = false;
-      if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStage);
-        if (e != cudaSuccess) return e;
-        configured = true;
-      }
-      kern<<<nb, kSchurThreads, kStage, s>>>(prm, nullptr);
-    } else {
-      const size_t smem = std::max(kStage, (size_t)NRED * (kSchurThreads + 1) * sizeof(double));
-      auto kern = k_schur<d, false>;
-      static bool configured = false;
-      if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-      }
-      // programmatic dependent launch: when K3 is enqueued behind a K2 that is still running (the speculative
-      // launch), its CTAs are scheduled as K2's drain and wait at griddepcontrol.wait, so the grid-launch ramp overlaps
-      // K2's tail; with nothing in front of it the wait returns at once
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(nb); cfg.blockDim = dim3(kSchurThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      at[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-      return cudaLaunchKernelEx(&cfg, kern, prm, prm.frame_red);
+    auto kern = k_schur<d, true>;
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStage);
+      if (e != cudaSuccess) return e;
+      configured = true;
     }
+    kern<<<nb, kSchurThreads, kStage, s>>>(prm, nullptr);
     return cudaGetLastError();
   });
 }

@@ -43,8 +43,59 @@ struct PeerXchg {
   int off;                       // double offset of the [world][kXchgMaxVals] slot area used by this exchange
 };
 
+// ---- device-driven loop (ccrs_loop.cu) ---------------------------------------------------------------------------
+// The Gauss-Newton / Levenberg-Marquardt iteration of a single problem runs without a host round trip: the host
+// enqueues K3, K2, K3, K2, ... (each a programmatic dependent of the one before), the last CTA of K3 executes the
+// controller rule (ccrs_rule.h: d x d solve, clamp, accept / reject, damping update, stop tests) on the reduced system
+// it has just summed and leaves {phase, intrinsics to linearise at, intrinsic step, damping} in this block for K2; K2's
+// last warp leaves {pose part of the model decrease, cost}. A slot whose turn it is not (phase mismatch, loop done)
+// exits at once. Every executed K3 publishes one record to mapped host memory; the host audits it by re-running the
+// same rule, fills the summary and stops enqueueing when a record says the loop is done.
+enum LoopPhase : int {
+  PH_LIN0 = 0,     // K2: linearise the start point (no step to apply)
+  PH_REDUCE = 1,   // K3: reduce blocks[cur] with damping ctl.u (first iteration, or after a rejected / mis-speculated step)
+  PH_TRIAL = 2,    // K2: apply the step (LM: into the trial buffers; GN: in place) and linearise there
+  PH_DECIDE = 3,   // K3: K2's statistics are in; LM: accept / reject, then reduce; GN: stop tests, then reduce
+  PH_DONE = 5
+};
+constexpr int kRecStride = 192;   // doubles per published record
+constexpr int kRecSlots = 32;     // ring of records in mapped host memory
+// record layout (doubles)
+enum : int {
+  REC_SEQ = 0, REC_PHASE, REC_STATUS, REC_STOP, REC_IT, REC_ITERATIONS, REC_ACCEPTED, REC_CUR, REC_RHO, REC_U, REC_V,
+  REC_CUR_ERR, REC_U_SOLVE, REC_MD_A, REC_SQ_NEW, REC_MD_POSE, REC_SQ_CUR_BEFORE, REC_U_BEFORE, REC_V_BEFORE,
+  REC_CUR_ERR_BEFORE, REC_MD_A_BEFORE, REC_HIST_IDX, REC_HIST_VAL, REC_SOLVED, REC_N_ACC, REC_N_REJ, REC_FINAL_ERR,
+  REC_SQ_CUR, REC_LAST_ERR_BEFORE, REC_DECIDED,
+  // device timestamps (globaltimer, low 40 bits, ns): the K2 in front of this K3 (first warp after its wait / last warp
+  // at its end), this K3 (entry of the last CTA after its wait, start of the last CTA's tail, record ready)
+  REC_T_K2_BEGIN, REC_T_K2_END, REC_T_K3_BEGIN, REC_T_TAIL, REC_T_END,
+  REC_INTR = 40, REC_TRIAL = 49, REC_Y = 58, REC_SCALE = 67, REC_OUT = 76   // out: d*d + 3d + 1 <= 109
+};
+struct LoopCtl {
+  // ---- configuration: constant during a loop
+  int mode;                 // 0 Gauss-Newton, 1 Levenberg-Marquardt
+  int D, max_iteration, fixed_mode, has_bounds, has_fixed;
+  double min_abs, min_rel, min_error, min_diag, max_diag, block_huber;
+  double lo[9], hi[9];
+  unsigned char fixed[16];
+  // ---- state
+  int phase, cur, it, iterations, first, seq, status, stop_reason, n_acc, n_rej;
+  double u, v;              // LM damping (1 / radius) and reject factor
+  double u_used;            // damping of the reduction whose elimination record K2 back-substitutes with
+  double intr[9];           // current intrinsics (optimised vector)
+  double trial[9];          // intrinsics K2 linearises at next
+  double step[9];           // intrinsic step in unscaled units (Jacobi scale x y_a): what K2's back-substitution uses
+  double scale[9];          // Jacobi scaling of the intrinsic columns (LM; 1 for GN)
+  double md_a;              // intrinsic part of the model decrease of the pending trial step
+  double sq_cur, cur_err, last_err, final_err;
+  double stat[2];           // K2 (this rank): {pose part of the model decrease, sum of corrected r^2} at the point it linearised
+  double t_k2_begin, t_k2_end;   // device timestamps of the last executed K2 (see REC_T_*)
+};
+static_assert(sizeof(LoopCtl) % 8 == 0, "LoopCtl is copied as 8-byte words");
+
 struct LinParams {
   ProblemDev pb;
+  LoopCtl* ctl;             // device-driven loop: phase, intrinsics, step, damping, buffer selector come from here
   const double* intr_dev;   // [n_problems][D] (batch) — single problem passes intr[] by value below
   double intr[9];           // full vector fx fy cx cy k.. (single problem; constant bank operands)
   const int32_t* acc_to_blk;  // [NACC] sparse accumulator -> dense packed block index
@@ -101,6 +152,30 @@ struct BacksubParams {
   int in_place;                 // GN: write the update into the current poses
   const unsigned char* active;  // [n_problems] nullable: problems whose poses must not move
 };
+
+// K3, single problem (ccrs_loop.cu): eight lanes per frame; Jacobi scaling of the intrinsic columns factored out of the
+// per-frame work and applied after the sum, so that the first LM reduction can compute it itself.
+struct Schur2Params {
+  ProblemDev pb;
+  LoopCtl* ctl;                 // nullable: host-driven call (u_val / which / scales below)
+  int which;
+  double u_val;
+  const double* intr_scale;     // [D] device or nullptr (host-driven)
+  int use_pose_scale;           // host-driven: 1 = read pose_scale
+  double* pose_scale;           // [6][Fs]
+  double min_diag, max_diag;
+  int no_pose;
+  double* elim;                 // [(6D+18)][Fs]: X (6xD, WITHOUT the intrinsic scaling), cg (6), g'_p (6), Dd (6)
+  double* partials;             // [n_ctas][NRED]
+  unsigned int* ticket;
+  double* red_out;              // [NRED] device (host-driven)
+  volatile double* host_red;    // mapped pinned [NRED] (host-driven; nullptr when a cross-rank NCCL exchange follows)
+  volatile double* rec;         // mapped pinned [kRecSlots][kRecStride] (ctl mode)
+  PeerXchg px;
+  unsigned int* xchg_count;     // device counter of executed exchanges (parity of the peer slots), nullable
+};
+cudaError_t launch_schur2(int D, const Schur2Params& prm, int n_frames, bool pdl, cudaStream_t s);
+int schur2_ctas(int n_frames);   // CTAs (= partial slots) of a k_schur2 launch
 
 // number of values K3 reduces per problem: S upper (D(D+1)/2) + g_s (D) + g_a (D) + diag_a (D) + sq_err (1)
 inline int nred_of(int D) { return D * (D + 1) / 2 + 3 * D + 1; }

@@ -346,6 +346,21 @@ int ccrs_step_trace(int enable, double* avg_us, int64_t* n_iterations);
  * and kernel leave the critical path; a different decision by the controller just launches K3 again. Process-wide
  * counters (speculative launches, launches whose result was used); returns 1 if enabled (CCRS_SPEC_K3=0 disables). */
 int ccrs_spec_k3_counters(int64_t* launched, int64_t* hits);
+/* Device-driven loop (single-problem handles; ccrs_solve_gn / ccrs_solve_lm / ccrs_calib_camera use it whenever the
+ * handle has no communicator or exchanges over peer memory): the host enqueues K3, K2, K3, K2, ... ahead of time, each a
+ * programmatic dependent of the one before; the last CTA of K3 runs the controller rule (accept / reject, damping, stop
+ * tests, d x d solve, clamp — the same source as the host controllers, csrc/ccrs_rule.h) and leaves the next
+ * linearisation point in device memory, so no host round trip sits between two kernels. The host audits every
+ * published iteration record by re-running the rule (decisions and solves must agree bit for bit) and ends the loop.
+ * CCRS_DEVICE_LOOP=0 selects the host-driven controllers instead.
+ * ccrs_loop_counters: number of device solves the host has audited (process-wide); returns 1 if the loop is enabled.
+ * ccrs_loop_trace: device-side phase trace (globaltimer stamps carried by the records), microseconds per iteration
+ * averaged since the last call, then resets and enables/disables tracing:
+ *   [0] K2: first warp past its dependency wait -> last warp done   [1] K2 done -> K3's last CTA past its wait
+ *   [2] K3 per-frame elimination + CTA sums (last CTA)              [3] K3 tail: cross-CTA sum, exchange, controller rule
+ *   [4] record ready -> next K2 running */
+int ccrs_loop_counters(int64_t* audited_solves);
+int ccrs_loop_trace(int enable, double* avg_us, int64_t* n_iterations);
 /* Kernel launches issued by this handle since creation. */
 int64_t ccrs_launch_count(const ccrs_problem* p);
 

@@ -316,29 +316,54 @@ def test_f32_observation_api_is_bit_identical(pkg):
     g64.close(); g32.close()
 
 
-def test_speculative_k3_is_used_and_changes_nothing(pkg, oracle):
-    """the K3 launched behind the trial K2 (for 'accepted, u_next = u / 3') must be consumed on a converging run and the
-    trajectory must be bit-identical to the run without it (same kernels, same arguments, only launched earlier)."""
-    import ctypes as C, os, subprocess, sys, json
+_SOLVE_CODE = ("import importlib,json,numpy as np;pkg=importlib.import_module('camera-intrinsic-calibration-rs_b200');"
+               "import ctypes as C;lib=pkg._abi.load();"
+               "s=pkg.synth.make_calib('eucm',100,seed=1,noise_px=0.1);gp=pkg.Problem.from_synth(s);gp.set_poses(s.init_poses);"
+               "intr,summ,hist=gp.%s(s.init_params);a,h,n=C.c_int64(0),C.c_int64(0),C.c_int64(0);"
+               "lib.ccrs_spec_k3_counters(C.byref(a),C.byref(h));lib.ccrs_loop_counters(C.byref(n));"
+               "print(json.dumps([intr.tolist(),hist.tolist(),gp.get_poses().tolist(),int(summ.iterations),a.value,h.value,n.value]))")
+
+
+def _solve_in_subprocess(loop, **env):
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", _SOLVE_CODE % loop], cwd=root, env=dict(os.environ, **env), capture_output=True,
+                         text=True, check=True).stdout
+    return json.loads(out.strip().splitlines()[-1])
+
+
+def test_device_loop_is_audited_and_matches_the_host_controllers(pkg, oracle):
+    """ccrs_solve_lm / ccrs_solve_gn run the device-driven loop (K3's last CTA executes the controller rule, no host
+    round trip): every solve must have been audited by the host (same rule, bit-for-bit) and the trajectory must match
+    the oracle and the host-driven controllers (CCRS_DEVICE_LOOP=0) at equal iteration count."""
+    import ctypes as C
     s, op, gp, intr0 = _setup(pkg, oracle, "eucm", 100, seed=1, noise_px=0.1)
     lib = pkg._abi.load()
-    a0, h0 = C.c_int64(0), C.c_int64(0)
-    enabled = lib.ccrs_spec_k3_counters(C.byref(a0), C.byref(h0))
-    gp.set_poses(s.init_poses)
-    intr, summ, hist = gp.solve_lm(intr0)
-    poses = gp.get_poses()
-    a1, h1 = C.c_int64(0), C.c_int64(0)
-    lib.ccrs_spec_k3_counters(C.byref(a1), C.byref(h1))
-    assert enabled == 1 and a1.value - a0.value == summ.iterations and h1.value - h0.value >= 1
-    intr_ref, poses_ref, res, hist_ref = op.levenberg_marquardt(intr0, s.init_poses)
-    assert summ.iterations == res.iterations and np.max(np.abs(intr - intr_ref) / np.abs(intr_ref)) < TOL_INTR
+    n0, n1 = C.c_int64(0), C.c_int64(0)
+    assert lib.ccrs_loop_counters(C.byref(n0)) == 1
+    for loop in ("solve_lm", "solve_gn"):
+        gp.set_poses(s.init_poses)
+        lib.ccrs_loop_counters(C.byref(n0))
+        intr, summ, hist = getattr(gp, loop)(intr0)
+        lib.ccrs_loop_counters(C.byref(n1))
+        # one audited device solve per iteration (Gauss-Newton's last iteration stops before its solve)
+        assert summ.status == 0 and n1.value - n0.value == summ.iterations - (0 if loop == "solve_lm" else 1)
+        ref = (op.levenberg_marquardt if loop == "solve_lm" else op.gauss_newton)(intr0, s.init_poses)
+        assert summ.iterations == ref[2].iterations and np.max(np.abs(intr - ref[0]) / np.abs(ref[0])) < TOL_INTR
+        assert np.max(np.abs(hist - np.asarray(ref[3])[: len(hist)]) / np.asarray(ref[3])[: len(hist)]) < 1e-9
+        i2, h2, p2, it2, _, _, n2 = _solve_in_subprocess(loop, CCRS_DEVICE_LOOP="0")
+        assert n2 == 0 and it2 == summ.iterations                               # the host-driven controller ran there
+        assert np.max(np.abs(intr - np.array(i2)) / np.abs(intr)) < 1e-12
+        assert np.max(np.abs(gp.get_poses() - np.array(p2))) < 1e-10
     gp.close()
-    # same solve in a process with CCRS_SPEC_K3=0: bitwise the same numbers
-    code = ("import importlib,json,numpy as np;pkg=importlib.import_module('camera-intrinsic-calibration-rs_b200');"
-            "s=pkg.synth.make_calib('eucm',100,seed=1,noise_px=0.1);gp=pkg.Problem.from_synth(s);gp.set_poses(s.init_poses);"
-            "intr,summ,hist=gp.solve_lm(s.init_params);print(json.dumps([intr.tolist(),hist.tolist(),gp.get_poses().tolist()]))")
-    env = dict(os.environ, CCRS_SPEC_K3="0")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, check=True).stdout
-    i2, h2, p2 = json.loads(out.strip().splitlines()[-1])
-    assert np.array_equal(intr, np.array(i2)) and np.array_equal(hist, np.array(h2)) and np.array_equal(poses, np.array(p2))
+
+
+def test_speculative_k3_is_used_and_changes_nothing():
+    """Host-driven LM (CCRS_DEVICE_LOOP=0): the K3 launched behind the trial K2 (for 'accepted, u_next = u / 3') must be
+    consumed on a converging run and the trajectory must be bit-identical to the run without it (same kernels, same
+    arguments, only launched earlier)."""
+    i1, h1, p1, it1, launched, hits, _ = _solve_in_subprocess("solve_lm", CCRS_DEVICE_LOOP="0")
+    assert launched == it1 and hits >= 1
+    i2, h2, p2, it2, launched2, _, _ = _solve_in_subprocess("solve_lm", CCRS_DEVICE_LOOP="0", CCRS_SPEC_K3="0")
+    assert launched2 == 0 and it1 == it2
+    assert np.array_equal(np.array(i1), np.array(i2)) and np.array_equal(np.array(h1), np.array(h2)) and np.array_equal(np.array(p1), np.array(p2))
