@@ -34,6 +34,20 @@ CCRS_D double peer_exchange(const PeerXchg& px, int v, double mine) {
   return tot;
 }
 
+// Loads for spin loops on self-validating slots: volatile (the compiler must re-issue them every pass — a plain
+// __ldcg may legally be hoisted out of the loop, which turns "not there yet" into an endless spin) and strong at GPU
+// scope (served by L2, the coherence point).
+CCRS_D double ld_spin(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+CCRS_D double2 ld_spin2(const double2* p) {
+  double2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
+
 // globaltimer (ns), low 40 bits: exact in a double, wraps every 18 minutes
 CCRS_D double stamp_ns() {
   unsigned long long t;

@@ -231,7 +231,7 @@ CCRS_D void stats_finalize(const LinParams& prm, unsigned n_parts, int lane, int
 #pragma unroll
       for (int q = 0; q < kBatch; ++q) {
         const unsigned w = w0 + 32 * q;
-        t[q] = w < n_parts ? __ldcg(part + w) : make_double2(0.0, 0.0);
+        t[q] = w < n_parts ? ld_spin2(part + w) : make_double2(0.0, 0.0);
         ok = ok && (__double_as_longlong(t[q].x) != kArmBits) && (__double_as_longlong(t[q].y) != kArmBits);
       }
       if (!ok && clock64() - t_spin > 4000000000LL) {   // ~2 s: a partial never arrived -> poison the result, not a hang

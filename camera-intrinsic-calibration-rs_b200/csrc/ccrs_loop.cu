@@ -216,10 +216,10 @@ __global__ void __launch_bounds__(kS2Threads, 1) k_schur2(const __grid_constant_
   int which_buf = pb.cur_val ^ prm.which;   // buffer index of the blocks to reduce
   double u = prm.u_val;
   int phase_in = -1, first = 0, skip = 0, use_pose_scale = prm.use_pose_scale;
+  __shared__ double s_head[sizeof(LoopCtl) / 8];   // the control block as it was when this grid started
+  __shared__ double s_u;
+  __shared__ int s_dec[4];   // which_buf, first, skip, run
   if (ctl) {
-    __shared__ double s_head[sizeof(LoopCtl) / 8];
-    __shared__ double s_u;
-    __shared__ int s_dec[4];   // which_buf, first, skip, run
     constexpr int kCtlWords = (int)(sizeof(LoopCtl) / 8);
     if (threadIdx.x < kCtlWords) s_head[threadIdx.x] = __ldcg(reinterpret_cast<const double*>(ctl) + threadIdx.x);
     __syncthreads();
@@ -251,6 +251,11 @@ __global__ void __launch_bounds__(kS2Threads, 1) k_schur2(const __grid_constant_
     }
     __syncthreads();
     if (!s_dec[3]) return;   // not this slot's turn / loop done
+  }
+  // The ticket only elects the CTA that will sum the partials (the last one to ARRIVE); it is taken now so that its
+  // round trip overlaps the block loads. Partial slots validate themselves, so the elected CTA simply waits for them.
+  if (threadIdx.x == 0) s_last = (atomicAdd(prm.ticket, 1u) == gridDim.x - 1);
+  if (ctl) {
     const LoopCtl* c = reinterpret_cast<const LoopCtl*>(s_head);
     phase_in = c->phase;
     use_pose_scale = c->mode;
@@ -386,9 +391,8 @@ __global__ void __launch_bounds__(kS2Threads, 1) k_schur2(const __grid_constant_
     if (fl == 0 && v < NRED) s_cta[wid * (NRED + 1) + v] = ((red[j] + x1) + x2) + x3;
   }
   __syncthreads();
-  // No fence: the partial slots validate themselves (armed with kArmBits at creation and re-armed by the last CTA of
-  // the previous launch); the relaxed ticket only elects the CTA that sums, and its round trip overlaps the stores.
-  if (threadIdx.x == 0) s_last = (atomicAdd(prm.ticket, 1u) == gridDim.x - 1);
+  // No fence: the partial slots validate themselves (armed with kArmBits at creation and re-armed by the summing CTA of
+  // the previous launch); the relaxed ticket (taken at the top) only elected the CTA that sums.
   if (threadIdx.x < NRED) {
     double s = s_cta[threadIdx.x];
 #pragma unroll
@@ -420,7 +424,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) k_schur2(const __grid_constant_
 #pragma unroll
           for (int q = 0; q < kFly; ++q) {
             const int b = b0 + q * SEG;
-            t[q] = b < nb ? __ldcg(prm.partials + (size_t)b * NRED + v) : 0.0;
+            t[q] = b < nb ? ld_spin(prm.partials + (size_t)b * NRED + v) : 0.0;
             ok = ok && (__double_as_longlong(t[q]) != kArmBits);
           }
           if (!ok && clock64() - t_spin > 4000000000LL) {   // ~2 s: a partial never arrived -> poison, not a hang
@@ -444,8 +448,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) k_schur2(const __grid_constant_
   // by the one thread that runs the rule)
   LoopCtl* const s_ctl = reinterpret_cast<LoopCtl*>(s_rec + kRecStride);
   constexpr int kCtlWords = (int)(sizeof(LoopCtl) / 8);
-  if (ctl && threadIdx.x < kCtlWords)
-    reinterpret_cast<double*>(s_ctl)[threadIdx.x] = __ldcg(reinterpret_cast<const double*>(ctl) + threadIdx.x);
+  if (ctl && threadIdx.x < kCtlWords) reinterpret_cast<double*>(s_ctl)[threadIdx.x] = s_head[threadIdx.x];   // unchanged since the head read it
   __syncthreads();
   if (threadIdx.x < C::NX) {
     double tot;
