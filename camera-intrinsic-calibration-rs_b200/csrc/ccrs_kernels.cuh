@@ -69,6 +69,7 @@ enum : int {
   // device timestamps (globaltimer, low 40 bits, ns): the K2 in front of this K3 (first warp after its wait / last warp
   // at its end), this K3 (entry of the last CTA after its wait, start of the last CTA's tail, record ready)
   REC_T_K2_BEGIN, REC_T_K2_END, REC_T_K3_BEGIN, REC_T_TAIL, REC_T_END,
+  REC_T_HEAD, REC_T_LOAD, REC_T_COMP, REC_T_SUMMED, REC_T_RULE,   // finer stamps of the last CTA (tools/loop_trace.py)
   REC_INTR = 40, REC_TRIAL = 49, REC_Y = 58, REC_SCALE = 67, REC_OUT = 76   // out: d*d + 3d + 1 <= 109
 };
 struct LoopCtl {

@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) k_schur2(const __grid_constant_
     u = s_u; which_buf = s_dec[0]; first = s_dec[1]; skip = s_dec[2];
   }
 
+  const double t_head = stamp_ns();
   double red[C::VPL];
 #pragma unroll
   for (int j = 0; j < C::VPL; ++j) red[j] = 0.0;
@@ -281,6 +282,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) k_schur2(const __grid_constant_
     sp_ld[i] = (wact && !skip && use_pose_scale && !first) ? __ldcg(prm.pose_scale + (size_t)i * pb.Fs + f) : 1.0;
   cp_async_wait<0>();
   __syncwarp();
+  const double t_load = stamp_ns();
   if (wact && !skip) {
     const size_t Fs = pb.Fs;
     auto H = [&](int i, int j) { return sb[tri_idx(NA, i, j)]; };
@@ -382,6 +384,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) k_schur2(const __grid_constant_
     }
   }
   // ---- fixed-order sums: the warp's four frames (shuffles), the CTA's warps, then the CTAs (last CTA) ----
+  const double t_comp = stamp_ns();
   double* const s_cta = smem + kS2Warps * C::WSTRIDE;     // [kS2Warps][NRED + 1]
 #pragma unroll
   for (int j = 0; j < C::VPL; ++j) {
@@ -470,6 +473,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) k_schur2(const __grid_constant_
     s_tot[threadIdx.x] = tot;
   }
   __syncthreads();
+  const double t_summed = stamp_ns();
   if (threadIdx.x == 0) {
     *prm.ticket = 0u;
     if (prm.xchg_count && prm.px.world > 1) *prm.xchg_count += 1u;
@@ -492,6 +496,8 @@ __global__ void __launch_bounds__(kS2Threads, 1) k_schur2(const __grid_constant_
   if (threadIdx.x == 0) {
     s_rec[REC_T_K2_BEGIN] = s_ctl->t_k2_begin; s_rec[REC_T_K2_END] = s_ctl->t_k2_end;
     s_rec[REC_T_K3_BEGIN] = t_begin; s_rec[REC_T_TAIL] = t_tail;
+    s_rec[REC_T_HEAD] = t_head; s_rec[REC_T_LOAD] = t_load; s_rec[REC_T_COMP] = t_comp; s_rec[REC_T_SUMMED] = t_summed;
+    s_rec[REC_T_RULE] = stamp_ns();
     loop_rule<D>(s_ctl, s_tot, s_rec, phase_in, u, which_buf);
     s_rec[REC_T_END] = stamp_ns();
   }

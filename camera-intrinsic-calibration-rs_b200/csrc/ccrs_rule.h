@@ -31,12 +31,14 @@
 #define CCRS_RSUB(a, b) __dsub_rn((a), (b))
 #define CCRS_RDIV(a, b) __ddiv_rn((a), (b))
 #define CCRS_RSQRT(a) __dsqrt_rn(a)
+#define CCRS_RFMA(a, b, c) __fma_rn((a), (b), (c))
 #else
 #define CCRS_RMUL(a, b) ((a) * (b))
 #define CCRS_RADD(a, b) ((a) + (b))
 #define CCRS_RSUB(a, b) ((a) - (b))
 #define CCRS_RDIV(a, b) ((a) / (b))
 #define CCRS_RSQRT(a) sqrt(a)
+#define CCRS_RFMA(a, b, c) fma((a), (b), (c))   /* correctly rounded by definition, with or without FMA hardware */
 #endif
 
 namespace ccrs_rule {
@@ -63,16 +65,34 @@ CCRS_RULE_HD double block_loss(double sq, double delta) {
   return (delta > 0.0 && sq > CCRS_RMUL(delta, delta)) ? CCRS_RMUL(delta, CCRS_RSQRT(sq)) : sq;
 }
 
-// in-place lower Cholesky of a dense n x n SPD matrix; false on a non-positive pivot. The diagonal holds the RECIPROCAL
-// pivots 1/l_jj (one division per column: the dependent divisions are what the device-side rule waits for).
+// 1/sqrt(x) for a normal positive x, identical bits on host and device: integer seed (relative error < 3.5e-2), then
+// four Newton steps y <- y (1 + e/2), e = 1 - x y^2, in correctly-rounded multiply / fused multiply-add arithmetic
+// (error after the steps ~1e-20 before rounding: within ~1 ulp). A third of the latency of an IEEE sqrt followed by an
+// IEEE division, which is what the device-side rule — one thread, one dependent chain — waits for.
+CCRS_RULE_HD double rule_rsqrt(double x) {
+  union { double d; long long i; } v;
+  v.d = x;
+  v.i = 0x5fe6eb50c7b537a9LL - (v.i >> 1);
+  double y = v.d;
+  CCRS_RULE_UNROLL
+  for (int it = 0; it < 4; ++it) {
+    const double t = CCRS_RMUL(x, y);
+    const double e = CCRS_RFMA(-t, y, 1.0);
+    y = CCRS_RFMA(y, CCRS_RMUL(0.5, e), y);
+  }
+  return y;
+}
+
+// in-place lower Cholesky of a dense n x n SPD matrix; false on a non-positive (or non-finite) pivot. The diagonal holds
+// the RECIPROCAL pivots 1/l_jj.
 CCRS_RULE_HD bool chol_factor(double* A, int n) {
   CCRS_RULE_UNROLL
   for (int j = 0; j < n; ++j) {
     double s = A[j * n + j];
     CCRS_RULE_UNROLL
     for (int k = 0; k < j; ++k) s = CCRS_RSUB(s, CCRS_RMUL(A[j * n + k], A[j * n + k]));
-    if (!(s > 0.0)) return false;
-    const double il = CCRS_RDIV(1.0, CCRS_RSQRT(s));
+    if (!(s > 0.0) || s > 1e300) return false;
+    const double il = rule_rsqrt(s);
     A[j * n + j] = il;
     CCRS_RULE_UNROLL
     for (int i = j + 1; i < n; ++i) {

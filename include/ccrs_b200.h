@@ -358,7 +358,9 @@ int ccrs_spec_k3_counters(int64_t* launched, int64_t* hits);
  * averaged since the last call, then resets and enables/disables tracing:
  *   [0] K2: first warp past its dependency wait -> last warp done   [1] K2 done -> K3's last CTA past its wait
  *   [2] K3 per-frame elimination + CTA sums (last CTA)              [3] K3 tail: cross-CTA sum, exchange, controller rule
- *   [4] record ready -> next K2 running */
+ *   [4] record ready -> next K2 running
+ *   [5..11] finer split of [2] and [3] in the last CTA of K3: control block + decision | block load | per-frame
+ *   elimination | CTA sum + partial store | cross-CTA sum (+ exchange) | staging | controller rule.   avg_us: [12] */
 int ccrs_loop_counters(int64_t* audited_solves);
 int ccrs_loop_trace(int enable, double* avg_us, int64_t* n_iterations);
 /* Kernel launches issued by this handle since creation. */

@@ -21,6 +21,7 @@ c.dist.init_comm(gp, rank, world)
 lib = c._abi.load()
 names = ["K2 (first warp past its wait -> last warp done)", "K2 done -> K3 last CTA past its wait", "K3 per-frame elimination + CTA sums",
          "K3 tail: cross-CTA sum, exchange, controller rule", "record ready -> next K2 running"]
+fine = ["control block + decision", "block load", "per-frame elimination", "CTA sum + partial store", "cross-CTA sum (+ exchange)", "staging", "controller rule"]
 out = {"frames_total": n, "frames_this_rank": int(hi - lo), "model": model, "n_gpus": world}
 for loop in ("lm", "gn"):
     o = c.default_options(max_iteration=40, min_abs_decrease=-1.0, min_rel_decrease=-1.0, min_error=-1.0)
@@ -29,10 +30,11 @@ for loop in ("lm", "gn"):
     lib.ccrs_loop_trace(1, None, None)
     gp.set_poses(s.init_poses[lo:hi])
     _, summ, _ = solve(s.init_params, options=o)
-    avg = (C.c_double * 5)(); cnt = C.c_int64(0)
+    avg = (C.c_double * 12)(); cnt = C.c_int64(0)
     lib.ccrs_loop_trace(0, avg, C.byref(cnt))
     out[loop] = {"iterations_traced": int(cnt.value), "device_ms_per_iteration_events": summ.device_ms / max(summ.iterations, 1),
-                 "phases_us": {names[i]: round(avg[i], 2) for i in range(5)}, "sum_us": round(sum(avg), 2)}
+                 "phases_us": {names[i]: round(avg[i], 2) for i in range(5)}, "sum_us": round(sum(avg[:5]), 2),
+                 "k3_last_cta_us": {fine[i]: round(avg[5 + i], 2) for i in range(7)}}
 if rank == 0:
     print(json.dumps(out, indent=1))
 gp.close()
