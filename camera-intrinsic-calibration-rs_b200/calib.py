@@ -509,6 +509,8 @@ def calib_all_camera_with_extrinsics(cameras: Sequence[GenericModel], t_cam_i_0:
     n_cams = len(cameras)
     model = cameras[0].model
     nfull = len(cameras[0].params)
+    if any(c.model != model or len(c.params) != nfull for c in cameras):
+        raise ValueError("calib_all_camera_with_extrinsics: every camera must use the same model")
     shift = 1 if xy_same_focal else 0
     d = nfull - shift
     frame_ids = sorted({f for c in range(n_cams) for f in cam_rtvecs[c]})      # valid_frame_board_to_cam0
@@ -532,10 +534,10 @@ def calib_all_camera_with_extrinsics(cameras: Sequence[GenericModel], t_cam_i_0:
                 if c == 0:
                     poses[fidx[f]] = rt.as_array()
                 else:                                      # 0 <- i <- board (util.rs:640-650): T_c_0^-1 * T_c_b
-                    import cv2
+                    from .synth import rotmat_to_rvec
                     Rc, tc = iso(t_cam_i_0[c]); Rb, tb = iso(rt)
                     R = Rc.T @ Rb; t = Rc.T @ (tb - tc)
-                    poses[fidx[f]] = np.concatenate([cv2.Rodrigues(R)[0].ravel(), t])
+                    poses[fidx[f]] = np.concatenate([rotmat_to_rvec(R), t])
                 have_pose[fidx[f]] = True
     intr = np.zeros((n_cams, d)); lo = np.zeros((n_cams, d)); hi = np.zeros((n_cams, d)); fixed = np.zeros((n_cams, d), dtype=np.uint8)
     keep = [i for i in range(nfull) if not (xy_same_focal and i == 1)]
@@ -549,8 +551,10 @@ def calib_all_camera_with_extrinsics(cameras: Sequence[GenericModel], t_cam_i_0:
         fixed[0, 0] = 1                                    # problem.fix_variable("params0", 0) (util.rs:664-667)
     extr = np.stack([t.as_array() for t in t_cam_i_0])
     jp = JointProblem(model, n_cams, len(frame_ids), bc, bf, offs, xs, ys, zs, us, vs, xy_same_focal=xy_same_focal, device=device)
-    a, e, p, s, _ = jp.solve_gn(intr, extr, poses, lo, hi, fixed, options)
-    jp.close()
+    try:
+        a, e, p, s, _ = jp.solve_gn(intr, extr, poses, lo, hi, fixed, options)
+    finally:
+        jp.close()
     if s.status in (-4, -5):
         return None
     out_cams = []

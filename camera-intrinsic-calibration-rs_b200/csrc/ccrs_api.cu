@@ -1494,14 +1494,14 @@ int ccrs_model_bounds(int model, int width, int height, double* lo, double* hi) 
   for (int i = 0; i < n; ++i) { lo[i] = -inf; hi[i] = inf; }
   lo[0] = 0; hi[0] = 1e4; lo[1] = 0; hi[1] = 1e4;       // util.rs:36-37
   lo[2] = 0; hi[2] = width; lo[3] = 0; hi[3] = height;  // util.rs:38-39
-  // GenericModel::distortion_params_bound() — restated (unpinned)
+  // GenericModel::distortion_params_bound() of camera-intrinsic-model 0.8 is not in the reference tree (un-vendored
+  // crate): only the bounds the projection itself requires are applied — alpha in (0, 1], beta > 0 of the unified
+  // models. Polynomial / tangential coefficients (KB4, OPENCV5, FTHETA k*, EUCMT t1 t2) stay UNBOUNDED rather than being
+  // clamped to an invented box: real lenses have |k| > 1 and a silent clamp would converge to a different answer.
   switch (model) {
     case CCRS_UCM: lo[4] = 1e-6; hi[4] = 1.0; break;
-    case CCRS_EUCM: case CCRS_EUCMT: lo[4] = 1e-6; hi[4] = 1.0; lo[5] = 1e-6; hi[5] = 100.0;
-      if (model == CCRS_EUCMT) { lo[6] = lo[7] = -1.0; hi[6] = hi[7] = 1.0; }
-      break;
-    case CCRS_KB4: case CCRS_FTHETA: for (int i = 4; i < 8; ++i) { lo[i] = -1.0; hi[i] = 1.0; } break;
-    case CCRS_OPENCV5: for (int i = 4; i < 9; ++i) { lo[i] = -1.0; hi[i] = 1.0; } break;
+    case CCRS_EUCM: case CCRS_EUCMT: lo[4] = 1e-6; hi[4] = 1.0; lo[5] = 1e-6; hi[5] = 100.0; break;
+    default: break;
   }
   return 0;
 }

@@ -69,6 +69,24 @@ def rodrigues(rvec: np.ndarray) -> np.ndarray:
     return np.eye(3) + a * k + b * (k @ k)
 
 
+def rotmat_to_rvec(R: np.ndarray) -> np.ndarray:
+    """(3,3) rotation matrix -> axis-angle (the log map; inverse of `rodrigues`, angles in [0, pi])."""
+    R = np.asarray(R, dtype=np.float64)
+    w = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    c = np.clip((np.trace(R) - 1.0) * 0.5, -1.0, 1.0)
+    s = 0.5 * np.linalg.norm(w)
+    th = np.arctan2(s, c)
+    if s > 1e-9:
+        return w * (th / (2.0 * s))
+    if c > 0.0:                      # near the identity: log R ~ (R - R^T)/2
+        return 0.5 * w
+    # near pi: axis from the largest diagonal entry of (R + I)/2 = a a^T
+    A = 0.5 * (R + np.eye(3))
+    i = int(np.argmax(np.diag(A)))
+    a = A[:, i] / np.sqrt(max(A[i, i], 1e-300))
+    return a * th
+
+
 def project(model: str | int, prm: np.ndarray, P: np.ndarray) -> np.ndarray:
     """numpy projection of camera-frame points P (…,3) with FULL parameter vector prm. Returns (…,2)."""
     m = MODELS[model] if isinstance(model, str) else int(model)

@@ -33,6 +33,12 @@ def test_model_nparams_and_bounds(pkg):
     lo, hi = pkg.model_bounds("eucm", 1024, 768)
     assert (lo[0], hi[0], hi[2], hi[3]) == (0.0, 1e4, 1024.0, 768.0)   # util.rs:36-39
     assert 0 < lo[4] < hi[4] <= 1.0
+    import numpy as np
+    for m in ("kb4", "opencv5", "ftheta"):      # polynomial coefficients are not boxed (no invented [-1, 1] clamp)
+        lo, hi = pkg.model_bounds(m, 1024, 768)
+        assert np.all(np.isneginf(lo[4:])) and np.all(np.isposinf(hi[4:]))
+    lo, hi = pkg.model_bounds("eucmt", 1024, 768)
+    assert np.all(np.isinf(lo[6:])) and np.all(np.isinf(hi[6:])) and hi[4] == 1.0
 
 
 def test_default_options_are_tiny_solver_defaults(pkg):

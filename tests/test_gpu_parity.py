@@ -212,6 +212,24 @@ def test_bounds_and_fixed_variables(pkg, oracle):
     gp.close()
 
 
+def test_polynomial_coefficients_are_not_clamped(pkg, oracle):
+    """A lens whose distortion coefficient exceeds 1 (real wide-angle KB4 / plumb-bob lenses do) must calibrate to that
+    value under the model's own bounds: only alpha / beta of the unified models are boxed, polynomial coefficients are
+    not (no invented [-1, 1] clamp)."""
+    gt = np.array([380.0, 380.0, 512.0, 512.0, 1.5, -0.3, 0.05, -0.004])
+    s = pkg.synth.make_calib("kb4", 60, seed=11, gt_params=gt)
+    op = oracle.OracleProblem.from_synth(s, pkg.MODELS["kb4"])
+    lo, hi = pkg.model_bounds("kb4", s.width, s.height)
+    assert np.all(np.isinf(lo[4:])) and np.all(np.isinf(hi[4:]))
+    with pkg.Problem.from_synth(s) as gp:
+        gp.set_poses(s.init_poses)
+        intr, summ, _ = gp.solve_gn(s.init_params, lo, hi)
+        ref, _, res, _ = op.gauss_newton(s.init_params, s.init_poses, lo, hi)
+        assert summ.status == 0 and summ.iterations == res.iterations
+        assert np.max(np.abs(intr - ref) / np.abs(ref)) < TOL_INTR
+        assert abs(intr[4] - 1.5) < 1e-4 and np.max(np.abs(intr - gt) / np.abs(gt)) < 1e-3
+
+
 def test_batch_equals_independent_problems(pkg, oracle):
     """BASELINE config 5 in miniature: a batch of independent KB4 calibrations in one handle."""
     probs = [pkg.synth.make_calib("kb4", nf, seed=20 + i, drop_fraction=0.1) for i, nf in enumerate([12, 30, 7, 21])]
