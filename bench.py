@@ -419,33 +419,46 @@ def run_ours(args):
         del sw, shw
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------------------
-    # the reference's FeaturePoint holds f32 (src/detected_points.rs:6-9): the f32 entry point is the natural host format
+    # Host data = what the reference holds (src/detected_points.rs:6-17): f32 p2d per detected corner keyed by corner id,
+    # p3d = the board point of that id (src/board.rs:46-95). Two host formats are timed: `board` (corner ids + board table,
+    # ccrs_problem_create_board_f32: 12 B per observation over PCIe) is the headline; `xyz` (x, y, z, u, v f32 arrays,
+    # ccrs_problem_create_f32: 20 B per observation) is the format of round 1.
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    a0, b0 = int(s.frame_offsets[lo]), int(s.frame_offsets[hi])
     hx, _tx = pinned(f32(sh["x"])); hy, _ty = pinned(f32(sh["y"])); hz, _tz = pinned(f32(sh["z"])); hu, _tu = pinned(f32(sh["u"])); hv, _tv = pinned(f32(sh["v"]))
+    hid, _ti = pinned(np.ascontiguousarray(s.extra["corner_id"][a0:b0], dtype=np.int32))
+    hboard = np.ascontiguousarray(s.extra["board"], dtype=np.float32)
     hfo, _tf = pinned(sh["frame_offsets"]); hp, _tp = pinned(poses0)
-    h2d = hx.nbytes * 5 + hfo.nbytes + hp.nbytes
-    d2h = hp.nbytes + d * 8
     e2e_steps = max(3, min(args.steps, 10))
-    evals = 0
-    e2e_times = []
-    for i in range(2 + e2e_steps):
-        R.barrier()
-        t0 = time.perf_counter()
-        q = pkg.Problem(MODEL, s.width, s.height, hfo, hx, hy, hz, hu, hv, device=dev)
-        if world > 1:
-            q.comm_init(None)
-        q.set_poses(hp)
-        intr, summ, _ = q.solve_lm(s.init_params)
-        out_poses = q.get_poses()
-        n_lin = 1 + summ.iterations          # initial linearisation + one (speculative) per iteration
-        d2h_iter = summ.iterations * (prob.nout + 2) * 8
-        q.close()
-        R.barrier()
-        if i >= 2:
-            e2e_times.append(time.perf_counter() - t0)
-            evals += n_total * n_lin
-    e2e_total = R.max(float(np.sum(e2e_times)))
-    e2e_value = evals / e2e_total
+
+    def e2e_run(fmt):
+        evals, times = 0, []
+        for i in range(2 + e2e_steps):
+            R.barrier()
+            t0 = time.perf_counter()
+            if fmt == "board":
+                q = pkg.Problem(MODEL, s.width, s.height, hfo, None, None, None, hu, hv, device=dev, corner_id=hid, board=hboard)
+            else:
+                q = pkg.Problem(MODEL, s.width, s.height, hfo, hx, hy, hz, hu, hv, device=dev)
+            if world > 1:
+                q.comm_init(None)
+            q.set_poses(hp)
+            intr, summ, _ = q.solve_lm(s.init_params)
+            out_poses = q.get_poses()
+            q.close()
+            R.barrier()
+            if i >= 2:
+                times.append(time.perf_counter() - t0)
+                evals += n_total * (1 + summ.iterations)     # initial linearisation + one (speculative) per iteration
+        total = R.max(float(np.sum(times)))
+        return evals / total, total / e2e_steps * 1e3, intr, summ
+
+    e2e_value, e2e_ms, intr, summ = e2e_run("board")
+    e2e_xyz_value, e2e_xyz_ms, _, _ = e2e_run("xyz")
+    h2d = hid.nbytes + hu.nbytes + hv.nbytes + hboard.nbytes + hfo.nbytes + hp.nbytes
+    h2d_xyz = hx.nbytes * 5 + hfo.nbytes + hp.nbytes
+    d2h = hp.nbytes + d * 8
+    d2h_iter = (summ.iterations + 1) * 192 * 8          # one iteration record per executed reduction
     rel_err = float(np.max(np.abs(intr - s.gt_params) / np.abs(s.gt_params)))
     prob.close()
 
@@ -478,9 +491,11 @@ def run_ours(args):
                                 "what": "ccrs_solve_gn (the loop the reference runs, util.rs:443-458), stop tests disabled, 20 iterations, CUDA events around the whole loop"},
             "wall_ms_timed_region_incl_flush": wall_ms,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h + d2h_iter),
-                    "ms_per_call": e2e_total / e2e_steps * 1e3, "lm_iterations_per_call": int(summ.iterations),
-                    "what": "ccrs_problem_create_f32 (H2D of the f32 FeaturePoint arrays from pinned memory) + set_poses + ccrs_solve_lm to convergence + get_poses (D2H) + destroy",
-                    "converged_rel_err_vs_gt": rel_err},
+                    "ms_per_call": e2e_ms, "lm_iterations_per_call": int(summ.iterations),
+                    "what": "ccrs_problem_create_board_f32 (H2D from pinned memory of corner ids + f32 p2d + the board table: the reference's FrameFeature / Board data model) + set_poses + ccrs_solve_lm to convergence + get_poses (D2H) + destroy",
+                    "converged_rel_err_vs_gt": rel_err,
+                    "xyz_f32_format": {"value": e2e_xyz_value, "ms_per_call": e2e_xyz_ms, "h2d_bytes_per_step": int(h2d_xyz),
+                                       "what": "same call sequence through ccrs_problem_create_f32 (x, y, z, u, v f32 arrays: round 1's format)"}},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         }
         if weak is not None:

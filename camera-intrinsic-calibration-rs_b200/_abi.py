@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("CCRS_B200_LIB") or os.path.join(_HERE, "libccrs_b200.
 
 # every symbol include/ccrs_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
-    "ccrs_model_nparams", "ccrs_last_error", "ccrs_problem_create", "ccrs_problem_create_f32", "ccrs_batch_create", "ccrs_problem_destroy", "ccrs_release_cached_memory",
+    "ccrs_model_nparams", "ccrs_last_error", "ccrs_problem_create", "ccrs_problem_create_f32", "ccrs_problem_create_board_f32", "ccrs_batch_create", "ccrs_problem_destroy", "ccrs_release_cached_memory",
     "ccrs_problem_dim", "ccrs_problem_nblk", "ccrs_problem_n_frames", "ccrs_problem_n_obs", "ccrs_problem_n_problems",
     "ccrs_set_poses", "ccrs_get_poses", "ccrs_eval_rj", "ccrs_validation", "ccrs_linearize", "ccrs_get_frame_blocks",
     "ccrs_compute_scale", "ccrs_set_intr_scale", "ccrs_reduce", "ccrs_backsub", "ccrs_eval_cost", "ccrs_accept",
@@ -89,6 +89,8 @@ def load():
     _fp = C.POINTER(C.c_float)
     lib.ccrs_problem_create_f32.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip,
                                             _fp, _fp, _fp, _fp, _fp, C.c_double, C.c_int]
+    lib.ccrs_problem_create_board_f32.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip,
+                                                  _fp, _fp, _fp, C.c_int, C.c_double, C.c_int]
     lib.ccrs_batch_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, C.c_int, _ip,
                                       _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_int]
     lib.ccrs_problem_destroy.argtypes = [vp]

@@ -14,6 +14,7 @@ initialisation is outside the accelerated path.
 from __future__ import annotations
 
 import ctypes as C
+import sys
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -75,10 +76,27 @@ class Problem:
     """One device-resident calibration problem (or a batch of independent ones)."""
 
     def __init__(self, model, width: int, height: int, frame_offsets, x, y, z, u, v, xy_same_focal: bool = False,
-                 huber_delta: float = 1.0, device: int = 0, problem_frame_offsets=None):
+                 huber_delta: float = 1.0, device: int = 0, problem_frame_offsets=None, corner_id=None, board=None):
+        """corner_id / board: the reference's own data model (FrameFeature.features: corner id -> FeaturePoint whose
+        p3d is the board point of that id): x, y, z are then ignored (pass None) and p3d = board[corner_id]."""
         self.lib = _abi.load()
         self.model = MODELS[model] if isinstance(model, str) else int(model)
         fo = np.ascontiguousarray(frame_offsets, dtype=np.int32)
+        if corner_id is not None:
+            ids = np.ascontiguousarray(corner_id, dtype=np.int32)
+            bd = np.ascontiguousarray(board, dtype=np.float32).reshape(-1, 3)
+            us, vs = (np.ascontiguousarray(a, dtype=np.float32) for a in (u, v))
+            n = int(fo[-1])
+            if ids.shape != (n,) or us.shape != (n,) or vs.shape != (n,):
+                raise ValueError("corner_id, u, v must have frame_offsets[-1] entries")
+            self.h = C.c_void_p()
+            fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+            ip = C.POINTER(C.c_int32)
+            check(self.lib.ccrs_problem_create_board_f32(C.byref(self.h), self.model, width, height, int(xy_same_focal), len(fo) - 1,
+                                                         fo.ctypes.data_as(ip), ids.ctypes.data_as(ip), fp(us), fp(vs), fp(bd),
+                                                         len(bd), float(huber_delta), int(device)))
+            self._finish_init()
+            return
         f32 = all(isinstance(a, np.ndarray) and a.dtype == np.float32 for a in (x, y, z, u, v)) and problem_frame_offsets is None
         conv = (lambda a: np.ascontiguousarray(a, dtype=np.float32)) if f32 else _f64
         xs, ys, zs, us, vs = map(conv, (x, y, z, u, v))
@@ -102,6 +120,9 @@ class Problem:
             check(self.lib.ccrs_batch_create(C.byref(self.h), self.model, width, height, int(xy_same_focal),
                                              len(pfo) - 1, pfo.ctypes.data_as(ip), len(fo) - 1, fo.ctypes.data_as(ip),
                                              _dp(xs), _dp(ys), _dp(zs), _dp(us), _dp(vs), float(huber_delta), int(device)))
+        self._finish_init()
+
+    def _finish_init(self):
         self.d = self.lib.ccrs_problem_dim(self.h)
         self.nblk = self.lib.ccrs_problem_nblk(self.h)
         self.n_frames = self.lib.ccrs_problem_n_frames(self.h)
@@ -120,10 +141,9 @@ class Problem:
 
     def __del__(self):
         # never call into CUDA while the interpreter is shutting down (the runtime may already be tearing down)
-        import sys
-        if sys is None or sys.is_finalizing():
-            return
         try:
+            if sys is None or sys.is_finalizing():
+                return
             self.close()
         except Exception:
             pass
@@ -472,10 +492,9 @@ class JointProblem:
             self.h = None
 
     def __del__(self):
-        import sys
-        if sys is None or sys.is_finalizing():
-            return
         try:
+            if sys is None or sys.is_finalizing():
+                return
             self.close()
         except Exception:
             pass

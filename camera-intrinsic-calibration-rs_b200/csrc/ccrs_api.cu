@@ -178,6 +178,11 @@ struct ccrs_problem {
   int64_t launches = 0;
 
   DevBuf<double> x, y, z, u, v;
+  DevBuf<int32_t> corner_id;      // board-format problems: corner id of every observation (expanded to x, y, z on the device)
+  DevBuf<float> board_dev;        // ... and the board table [n_board][3]
+  const int32_t* h_corner_id = nullptr;   // set by ccrs_problem_create_board_f32 for the duration of the upload
+  const float* h_board = nullptr;
+  int n_board = 0;
   DevBuf<int32_t> frame_offsets, frame_problem, problem_frame_offsets, obs_frame, cur, acc_to_blk;
   DevBuf<double> poses[2], blocks[2], frame_cost[2];
   DevBuf<double> elim, frame_red, pose_scale, frame_md, cta_part;
@@ -188,6 +193,8 @@ struct ccrs_problem {
   DevBuf<double> red_out, stat_out, gather, intr_dev, ya_dev, u_dev, scale_dev, l2_flush;
   DevBuf<double> ctl_dev;         // LoopCtl of the device-driven loop (single problem)
   DevBuf<double> s2_part;         // K3 (k_schur2) per-CTA partials [n_ctas][NRED]: self-validating slots, armed
+  DevBuf<double> bctl_dev, hist_dev;   // batch: per-problem controller state (BatchCtl), error history of problem 0
+  PinBuf<double> h_bctl, h_bstatus;    // batch: staging of the controller state; mapped status ring [kRecSlots][2]
   PinBuf<double> h_rec, h_ctl;    // mapped: record ring [kRecSlots][kRecStride]; staging copy of the control block
   double h_scale[9] = {1, 1, 1, 1, 1, 1, 1, 1, 1};   // host copy of the Jacobi scaling of the intrinsic columns (single problem)
   long loop_records = 0;          // records consumed from the ring since creation
@@ -283,17 +290,32 @@ int upload_problem(ccrs_problem* p, int n_problems, const int32_t* problem_frame
   const size_t esz = p->f32 ? 4 : 8, nel = p->f32 ? (N + 1) / 2 : N;   // floats are packed into the double-typed buffers
   CK(p->x.alloc(nel)); CK(p->y.alloc(nel)); CK(p->z.alloc(nel)); CK(p->u.alloc(nel)); CK(p->v.alloc(nel));
   // start the big copies first so everything below overlaps with them
-  CK(cudaMemcpyAsync(p->x.p, x, N * esz, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(p->y.p, y, N * esz, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(p->z.p, z, N * esz, cudaMemcpyHostToDevice, s));
+  if (p->h_corner_id) {
+    // board format: 12 bytes per observation cross PCIe (corner id, u, v) instead of 20; p3d = board[id] is expanded
+    // into the f32 x, y, z arrays by one small kernel, so the linearisation kernels see the usual layout
+    CK(p->corner_id.alloc(N)); CK(p->board_dev.alloc((size_t)3 * p->n_board));
+    CK(cudaMemcpyAsync(p->board_dev.p, p->h_board, (size_t)3 * p->n_board * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->corner_id.p, p->h_corner_id, N * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    // the ids are range-checked where they are expanded (a host pass over a million ids would cost more than the
+    // transfer saves): the kernel raises a flag in mapped host memory, read after the upload's final synchronise
+    CK(p->h_colsq.alloc(P * p->D + 1));
+    p->h_colsq.p[0] = 0.0;
+    CK(launch_expand_board(p->corner_id.p, p->board_dev.p, p->n_board, (int64_t)N, reinterpret_cast<float*>(p->x.p),
+                           reinterpret_cast<float*>(p->y.p), reinterpret_cast<float*>(p->z.p), p->h_colsq.p, s));
+    p->launches++;
+  } else {
+    CK(cudaMemcpyAsync(p->x.p, x, N * esz, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->y.p, y, N * esz, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->z.p, z, N * esz, cudaMemcpyHostToDevice, s));
+  }
   CK(cudaMemcpyAsync(p->u.p, u, N * esz, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(p->v.p, v, N * esz, cudaMemcpyHostToDevice, s));
   CK(p->frame_offsets.alloc(F + 1));
   CK(p->problem_frame_offsets.alloc(P + 1));
   CK(p->cur.alloc(P));
   CK(p->acc_to_blk.alloc(p->NACC));
-  CK(p->tickets.alloc(2));
-  CK(cudaMemsetAsync(p->tickets.p, 0, 2 * sizeof(unsigned int), s));
+  CK(p->tickets.alloc(4));        // [0] K2 statistics, [1] K3 reduction, [2] batch: active problems, [3] batch: status ticket
+  CK(cudaMemsetAsync(p->tickets.p, 0, 4 * sizeof(unsigned int), s));
   for (int i = 0; i < 2; ++i) {
     CK(p->poses[i].alloc(F * 6));
     CK(p->blocks[i].alloc((size_t)p->NBLK * Fs));
@@ -311,7 +333,8 @@ int upload_problem(ccrs_problem* p, int n_problems, const int32_t* problem_frame
   CK(p->stat_out.alloc(P * 2));
   CK(p->intr_dev.alloc(P * p->D)); CK(p->ya_dev.alloc(P * p->D)); CK(p->u_dev.alloc(P)); CK(p->scale_dev.alloc(P * p->D));
   CK(p->mask_dev.alloc(P));
-  CK(p->h_red.alloc(2 * (P * p->NRED + 1))); CK(p->h_stat.alloc(P * 2 + 2)); CK(p->h_colsq.alloc(P * p->D));
+  CK(p->h_red.alloc(2 * (P * p->NRED + 1))); CK(p->h_stat.alloc(P * 2 + 2));
+  if (!p->h_colsq.p) CK(p->h_colsq.alloc(P * p->D + 1));
   if (!p->batch) {
     CK(p->ctl_dev.alloc(sizeof(LoopCtl) / 8)); CK(p->h_ctl.alloc(sizeof(LoopCtl) / 8));
     CK(p->h_rec.alloc((size_t)kRecSlots * kRecStride));
@@ -336,6 +359,7 @@ int upload_problem(ccrs_problem* p, int n_problems, const int32_t* problem_frame
     CK(cudaMemcpyAsync(p->frame_problem.p, fp.data(), F * 4, cudaMemcpyHostToDevice, s));
   }
   CK(cudaStreamSynchronize(s));
+  if (p->h_corner_id && p->h_colsq.p[0] != 0.0) return fail(CCRS_ERR_INVALID, "a corner id lies outside the board table (%d corners)", p->n_board);
   return 0;
 }
 
@@ -360,9 +384,13 @@ struct DevInfo { bool known = false; int major = 0, minor = 0, sms = 0; } g_dev_
 int create_common(ccrs_problem** out, int model, int width, int height, int xy_same_focal, int n_problems,
                   const int32_t* problem_frame_offsets, int n_frames, const int32_t* frame_offsets, const void* x,
                   const void* y, const void* z, const void* u, const void* v, double huber_delta, int device_id,
-                  bool batch, bool f32 = false) {
-  if (!out || !frame_offsets || !x || !y || !z || !u || !v || n_frames <= 0 || n_problems <= 0)
+                  bool batch, bool f32 = false, const int32_t* corner_id = nullptr, const float* board = nullptr, int n_board = 0) {
+  if (!out || !frame_offsets || !u || !v || n_frames <= 0 || n_problems <= 0 || (!corner_id && (!x || !y || !z)))
     return fail(CCRS_ERR_INVALID, "null pointer or empty problem");
+  if (frame_offsets[0] != 0) return fail(CCRS_ERR_INVALID, "frame_offsets[0] must be 0");
+  for (int f = 0; f < n_frames; ++f)
+    if (frame_offsets[f + 1] == frame_offsets[f]) return fail(CCRS_ERR_INVALID, "frame %d has no observations (drop it: its pose block would be singular)", f);
+  if (corner_id && (!board || n_board <= 0)) return fail(CCRS_ERR_INVALID, "board table missing");
   if (model < 0 || model > 5) return fail(CCRS_ERR_INVALID, "unknown model %d", model);
   for (int f = 0; f < n_frames; ++f)
     if (frame_offsets[f + 1] < frame_offsets[f]) return fail(CCRS_ERR_INVALID, "frame_offsets not monotone at %d", f);
@@ -384,12 +412,14 @@ int create_common(ccrs_problem** out, int model, int width, int height, int xy_s
   ccrs_problem* p = new ccrs_problem();
   p->model = model; p->width = width; p->height = height; p->one_focal = xy_same_focal ? 1 : 0;
   p->huber = huber_delta; p->device = device_id; p->batch = batch; p->n_sms = di.sms; p->f32 = f32;
+  p->h_corner_id = corner_id; p->h_board = board; p->n_board = n_board;
   model_dims(model, p->one_focal, &p->D, &p->NA, &p->NBLK, &p->NACC);
   p->NRED = nred_of(p->D);
   p->NOUT = p->D * p->D + 3 * p->D + 1;
   cudaError_t e = get_stream(device_id, &p->stream);
   if (e != cudaSuccess) { delete p; return fail(CCRS_ERR_CUDA, "stream: %s", cudaGetErrorString(e)); }
   int st = upload_problem(p, n_problems, problem_frame_offsets, n_frames, frame_offsets, x, y, z, u, v);
+  p->h_corner_id = nullptr; p->h_board = nullptr;   // caller-owned: not retained
   if (st != 0) { ccrs_problem_destroy(p); return st; }
   *out = p;
   return 0;
@@ -965,6 +995,157 @@ int run_device_loop(ccrs_problem* p, bool lm, double* intr, const double* lo, co
   return sum->status;
 }
 
+
+// ---- device-driven loop for a batch of independent problems ----------------------------------------------------------
+// Per iteration the host enqueues K3, k_batch_solve, K2, k_batch_decide (GN: K2, K3, k_batch_solve) and reads one
+// number — the count of still-active problems — from a mapped status ring; every per-problem decision (ccrs_rule.h)
+// is taken by the two controller kernels, which write straight into the arrays K2 / K3 read.
+bool batch_loop_ok(const ccrs_problem* p, bool lm, const ccrs_options& opt) {
+  if (!g_device_loop || !p->batch || p->comm) return false;
+  if (lm && !opt.speculative) return false;
+  if (!lm && opt.block_huber_delta > 0.0) return false;
+  return true;
+}
+
+int batch_launch_k2(ccrs_problem* p, int which, int backsub, bool use_pose_scale) {
+  LinParams prm{};
+  prm.pb = p->dev();
+  prm.which = which; prm.G = p->G; prm.FPW = p->FPW;
+  prm.acc_to_blk = p->acc_to_blk.p;
+  prm.backsub = backsub;
+  prm.elim = p->elim.p;
+  prm.pose_scale = use_pose_scale ? p->pose_scale.p : nullptr;
+  prm.ya_dev = p->ya_dev.p; prm.u_dev = p->u_dev.p;
+  prm.active = p->mask_dev.p;
+  prm.frame_md = p->frame_md.p;
+  prm.intr_dev = p->intr_dev.p;
+  CK(launch_linearize(p->model, p->one_focal, true, false, prm, p->n_lin_ctas, p->stream));
+  p->launches++;
+  return 0;
+}
+
+int batch_launch_k3(ccrs_problem* p, bool lm, const ccrs_options& opt) {
+  SchurParams prm{};
+  prm.pb = p->dev();
+  prm.which = 0;
+  prm.intr_scale = lm ? p->scale_dev.p : nullptr;
+  prm.pose_scale = lm ? p->pose_scale.p : nullptr;
+  prm.min_diag = opt.lm_min_diag; prm.max_diag = opt.lm_max_diag;
+  prm.no_pose = p->fixed_poses ? 1 : 0;
+  prm.active = p->mask_dev.p;
+  prm.elim = p->elim.p;
+  prm.frame_red = p->frame_red.p;
+  prm.u_dev = p->u_dev.p;
+  p->last_use_scale = lm;
+  CK(launch_schur(p->D, prm, p->stream));
+  p->launches++;
+  return 0;
+}
+
+int run_batch_loop(ccrs_problem* p, bool lm, double* intr, const double* lo, const double* hi, const unsigned char* fixed,
+                   const ccrs_options& opt, ccrs_summary* sum, double* err_hist) {
+  std::memset(sum, 0, sizeof(*sum));
+  const int P = p->n_problems, D = p->D;
+  if (opt.max_iteration <= 0) return 0;
+  int st = flush_pending(p);
+  if (st) return st;
+  p->spec.valid = false;
+  constexpr size_t kCtlWords = sizeof(BatchCtl) / 8;
+  if (!p->bctl_dev.p) {
+    CK(p->bctl_dev.alloc((size_t)P * kCtlWords)); CK(p->h_bctl.alloc((size_t)P * kCtlWords));
+    CK(p->h_bstatus.alloc((size_t)kRecSlots * 2));
+  }
+  const bool want_hist = err_hist && opt.max_iteration <= (1 << 20);
+  if (want_hist) { p->hist_dev.release(); CK(p->hist_dev.alloc((size_t)opt.max_iteration)); }
+  // ---- start: linearise the start point; LM: Jacobi scaling from that linearisation (one-time, host-assisted)
+  std::vector<unsigned char> ones((size_t)P, 1);
+  CK(cudaMemcpyAsync(p->mask_dev.p, ones.data(), (size_t)P, cudaMemcpyHostToDevice, p->stream));
+  CK(cudaMemsetAsync(p->u_dev.p, 0, (size_t)P * 8, p->stream));
+  st = upload_intr(p, intr);
+  if (!st) st = batch_launch_k2(p, 0, 0, false);
+  if (st) return st;
+  std::vector<double> scale((size_t)P * D, 1.0);
+  if (lm) {
+    std::vector<double> colsq((size_t)P * D);
+    st = ccrs_compute_scale(p, 0, colsq.data());
+    if (st) return st;
+    for (size_t i = 0; i < scale.size(); ++i) scale[i] = 1.0 / (1.0 + std::sqrt(colsq[i]));
+    st = ccrs_set_intr_scale(p, scale.data());
+    if (st) return st;
+  }
+  BatchCtl* hc = reinterpret_cast<BatchCtl*>(p->h_bctl.p);
+  std::vector<double> u0((size_t)P, lm ? 1.0 / opt.lm_initial_radius : 0.0);
+  for (int q = 0; q < P; ++q) {
+    BatchCtl& c = hc[q];
+    std::memset(&c, 0, sizeof(c));
+    c.u = u0[q]; c.v = ccrs_rule::kLmRejectFactor0; c.active = 1;
+    for (int i = 0; i < D; ++i) { c.intr[i] = c.trial[i] = intr[(size_t)q * D + i]; c.scale[i] = scale[(size_t)q * D + i]; }
+  }
+  CK(cudaMemcpyAsync(p->bctl_dev.p, hc, (size_t)P * sizeof(BatchCtl), cudaMemcpyHostToDevice, p->stream));
+  CK(cudaMemcpyAsync(p->u_dev.p, u0.data(), (size_t)P * 8, cudaMemcpyHostToDevice, p->stream));
+  CK(cudaMemsetAsync(p->tickets.p + 2, 0, 2 * sizeof(unsigned int), p->stream));
+  CK(cudaStreamSynchronize(p->stream));   // the staging vectors above are pageable / reused
+  arm_payload(p->h_bstatus.p, kRecSlots * 2);
+  BatchRuleParams rp{};
+  rp.pb = p->dev();
+  rp.ctl = reinterpret_cast<BatchCtl*>(p->bctl_dev.p);
+  rp.lm = lm ? 1 : 0; rp.D = D; rp.NRED = p->NRED; rp.max_iteration = opt.max_iteration; rp.fixed_mode = opt.fixed_mode;
+  rp.has_bounds = (lo && hi) ? 1 : 0; rp.has_fixed = fixed ? 1 : 0; rp.rr_idx = p->NBLK - 1;
+  rp.min_abs = opt.min_abs_decrease; rp.min_rel = opt.min_rel_decrease; rp.min_error = opt.min_error;
+  rp.min_diag = opt.lm_min_diag; rp.max_diag = opt.lm_max_diag;
+  for (int i = 0; i < D; ++i) { rp.lo[i] = rp.has_bounds ? lo[i] : 0.0; rp.hi[i] = rp.has_bounds ? hi[i] : 0.0; rp.fixed[i] = fixed ? fixed[i] : 0; }
+  rp.frame_red = p->frame_red.p; rp.frame_md = p->frame_md.p;
+  rp.intr_dev = p->intr_dev.p; rp.ya_dev = p->ya_dev.p; rp.u_dev = p->u_dev.p; rp.cur = p->cur.p; rp.active = p->mask_dev.p;
+  rp.n_active = p->tickets.p + 2; rp.ticket = p->tickets.p + 3;
+  rp.host_status = p->h_bstatus.p;
+  rp.err_hist0 = want_hist ? p->hist_dev.p : nullptr;
+  // ---- the loop: enqueue ahead, read one status word pair per iteration
+  long enq = 0, got = 0;
+  bool done = false;
+  auto enqueue = [&]() -> int {
+    int s2 = 0;
+    rp.seq = (int)(enq + 1);
+    if (lm) {
+      s2 = batch_launch_k3(p, true, opt);
+      if (!s2) { CK(launch_batch_solve(rp, p->stream)); p->launches++; s2 = batch_launch_k2(p, 1, 1, true); }
+      if (!s2) { CK(launch_batch_decide(rp, p->stream)); p->launches++; }
+    } else {
+      if (enq > 0) s2 = batch_launch_k2(p, 0, 2, false);   // apply the step in place and linearise there
+      if (!s2) s2 = batch_launch_k3(p, false, opt);
+      if (!s2) { CK(launch_batch_solve(rp, p->stream)); p->launches++; }
+    }
+    ++enq;
+    return s2;
+  };
+  while (!st && !done) {
+    while (!st && enq - got < g_loop_ahead && enq <= opt.max_iteration) st = enqueue();
+    if (st) break;
+    volatile double* slot = p->h_bstatus.p + (size_t)(got % kRecSlots) * 2;
+    st = wait_payload(p, slot, 2);
+    if (st) break;
+    const double n_active = slot[1];
+    arm_payload(slot, 2);
+    ++got;
+    if (n_active == 0.0 || got > opt.max_iteration) done = true;
+  }
+  if (st) { cudaStreamSynchronize(p->stream); sum->status = st; return st; }
+  CK(cudaMemcpyAsync(hc, p->bctl_dev.p, (size_t)P * sizeof(BatchCtl), cudaMemcpyDeviceToHost, p->stream));
+  std::vector<double> hist;
+  if (want_hist) { hist.resize((size_t)opt.max_iteration); CK(cudaMemcpyAsync(hist.data(), p->hist_dev.p, hist.size() * 8, cudaMemcpyDeviceToHost, p->stream)); }
+  CK(cudaStreamSynchronize(p->stream));
+  int worst = 0, iters = 0;
+  for (int q = 0; q < P; ++q) {
+    const BatchCtl& c = hc[q];
+    for (int i = 0; i < D; ++i) intr[(size_t)q * D + i] = c.intr[i];
+    if (c.status != 0) worst = c.status;
+    iters = std::max(iters, c.iterations);
+  }
+  sum->iterations = iters; sum->status = worst; sum->stop_reason = hc[0].stop; sum->final_error = hc[0].final_err;
+  sum->n_accepted = hc[0].n_acc; sum->n_rejected = hc[0].n_rej;
+  if (want_hist) for (int i = 0; i < hc[0].iterations && i < opt.max_iteration; ++i) err_hist[i] = hist[i];
+  return worst;
+}
+
 }  // namespace
 
 extern "C" {
@@ -991,6 +1172,13 @@ int ccrs_problem_create_f32(ccrs_problem** out, int model, int width, int height
                        huber_delta, device_id, false, true);
 }
 
+int ccrs_problem_create_board_f32(ccrs_problem** out, int model, int width, int height, int xy_same_focal, int n_frames,
+                                  const int32_t* frame_offsets, const int32_t* corner_id, const float* u, const float* v,
+                                  const float* board_xyz, int n_board, double huber_delta, int device_id) {
+  return create_common(out, model, width, height, xy_same_focal, 1, nullptr, n_frames, frame_offsets, nullptr, nullptr, nullptr,
+                       u, v, huber_delta, device_id, false, true, corner_id, board_xyz, n_board);
+}
+
 int ccrs_batch_create(ccrs_problem** out, int model, int width, int height, int xy_same_focal, int n_problems,
                       const int32_t* problem_frame_offsets, int n_frames, const int32_t* frame_offsets, const double* x,
                       const double* y, const double* z, const double* u, const double* v, double huber_delta,
@@ -1006,6 +1194,7 @@ int ccrs_problem_destroy(ccrs_problem* p) {
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   p->x.release(); p->y.release(); p->z.release(); p->u.release(); p->v.release();
+  p->corner_id.release(); p->board_dev.release();
   p->frame_offsets.release(); p->frame_problem.release(); p->problem_frame_offsets.release(); p->obs_frame.release();
   p->cur.release(); p->acc_to_blk.release(); p->tickets.release();
   for (int i = 0; i < 2; ++i) { p->poses[i].release(); p->blocks[i].release(); p->frame_cost[i].release(); }
@@ -1014,6 +1203,7 @@ int ccrs_problem_destroy(ccrs_problem* p) {
   p->u_dev.release(); p->scale_dev.release(); p->l2_flush.release(); p->mask_dev.release();
   p->h_red.release(); p->h_stat.release(); p->h_colsq.release();
   p->ctl_dev.release(); p->h_rec.release(); p->h_ctl.release(); p->s2_part.release();
+  p->bctl_dev.release(); p->hist_dev.release(); p->h_bctl.release(); p->h_bstatus.release();
   if (p->stream) put_stream(p->device, p->stream);
   delete p;
   return 0;
@@ -1465,6 +1655,7 @@ static int timed_solve(ccrs_problem* p, bool lm, double* intr, const double* lo,
   if (opt) o = *opt; else ccrs_default_options(&o);
   int st;
   if (device_loop_ok(p, lm, o)) st = run_device_loop(p, lm, intr, lo, hi, fixed, o, summary, err_hist);
+  else if (batch_loop_ok(p, lm, o)) st = run_batch_loop(p, lm, intr, lo, hi, fixed, o, summary, err_hist);
   else st = lm ? ccrs_controller_lm(&be, intr, lo, hi, fixed, opt, summary, err_hist)
                : ccrs_controller_gn(&be, intr, lo, hi, fixed, opt, summary, err_hist);
   cudaEventRecord(e1, p->stream);

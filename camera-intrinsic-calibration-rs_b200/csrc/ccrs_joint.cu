@@ -340,12 +340,23 @@ __global__ void __launch_bounds__(32 * kJSchurWarps) k_joint_schur(JointDev jd, 
 }
 
 // out[v] = sum_f fs[f][v], f ascending (fixed order)
-__global__ void k_joint_sum(const double* __restrict__ fs, int F, int NV, double* __restrict__ out) {
+// out[v] = sum over frames (frame order: deterministic), eight loads in flight; published straight to mapped host memory
+// (host_out: the host armed the NV words with a sentinel and spins until all of them changed — no memcpy, no sync)
+__global__ void k_joint_sum(const double* __restrict__ fs, int F, int NV, double* __restrict__ out, volatile double* host_out) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= NV) return;
   double s = 0.0;
-  for (int f = 0; f < F; ++f) s += fs[(size_t)f * NV + v];
+  int f = 0;
+  for (; f + 8 <= F; f += 8) {
+    double t[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t[q] = fs[(size_t)(f + q) * NV + v];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += t[q];
+  }
+  for (; f < F; ++f) s += fs[(size_t)f * NV + v];
   out[v] = s;
+  if (host_out) host_out[v] = s;
 }
 
 // one warp per frame: lane (i, part) sums a strided part of row i of X y; five lanes per row, fixed combine order
@@ -396,6 +407,9 @@ struct ccrs_joint {
   int32_t *frame_block_offsets = nullptr, *frame_blocks = nullptr;
   uint16_t* ij_table = nullptr;
   double *intr = nullptr, *extr = nullptr, *poses = nullptr, *jblk = nullptr, *fs = nullptr, *el = nullptr, *red = nullptr, *ydev = nullptr;
+  double* state_dev = nullptr;    // [C*d | C*6 | M] = intr | extr | y: one allocation, one copy per iteration
+  double* h_state = nullptr;      // pinned staging of the same layout
+  double* h_red = nullptr;        // mapped pinned [NS + M + 1]: the reduced system, published by k_joint_sum
   int64_t launches = 0;
 
   template <class T> cudaError_t alloc(T** p, size_t n) {
@@ -415,14 +429,45 @@ struct ccrs_joint {
 };
 
 namespace {
-int upload_state(ccrs_joint* p, const double* intr, const double* extr, const double* poses) {
-  JCK(cudaMemcpyAsync(p->intr, intr, (size_t)p->n_cams * p->d * 8, cudaMemcpyHostToDevice, p->stream));
-  std::vector<double> e(extr, extr + (size_t)p->n_cams * 6);
-  for (int i = 0; i < 6; ++i) e[i] = 0.0;   // cam0 is the reference frame (util.rs:689-690)
-  JCK(cudaMemcpyAsync(p->extr, e.data(), e.size() * 8, cudaMemcpyHostToDevice, p->stream));
-  if (poses) JCK(cudaMemcpyAsync(p->poses, poses, (size_t)p->n_frames * 48, cudaMemcpyHostToDevice, p->stream));
-  JCK(cudaStreamSynchronize(p->stream));
+// intr | extr (| y) go to the device as ONE asynchronous copy from pinned staging; no synchronisation (the staging buffer
+// is rewritten only after the host has seen the next reduced system, i.e. after this copy has been consumed)
+int upload_state(ccrs_joint* p, const double* intr, const double* extr, const double* poses, const double* y = nullptr) {
+  const size_t ni = (size_t)p->n_cams * p->d, ne = (size_t)p->n_cams * 6;
+  std::memcpy(p->h_state, intr, ni * 8);
+  std::memcpy(p->h_state + ni, extr, ne * 8);
+  for (int i = 0; i < 6; ++i) p->h_state[ni + i] = 0.0;   // cam0 is the reference frame (util.rs:689-690)
+  if (y) std::memcpy(p->h_state + ni + ne, y, (size_t)p->M * 8);
+  JCK(cudaMemcpyAsync(p->state_dev, p->h_state, (ni + ne + (y ? p->M : 0)) * 8, cudaMemcpyHostToDevice, p->stream));
+  if (poses) {
+    JCK(cudaMemcpyAsync(p->poses, poses, (size_t)p->n_frames * 48, cudaMemcpyHostToDevice, p->stream));
+    JCK(cudaStreamSynchronize(p->stream));   // caller-owned pageable memory
+  }
   return 0;
+}
+
+constexpr unsigned long long kJSentinel = 0x7ff8dead5e471e15ULL;
+void jarm(volatile double* dst, int n) {
+  volatile unsigned long long* w = reinterpret_cast<volatile unsigned long long*>(dst);
+  for (int i = 0; i < n; ++i) w[i] = kJSentinel;
+  __sync_synchronize();
+}
+int jwait(ccrs_joint* p, volatile double* src, int n) {
+  volatile unsigned long long* w = reinterpret_cast<volatile unsigned long long*>(src);
+  for (unsigned long spins = 1;; ++spins) {
+    int i = n - 1;
+    while (i >= 0 && w[i] != kJSentinel) --i;
+    if (i < 0) return 0;
+    if ((spins & 0x3fff) == 0) {
+      cudaError_t e = cudaStreamQuery(p->stream);
+      if (e == cudaSuccess) {
+        i = n - 1;
+        while (i >= 0 && w[i] != kJSentinel) --i;
+        if (i < 0) return 0;
+        return jfail(CCRS_ERR_CUDA, "stream drained but the reduced system was never published");
+      }
+      if (e != cudaErrorNotReady) return jfail(CCRS_ERR_CUDA, "stream error while waiting: %s", cudaGetErrorString(e));
+    }
+  }
 }
 }  // namespace
 
@@ -469,9 +514,14 @@ int ccrs_joint_create(ccrs_joint** out, int model, int xy_same_focal, int n_cams
   JA(x, N); JA(y, N); JA(z, N); JA(u, N); JA(v, N);
   JA(block_cam, n_blocks); JA(block_frame, n_blocks); JA(block_offsets, n_blocks + 1); JA(obs_block, N);
   JA(frame_block_offsets, n_frames + 1); JA(frame_blocks, n_blocks); JA(ij_table, p->NBJ);
-  JA(intr, (size_t)n_cams * p->d); JA(extr, (size_t)n_cams * 6); JA(poses, (size_t)n_frames * 6);
+  JA(state_dev, (size_t)n_cams * p->d + (size_t)n_cams * 6 + p->M); JA(poses, (size_t)n_frames * 6);
+  p->intr = p->state_dev; p->extr = p->state_dev + (size_t)n_cams * p->d; p->ydev = p->extr + (size_t)n_cams * 6;
+  if (cudaHostAlloc((void**)&p->h_state, ((size_t)n_cams * p->d + (size_t)n_cams * 6 + p->M) * 8, cudaHostAllocDefault) != cudaSuccess ||
+      cudaHostAlloc((void**)&p->h_red, (size_t)(p->NS + p->M + 1) * 8, cudaHostAllocMapped) != cudaSuccess) {
+    ccrs_joint_destroy(p); return jfail(CCRS_ERR_CUDA, "cudaHostAlloc");
+  }
   JA(jblk, (size_t)n_blocks * p->NBJ); JA(fs, (size_t)n_frames * (p->NS + p->M + 1)); JA(el, (size_t)n_frames * (6 * p->M + 6));
-  JA(red, p->NS + p->M + 1); JA(ydev, p->M);
+  JA(red, p->NS + p->M + 1);
 #undef JA
   cudaStream_t s = p->stream;
   cudaMemcpyAsync(p->x, x, N * 8, cudaMemcpyHostToDevice, s); cudaMemcpyAsync(p->y, y, N * 8, cudaMemcpyHostToDevice, s);
@@ -495,6 +545,8 @@ int ccrs_joint_destroy(ccrs_joint* p) {
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   for (void* a : p->allocs) cudaFree(a);
+  if (p->h_state) cudaFreeHost(p->h_state);
+  if (p->h_red) cudaFreeHost(p->h_red);
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
   return 0;
@@ -568,11 +620,13 @@ int ccrs_joint_solve_gn(ccrs_joint* p, double* intr, double* extr, double* poses
       k_joint_schur<<<(F + kJSchurWarps - 1) / kJSchurWarps, 32 * kJSchurWarps, smem, p->stream>>>(jd, p->jblk, p->ij_table, p->NAJ, M, 0.0, p->fs, p->el);
     }
     JCK(cudaGetLastError());
-    k_joint_sum<<<(NV + 127) / 128, 128, 0, p->stream>>>(p->fs, F, NV, p->red);
+    jarm(p->h_red, NV);
+    k_joint_sum<<<(NV + 31) / 32, 32, 0, p->stream>>>(p->fs, F, NV, p->red, p->h_red);
     JCK(cudaGetLastError());
     p->launches += 3;
-    JCK(cudaMemcpyAsync(red.data(), p->red, (size_t)NV * 8, cudaMemcpyDeviceToHost, p->stream));
-    JCK(cudaStreamSynchronize(p->stream));
+    st = jwait(p, p->h_red, NV);     // mapped-memory publication: no memcpy, no stream synchronise
+    if (st) return st;
+    for (int i = 0; i < NV; ++i) red[i] = p->h_red[i];
     const double err = std::sqrt(red[NS + M]);
     if (err_hist) err_hist[it] = err;
     sum->iterations = it + 1; sum->final_error = err;
@@ -598,12 +652,11 @@ int ccrs_joint_solve_gn(ccrs_joint* p, double* intr, double* extr, double* poses
       intr[i] = v;
     }
     for (int c = 1; c < C; ++c) for (int i = 0; i < 6; ++i) extr[6 * c + i] += y[C * d + 6 * (c - 1) + i];
-    JCK(cudaMemcpyAsync(p->ydev, y.data(), (size_t)M * 8, cudaMemcpyHostToDevice, p->stream));
+    st = upload_state(p, intr, extr, nullptr, y.data());   // y | new intr | new extr in one copy
+    if (st) return st;
     k_joint_backsub<<<(F + 3) / 4, 128, 0, p->stream>>>(jd, p->el, p->ydev, M);
     JCK(cudaGetLastError());
     p->launches++;
-    st = upload_state(p, intr, extr, nullptr);
-    if (st) return st;
   }
   JCK(cudaEventRecord(e1, p->stream));
   JCK(cudaEventSynchronize(e1));

@@ -11,6 +11,7 @@
 // per-frame blocks are 6x6 / 6xd. Determinism: no floating-point atomics anywhere; every sum has a fixed order.
 #include "ccrs_devutil.cuh"
 
+#include <algorithm>
 #include <type_traits>
 
 namespace ccrs {
@@ -514,7 +515,9 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   double lin_intr[C::D];
   if constexpr (BATCH) {
     // batch handles reach their pose through two more dependent loads (frame -> problem -> state selector): there the
-    // observation prefetch goes out as soon as the frame offsets are back
+    // observation prefetch goes out as soon as the frame offsets are back. A problem that has stopped contributes no
+    // observations (its frames' poses stay put, its blocks are not needed any more).
+    if (active && prm.active && !prm.active[prob]) fo_end = fo_beg;
     prefetch_first_stages();
     if (active) cur = cur_of(pb, prob);
   } else if (prm.ctl) {
@@ -895,7 +898,8 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(const __grid_constant__
   // launched as a programmatic dependent of the K2 in front of it: wait until that grid has completed and flushed
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const int f = blockIdx.x * kSchurThreads + threadIdx.x;
-  const bool valid = f < pb.n_frames;
+  bool valid = f < pb.n_frames;
+  if (BATCH && valid && prm.active && !prm.active[pb.frame_problem[f]]) valid = false;   // its problem has stopped
   double red[NRED];
 #pragma unroll
   for (int i = 0; i < NRED; ++i) red[i] = 0.0;
@@ -1234,6 +1238,29 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
     a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
   }
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// board-format problems (ccrs_problem_create_board_f32): p3d of observation k = board[corner_id[k]] (board.rs:46-95:
+// corner id -> board point), expanded once into the f32 SoA arrays the linearisation kernels read
+__global__ void __launch_bounds__(256) k_expand_board(const int32_t* __restrict__ id, const float* __restrict__ board, int n_board,
+                                                      int64_t n, float* __restrict__ x, float* __restrict__ y, float* __restrict__ z,
+                                                      volatile double* bad_flag) {
+  extern __shared__ float s_board[];
+  for (int i = threadIdx.x; i < 3 * n_board; i += blockDim.x) s_board[i] = board[i];
+  __syncthreads();
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    int c = id[k];
+    if ((unsigned)c >= (unsigned)n_board) { *bad_flag = 1.0; c = 0; }   // reported by ccrs_problem_create_board_f32
+    x[k] = s_board[3 * c]; y[k] = s_board[3 * c + 1]; z[k] = s_board[3 * c + 2];
+  }
+}
+cudaError_t launch_expand_board(const int32_t* id, const float* board, int n_board, int64_t n, float* x, float* y, float* z,
+                                volatile double* bad_flag, cudaStream_t s) {
+  const size_t smem = (size_t)3 * n_board * sizeof(float);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;   // > 4096 board corners: not a calibration board
+  const int nb = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  k_expand_board<<<nb, 256, smem, s>>>(id, board, n_board, n, x, y, z, bad_flag);
+  return cudaGetLastError();
 }
 
 __global__ void k_l2_flush(double* buf, size_t n) {

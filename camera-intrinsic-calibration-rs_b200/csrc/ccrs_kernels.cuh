@@ -132,6 +132,7 @@ struct SchurParams {
   double u_val;                 // single problem: damping by value (u_dev == nullptr)
   double min_diag, max_diag;
   int no_pose;                  // poses are constants of the problem (ModelConvertFactor): B' = 0, g'_p = 0, C' = I
+  const unsigned char* active;  // batch, nullable: frames of problems that have stopped are skipped
   double* elim;                 // [(6D+18)][Fs]: X (6xD), cg (6), g'_p (6), Dd (6)
   double* frame_red;            // batch: [NRED][Fs] per-frame contributions; single: [n_ctas][NRED] CTA partials
   // single problem: the last CTA sums the CTA partials in CTA order
@@ -178,6 +179,41 @@ struct Schur2Params {
 cudaError_t launch_schur2(int D, const Schur2Params& prm, int n_frames, bool pdl, cudaStream_t s);
 int schur2_ctas(int n_frames);   // CTAs (= partial slots) of a k_schur2 launch
 
+// ---- device-driven loop for a BATCH of independent problems (ccrs_loop.cu) -----------------------------------------
+// Every problem carries its own controller state; two small kernels (one CTA per problem) run the rule of ccrs_rule.h:
+//   k_batch_solve : per-problem sum of K3's frame contributions -> (GN: stop tests) damped d x d solve -> next point
+//   k_batch_decide: per-problem sum of K2's trial statistics -> LM accept / reject, damping, stop tests
+// and write straight into the arrays K2 / K3 read (intrinsics, step, damping, buffer selector, active mask). The host
+// enqueues K3, solve, K2, decide ahead of time and only reads the number of still-active problems per iteration from
+// mapped host memory: no per-iteration memcpy, no stream synchronise.
+struct BatchCtl {
+  double u, v, cur_err, last_err, sq_cur, md_a, final_err;
+  double intr[9], trial[9], scale[9];
+  int it, iterations, active, status, stop, n_acc, n_rej, pad;
+};
+struct BatchRuleParams {
+  ProblemDev pb;
+  BatchCtl* ctl;                // [n_problems]
+  int lm, D, NRED, max_iteration, fixed_mode, has_bounds, has_fixed, rr_idx;
+  double min_abs, min_rel, min_error, min_diag, max_diag;
+  double lo[9], hi[9];
+  unsigned char fixed[16];
+  const double* frame_red;      // [NRED][Fs] K3's per-frame contributions
+  const double* frame_md;       // [Fs] K2's per-frame model-decrease parts
+  double* intr_dev;             // [n_problems][D]  intrinsics K2 linearises at
+  double* ya_dev;               // [n_problems][D]  (scaled) intrinsic step for K2's back-substitution
+  double* u_dev;                // [n_problems]     damping for K3 / K2
+  int32_t* cur;                 // [n_problems]     buffer selector
+  unsigned char* active;        // [n_problems]     K2 / K3 skip the frames of problems that have stopped
+  unsigned int* ticket;         // last CTA publishes the iteration status
+  unsigned int* n_active;       // device counter
+  volatile double* host_status; // mapped pinned ring [kRecSlots][2] = {sequence number, active problems}
+  int seq;                      // sequence number of this launch (1-based)
+  double* err_hist0;            // device [max_iteration] error history of problem 0 (nullable)
+};
+cudaError_t launch_batch_solve(const BatchRuleParams& prm, cudaStream_t s);
+cudaError_t launch_batch_decide(const BatchRuleParams& prm, cudaStream_t s);
+
 // number of values K3 reduces per problem: S upper (D(D+1)/2) + g_s (D) + g_a (D) + diag_a (D) + sq_err (1)
 inline int nred_of(int D) { return D * (D + 1) / 2 + 3 * D + 1; }
 
@@ -220,6 +256,9 @@ cudaError_t launch_select(const double* v, int64_t n, SelectState* st, unsigned*
 // batched initial board poses (ccrs_pnp.cu): one warp per frame; poses_out [n_frames][6], cost_out [n_frames] nullable
 cudaError_t launch_pnp(const int32_t* frame_offsets, const double* x, const double* y, const double* z, const double* xn,
                        const double* yn, int n_frames, double* poses_out, double* cost_out, cudaStream_t s);
+// x, y, z[k] = board[3 id[k] + 0, 1, 2] (board-format problems)
+cudaError_t launch_expand_board(const int32_t* id, const float* board, int n_board, int64_t n, float* x, float* y, float* z,
+                                volatile double* bad_flag /* mapped host word, set to 1 on an id outside the table */, cudaStream_t s);
 cudaError_t launch_fp64_peak(double* out, int n_ctas, int iters, cudaStream_t s);
 cudaError_t launch_l2_flush(double* buf, size_t n, cudaStream_t s);
 

@@ -509,6 +509,172 @@ __global__ void __launch_bounds__(kS2Threads, 1) k_schur2(const __grid_constant_
   }
 }
 
+// ---- batch controller kernels: one CTA per problem -------------------------------------------------------------------
+constexpr int kBatchThreads = 256;
+
+// status of the iteration: active problems counted with an integer atomic (order-free), published by the last CTA
+CCRS_D void batch_publish(const BatchRuleParams& prm, int active_now) {
+  __shared__ int s_is_last;
+  if (threadIdx.x == 0) {
+    if (active_now) atomicAdd(prm.n_active, 1u);
+    __threadfence();
+    s_is_last = (atomicAdd(prm.ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_is_last && threadIdx.x == 0) {
+    __threadfence();
+    const unsigned n = atomicExch(prm.n_active, 0u);
+    *prm.ticket = 0u;
+    volatile double* slot = prm.host_status + (size_t)((prm.seq - 1) % kRecSlots) * 2;
+    slot[1] = (double)n;
+    slot[0] = (double)prm.seq;   // sentinel protocol: both words are waited for
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kBatchThreads) k_batch_solve(const __grid_constant__ BatchRuleParams prm) {
+  using namespace ccrs_rule;
+  constexpr int NS = D * (D + 1) / 2, NRED = NS + 3 * D + 1, NOUT = D * D + 3 * D + 1;
+  __shared__ double s_red[NRED];
+  const int q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  BatchCtl* bc = prm.ctl + q;
+  int active = bc->active;
+  if (active) {
+    // per-problem sum of the frame contributions: one warp per value, lane-strided partial sums in frame order, then a
+    // fixed butterfly (the order k_segreduce uses on the host-driven path: identical bits)
+    const int b = prm.pb.problem_frame_offsets[q], e = prm.pb.problem_frame_offsets[q + 1];
+    for (int v = warp; v < NRED; v += kBatchThreads / 32) {
+      const double* src = prm.frame_red + (size_t)v * prm.pb.Fs;
+      double s = 0.0;
+      for (int f = b + lane; f < e; f += 32) s += src[f];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) s_red[v] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double out[NOUT];
+      int e2 = 0;
+      for (int a = 0; a < D; ++a)
+        for (int c = a; c < D; ++c) { out[a * D + c] = s_red[e2]; out[c * D + a] = s_red[e2]; ++e2; }
+      for (int i = 0; i < 3 * D + 1; ++i) out[D * D + i] = s_red[NS + i];
+      const Reduced r = view(out, D);
+      const unsigned char* fixed = prm.has_fixed ? prm.fixed : nullptr;
+      const double* lo = prm.has_bounds ? prm.lo : nullptr;
+      const double* hi = prm.has_bounds ? prm.hi : nullptr;
+      double y[D], next[D];
+      int status = 0;
+      if (prm.lm) {
+        if (bc->it == 0) bc->cur_err = err_metric(r.sq_err);
+        bc->sq_cur = r.sq_err;
+        bc->iterations = bc->it + 1;
+        double md_a = 0.0;
+        status = solve_intrinsics(r, D, bc->u, prm.min_diag, prm.max_diag, fixed, prm.fixed_mode, y, &md_a);
+        if (status == 0) {
+          double dx[D];
+          for (int i = 0; i < D; ++i) dx[i] = CCRS_RMUL(bc->scale[i], y[i]);
+          update_intr(D, bc->intr, dx, lo, hi, fixed, next);
+          bc->md_a = md_a;
+          for (int i = 0; i < D; ++i) { bc->trial[i] = next[i]; prm.intr_dev[(size_t)q * D + i] = next[i]; prm.ya_dev[(size_t)q * D + i] = y[i]; }
+          prm.u_dev[q] = bc->u;
+        }
+      } else if (bc->it >= prm.max_iteration) {
+        active = 0;   // the step of the last allowed iteration has been applied (and linearised): nothing else to do
+      } else {
+        const double err = err_metric(r.sq_err);
+        bc->iterations = bc->it + 1;
+        bc->final_err = err;
+        if (q == 0 && prm.err_hist0) prm.err_hist0[bc->it] = err;
+        const int why = gn_stop(bc->it, bc->last_err, err, prm.min_error, prm.min_abs, prm.min_rel, &status);
+        if (status == 0 && why != 0) { bc->stop = why; active = 0; }
+        if (status == 0 && active) {
+          bc->last_err = err;
+          status = solve_intrinsics(r, D, 0.0, prm.min_diag, prm.max_diag, fixed, prm.fixed_mode, y, nullptr);
+          if (status == 0) {
+            update_intr(D, bc->intr, y, lo, hi, fixed, next);
+            for (int i = 0; i < D; ++i) { bc->intr[i] = next[i]; prm.intr_dev[(size_t)q * D + i] = next[i]; prm.ya_dev[(size_t)q * D + i] = y[i]; }
+            bc->it += 1;
+          }
+        }
+      }
+      if (status != 0) { bc->status = status; active = 0; }
+      bc->active = active;
+      prm.active[q] = (unsigned char)active;   // K2 / K3 skip the frames of a problem that has stopped
+      s_red[0] = (double)active;
+    }
+    __syncthreads();
+    active = (int)s_red[0];
+  }
+  if (!prm.lm) batch_publish(prm, active);
+}
+
+// LM: accept / reject of the trial point every active problem has just been linearised at
+__global__ void __launch_bounds__(kBatchThreads) k_batch_decide(const __grid_constant__ BatchRuleParams prm) {
+  using namespace ccrs_rule;
+  __shared__ double sh0[kBatchThreads], sh1[kBatchThreads];
+  const int q = blockIdx.x, D = prm.D;
+  BatchCtl* bc = prm.ctl + q;
+  int active = bc->active;
+  if (active) {
+    const int b = prm.pb.problem_frame_offsets[q], e = prm.pb.problem_frame_offsets[q + 1];
+    const int cur = prm.cur[q];
+    const double* cost = prm.pb.blocks[cur ^ 1] + (size_t)prm.rr_idx * prm.pb.Fs;
+    double s0 = 0.0, s1 = 0.0;   // same order as k_trial_stats (thread-strided, then a fixed tree)
+    for (int f = b + threadIdx.x; f < e; f += kBatchThreads) { s0 += prm.frame_md[f]; s1 += cost[f]; }
+    sh0[threadIdx.x] = s0; sh1[threadIdx.x] = s1;
+    __syncthreads();
+    for (int w = kBatchThreads / 2; w > 0; w >>= 1) {
+      if (threadIdx.x < w) { sh0[threadIdx.x] += sh0[threadIdx.x + w]; sh1[threadIdx.x] += sh1[threadIdx.x + w]; }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      LmState st{bc->u, bc->v, bc->cur_err};
+      const double last_err = bc->cur_err;
+      double rho;
+      const int acc = lm_decide(bc->sq_cur, sh1[0], CCRS_RADD(bc->md_a, sh0[0]), &st, &rho);
+      bc->u = st.u; bc->v = st.v; bc->cur_err = st.cur_err; bc->final_err = st.cur_err;
+      if (acc) {
+        for (int i = 0; i < D; ++i) bc->intr[i] = bc->trial[i];
+        prm.cur[q] = cur ^ 1;
+        bc->n_acc++;
+      } else {
+        bc->n_rej++;
+      }
+      if (q == 0 && prm.err_hist0) prm.err_hist0[bc->it] = st.cur_err;
+      int status = 0;
+      const int why = lm_stop(last_err, st.cur_err, rho, acc, prm.min_error, prm.min_abs, prm.min_rel, &status);
+      if (status != 0) { bc->status = status; active = 0; }
+      else if (why != 0) { bc->stop = why; active = 0; }
+      bc->it += 1;
+      if (bc->it >= prm.max_iteration) active = 0;
+      bc->active = active;
+      prm.active[q] = (unsigned char)active;
+      prm.u_dev[q] = bc->u;          // damping of the next reduction
+      sh0[0] = (double)active;
+    }
+    __syncthreads();
+    active = (int)sh0[0];
+  }
+  batch_publish(prm, active);
+}
+
+cudaError_t launch_batch_solve(const BatchRuleParams& prm, cudaStream_t s) {
+  switch (prm.D) {
+    case 4: k_batch_solve<4><<<prm.pb.n_problems, kBatchThreads, 0, s>>>(prm); break;
+    case 5: k_batch_solve<5><<<prm.pb.n_problems, kBatchThreads, 0, s>>>(prm); break;
+    case 6: k_batch_solve<6><<<prm.pb.n_problems, kBatchThreads, 0, s>>>(prm); break;
+    case 7: k_batch_solve<7><<<prm.pb.n_problems, kBatchThreads, 0, s>>>(prm); break;
+    case 8: k_batch_solve<8><<<prm.pb.n_problems, kBatchThreads, 0, s>>>(prm); break;
+    case 9: k_batch_solve<9><<<prm.pb.n_problems, kBatchThreads, 0, s>>>(prm); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+cudaError_t launch_batch_decide(const BatchRuleParams& prm, cudaStream_t s) {
+  k_batch_decide<<<prm.pb.n_problems, kBatchThreads, 0, s>>>(prm);
+  return cudaGetLastError();
+}
+
 template <class F>
 static cudaError_t dispatch_d2(int D, F&& f) {
   switch (D) {

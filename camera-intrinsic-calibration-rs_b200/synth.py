@@ -199,7 +199,8 @@ def make_calib(model: str = "eucm", n_frames: int = 100, seed: int = 0, noise_px
     init_poses[:, :3] += rng.normal(scale=0.01, size=(len(poses), 3))
     init_poses[:, 3:] += rng.normal(scale=0.005, size=(len(poses), 3))
     return SyntheticCalib(model=model, width=width, height=height, frame_offsets=offs, x=x, y=y, z=z, u=u, v=v,
-                          gt_params=gt, gt_poses=poses, init_params=init_params, init_poses=init_poses)
+                          gt_params=gt, gt_poses=poses, init_params=init_params, init_poses=init_poses,
+                          extra={"corner_id": ki.astype(np.int32), "board": board.astype(np.float32)})
 
 
 def to_frame_features(s: SyntheticCalib, poses: np.ndarray | None = None):

@@ -78,6 +78,16 @@ int ccrs_problem_create_f32(ccrs_problem** out, int model, int width, int height
                             const float* u, const float* v,
                             double huber_delta, int device_id);
 
+/* Same problem in the reference's own data model: FrameFeature.features is a map corner id -> FeaturePoint
+ * (src/detected_points.rs:13-17) and every p3d is the board point of that id (Board::init_aprilgrid id -> 3-D,
+ * src/board.rs:46-95). corner_id[N] indexes board_xyz[n_board][3] (f32, row-major x y z); u, v as above. 12 bytes per
+ * observation cross PCIe instead of 20; the device expands p3d = board[id] once, so every kernel and every result is
+ * bit-identical to ccrs_problem_create_f32 on the expanded arrays. n_board <= 4096. */
+int ccrs_problem_create_board_f32(ccrs_problem** out, int model, int width, int height, int xy_same_focal,
+                                  int n_frames, const int32_t* frame_offsets, const int32_t* corner_id,
+                                  const float* u, const float* v, const float* board_xyz, int n_board,
+                                  double huber_delta, int device_id);
+
 /* Batch of independent calibrations in one handle (BASELINE config 5): problem b owns frames
  * [problem_frame_offsets[b], problem_frame_offsets[b+1]). Same model/size/flags for all problems.
  * Intrinsic arrays passed to the calls below are then [n_problems][d]; scalars become [n_problems]. */

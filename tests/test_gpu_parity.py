@@ -376,6 +376,28 @@ def test_device_loop_is_audited_and_matches_the_host_controllers(pkg, oracle):
     gp.close()
 
 
+def test_board_format_is_bit_identical(pkg):
+    """ccrs_problem_create_board_f32 (corner ids + board table: the reference's FrameFeature / Board data model) expands
+    p3d = board[id] on the device: results must equal the f32 entry point on the expanded arrays bit for bit."""
+    s = pkg.synth.make_calib("eucm", 90, seed=12, drop_fraction=0.25)
+    f = lambda a: a.astype(np.float32)
+    ids, board = s.extra["corner_id"], s.extra["board"]
+    assert np.array_equal(board[ids, 0].astype(np.float64), s.x) and np.array_equal(board[ids, 2].astype(np.float64), s.z)
+    g32 = pkg.Problem(s.model, s.width, s.height, s.frame_offsets, f(s.x), f(s.y), f(s.z), f(s.u), f(s.v))
+    gb = pkg.Problem(s.model, s.width, s.height, s.frame_offsets, None, None, None, f(s.u), f(s.v), corner_id=ids, board=board)
+    for g in (g32, gb):
+        g.set_poses(s.init_poses)
+    assert np.array_equal(g32.linearize(s.init_params), gb.linearize(s.init_params))
+    assert np.array_equal(g32.frame_blocks(), gb.frame_blocks())
+    i1, s1, h1 = g32.solve_lm(s.init_params)
+    i2, s2, h2 = gb.solve_lm(s.init_params)
+    assert np.array_equal(i1, i2) and np.array_equal(h1, h2) and np.array_equal(g32.get_poses(), gb.get_poses())
+    g32.close(); gb.close()
+    bad = ids.copy(); bad[5] = len(board)
+    with pytest.raises(pkg.CcrsError):
+        pkg.Problem(s.model, s.width, s.height, s.frame_offsets, None, None, None, f(s.u), f(s.v), corner_id=bad, board=board)
+
+
 def test_speculative_k3_is_used_and_changes_nothing():
     """Host-driven LM (CCRS_DEVICE_LOOP=0): the K3 launched behind the trial K2 (for 'accepted, u_next = u / 3') must be
     consumed on a converging run and the trajectory must be bit-identical to the run without it (same kernels, same
