@@ -222,7 +222,7 @@ CCRS_D void stats_finalize(const LinParams& prm, unsigned n_parts, int lane, int
   // in flight per lane) until none still holds the arming pattern, sum in a fixed order, re-arm for the next launch
   double2* part = reinterpret_cast<double2*>(prm.cta_part);
   double a = 0.0, b = 0.0;
-  constexpr int kBatch = 40;   // loads in flight per lane: one pass for the 1167 warps of 7,000 frames (the accumulators are dead here)
+  constexpr int kBatch = 16;   // loads in flight per lane (40 would cover 7,000 frames in one pass, but the 160 live registers cost the main loop 6 us)
   const long long t_spin = clock64();
   for (unsigned w0 = lane; w0 < n_parts; w0 += 32 * kBatch) {
     double2 t[kBatch];
