@@ -458,7 +458,7 @@ def run_ours(args):
     h2d = hid.nbytes + hu.nbytes + hv.nbytes + hboard.nbytes + hfo.nbytes + hp.nbytes
     h2d_xyz = hx.nbytes * 5 + hfo.nbytes + hp.nbytes
     d2h = hp.nbytes + d * 8
-    d2h_iter = (summ.iterations + 1) * 192 * 8          # one iteration record per executed reduction
+    d2h_iter = (summ.iterations + 1) * 208 * 8          # one iteration record per executed reduction
     rel_err = float(np.max(np.abs(intr - s.gt_params) / np.abs(s.gt_params)))
     prob.close()
 

@@ -792,6 +792,7 @@ struct LoopTrace {
   bool on = false;
   long n = 0;
   double acc[5] = {0, 0, 0, 0, 0};
+  double wake = 0.0;              // record ready -> first K2 warp past its dependency wait (part of acc[4])
   double fine[7] = {0, 0, 0, 0, 0, 0, 0};   // last CTA of K3: head | block load | per-frame compute | CTA sum + partial store | partial sum (+ exchange) | pre-rule | rule
   double prev_end = -1.0;
   void add(const double* r) {
@@ -804,6 +805,7 @@ struct LoopTrace {
       acc[2] += d(r[REC_T_K3_BEGIN], r[REC_T_TAIL]);
       acc[3] += d(r[REC_T_TAIL], r[REC_T_END]);
       acc[4] += d(prev_end, r[REC_T_K2_BEGIN]);
+      wake += d(prev_end, r[REC_T_K2_WAKE]);
       fine[0] += d(r[REC_T_K3_BEGIN], r[REC_T_HEAD]); fine[1] += d(r[REC_T_HEAD], r[REC_T_LOAD]);
       fine[2] += d(r[REC_T_LOAD], r[REC_T_COMP]); fine[3] += d(r[REC_T_COMP], r[REC_T_TAIL]);
       fine[4] += d(r[REC_T_TAIL], r[REC_T_SUMMED]); fine[5] += d(r[REC_T_SUMMED], r[REC_T_RULE]);
@@ -1778,10 +1780,11 @@ int ccrs_init_poses(int n_frames, const int32_t* frame_offsets, const double* x,
   return 0;
 }
 
-int ccrs_loop_trace(int enable, double* avg_us /* [12] or NULL */, int64_t* n_iterations) {
+int ccrs_loop_trace(int enable, double* avg_us /* [13] or NULL */, int64_t* n_iterations) {
   if (avg_us) {
     for (int i = 0; i < 5; ++i) avg_us[i] = g_loop_trace.n ? g_loop_trace.acc[i] * 1e-3 / g_loop_trace.n : 0.0;
     for (int i = 0; i < 7; ++i) avg_us[5 + i] = g_loop_trace.n ? g_loop_trace.fine[i] * 1e-3 / g_loop_trace.n : 0.0;
+    avg_us[12] = g_loop_trace.n ? g_loop_trace.wake * 1e-3 / g_loop_trace.n : 0.0;
   }
   if (n_iterations) *n_iterations = g_loop_trace.n;
   g_loop_trace = LoopTrace{};

@@ -442,8 +442,8 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   const int f0 = gw * FPW;
   const int nf = max(0, min(FPW, pb.n_frames - f0));    // frames of this warp
   double* s_fc = smem + (size_t)wid * lin_warp_smem_doubles(FPW, BATCH, COST_ONLY);  // [FPW][kFrameConst]
-  double* s_intr = s_fc + FPW * kFrameConst;             // [FPW][kMaxFull]   (BATCH only)
-  double* s_stat = s_intr + (BATCH ? FPW * kMaxFull : 0);  // [2][FPW] per-frame md, cost
+  double* s_intr = s_fc + FPW * kFrameConst;             // batch: [FPW][kMaxFull] per frame; single problem: [kMaxFull + 1] per warp
+  double* s_stat = s_intr + (BATCH ? FPW * kMaxFull : kMaxFull + 1);  // [2][FPW] per-frame md, cost
   double* s_red = s_stat + 2 * FPW;                      // [kRedChunk][kRedStride]
   double* s_obs = s_red + (COST_ONLY ? 32 : kRedChunk * kRedStride);  // [kObsStages][5][32] cp.async ring of x,y,z,u,v
   int* s_a2b = reinterpret_cast<int*>(s_obs + kObsStages * 5 * 32);  // [NACC] accumulator -> packed block entry
@@ -528,6 +528,7 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
     prefetch_first_stages();
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const LoopCtl* ctl = prm.ctl;
+    if (gw == 0 && lane == 0) prm.ctl->t_k2_wake = stamp_ns();
     const int ph = __ldcg(&ctl->phase), lm = __ldcg(&ctl->mode), cu = __ldcg(&ctl->cur);
     u_bs = __ldcg(&ctl->u_used);
 #pragma unroll

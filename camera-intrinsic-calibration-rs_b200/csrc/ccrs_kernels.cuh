@@ -58,7 +58,7 @@ enum LoopPhase : int {
   PH_DECIDE = 3,   // K3: K2's statistics are in; LM: accept / reject, then reduce; GN: stop tests, then reduce
   PH_DONE = 5
 };
-constexpr int kRecStride = 192;   // doubles per published record
+constexpr int kRecStride = 208;   // doubles per published record
 constexpr int kRecSlots = 32;     // ring of records in mapped host memory
 // record layout (doubles)
 enum : int {
@@ -70,7 +70,9 @@ enum : int {
   // at its end), this K3 (entry of the last CTA after its wait, start of the last CTA's tail, record ready)
   REC_T_K2_BEGIN, REC_T_K2_END, REC_T_K3_BEGIN, REC_T_TAIL, REC_T_END,
   REC_T_HEAD, REC_T_LOAD, REC_T_COMP, REC_T_SUMMED, REC_T_RULE,   // finer stamps of the last CTA (tools/loop_trace.py)
-  REC_INTR = 40, REC_TRIAL = 49, REC_Y = 58, REC_SCALE = 67, REC_OUT = 76   // out: d*d + 3d + 1 <= 109
+  REC_T_K2_WAKE,
+  REC_LAST_SCALAR,
+  REC_INTR = 48, REC_TRIAL = 57, REC_Y = 66, REC_SCALE = 75, REC_OUT = 84   // out: d*d + 3d + 1 <= 109
 };
 struct LoopCtl {
   // ---- configuration: constant during a loop
@@ -91,8 +93,10 @@ struct LoopCtl {
   double sq_cur, cur_err, last_err, final_err;
   double stat[2];           // K2 (this rank): {pose part of the model decrease, sum of corrected r^2} at the point it linearised
   double t_k2_begin, t_k2_end;   // device timestamps of the last executed K2 (see REC_T_*)
+  double t_k2_wake;              // ... its first warp straight after the dependency wait (before the prologue loads)
 };
 static_assert(sizeof(LoopCtl) % 8 == 0, "LoopCtl is copied as 8-byte words");
+static_assert(REC_LAST_SCALAR <= REC_INTR && REC_OUT + 9 * 9 + 3 * 9 + 1 <= kRecStride, "record layout overlaps");
 
 struct LinParams {
   ProblemDev pb;

@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) k_schur2(const __grid_constant_
     return;
   }
   if (threadIdx.x == 0) {
-    s_rec[REC_T_K2_BEGIN] = s_ctl->t_k2_begin; s_rec[REC_T_K2_END] = s_ctl->t_k2_end;
+    s_rec[REC_T_K2_BEGIN] = s_ctl->t_k2_begin; s_rec[REC_T_K2_END] = s_ctl->t_k2_end; s_rec[REC_T_K2_WAKE] = s_ctl->t_k2_wake;
     s_rec[REC_T_K3_BEGIN] = t_begin; s_rec[REC_T_TAIL] = t_tail;
     s_rec[REC_T_HEAD] = t_head; s_rec[REC_T_LOAD] = t_load; s_rec[REC_T_COMP] = t_comp; s_rec[REC_T_SUMMED] = t_summed;
     s_rec[REC_T_RULE] = stamp_ns();

@@ -370,7 +370,8 @@ int ccrs_spec_k3_counters(int64_t* launched, int64_t* hits);
  *   [2] K3 per-frame elimination + CTA sums (last CTA)              [3] K3 tail: cross-CTA sum, exchange, controller rule
  *   [4] record ready -> next K2 running
  *   [5..11] finer split of [2] and [3] in the last CTA of K3: control block + decision | block load | per-frame
- *   elimination | CTA sum + partial store | cross-CTA sum (+ exchange) | staging | controller rule.   avg_us: [12] */
+ *   elimination | CTA sum + partial store | cross-CTA sum (+ exchange) | staging | controller rule.
+ *   [12] the part of [4] up to the first K2 warp leaving its dependency wait (the rest is its prologue loads).  avg_us: [13] */
 int ccrs_loop_counters(int64_t* audited_solves);
 int ccrs_loop_trace(int enable, double* avg_us, int64_t* n_iterations);
 /* Kernel launches issued by this handle since creation. */

@@ -30,11 +30,12 @@ for loop in ("lm", "gn"):
     lib.ccrs_loop_trace(1, None, None)
     gp.set_poses(s.init_poses[lo:hi])
     _, summ, _ = solve(s.init_params, options=o)
-    avg = (C.c_double * 12)(); cnt = C.c_int64(0)
+    avg = (C.c_double * 13)(); cnt = C.c_int64(0)
     lib.ccrs_loop_trace(0, avg, C.byref(cnt))
     out[loop] = {"iterations_traced": int(cnt.value), "device_ms_per_iteration_events": summ.device_ms / max(summ.iterations, 1),
                  "phases_us": {names[i]: round(avg[i], 2) for i in range(5)}, "sum_us": round(sum(avg[:5]), 2),
-                 "k3_last_cta_us": {fine[i]: round(avg[5 + i], 2) for i in range(7)}}
+                 "k3_last_cta_us": {fine[i]: round(avg[5 + i], 2) for i in range(7)},
+                 "record_ready_to_k2_past_its_wait_us": round(avg[12], 2)}
 if rank == 0:
     print(json.dumps(out, indent=1))
 gp.close()
