@@ -174,6 +174,10 @@ struct ccrs_problem {
   int n_sms = 148;
   cudaStream_t stream = nullptr;
   int G = 1, FPW = 32, n_lin_ctas = 0, n_schur_ctas = 0;
+  bool use_mma = false;           // K2 with the Gram block on the FP64 tensor path (models with d + 7 >= 14 columns)
+  int n_mma_ctas = 0;
+  DevBuf<double> frame_stat;      // ... its per-frame {model decrease, cost} slots
+  DevBuf<unsigned int> chunk_cnt; // ... frames done per chunk of 16
   double huber = 1.0;
   int64_t launches = 0;
 
@@ -271,6 +275,19 @@ void choose_slicing(ccrs_problem* p) {
   p->FPW = 32 / bestG;
   const int warps = (p->n_frames + p->FPW - 1) / p->FPW;
   p->n_lin_ctas = (warps + kLinWarps - 1) / kLinWarps;
+  // tensor-core variant: one resident wave of warps, frames handed out dynamically
+  const char* em = getenv("CCRS_K2_MMA");
+  p->use_mma = lin_mma_available(p->model, p->one_focal) && !(em && atoi(em) == 0);
+  p->n_mma_ctas = lin_mma_ctas(p->n_sms, p->n_frames);
+}
+
+// K2 launch: the tensor-core variant where it applies (never for the cost-only pass), else the register-accumulator kernel
+cudaError_t launch_k2(ccrs_problem* p, bool batch, bool cost_only, LinParams& prm) {
+  prm.frame_ctr = reinterpret_cast<unsigned long long*>(p->tickets.p + 4);
+  prm.frame_stat = p->frame_stat.p;
+  prm.chunk_cnt = p->chunk_cnt.p;
+  if (p->use_mma && !cost_only) return launch_linearize_mma(p->model, p->one_focal, batch, prm, p->n_mma_ctas, p->stream);
+  return launch_linearize(p->model, p->one_focal, batch, cost_only, prm, p->n_lin_ctas, p->stream);
 }
 
 int upload_problem(ccrs_problem* p, int n_problems, const int32_t* problem_frame_offsets, int n_frames,
@@ -314,8 +331,14 @@ int upload_problem(ccrs_problem* p, int n_problems, const int32_t* problem_frame
   CK(p->problem_frame_offsets.alloc(P + 1));
   CK(p->cur.alloc(P));
   CK(p->acc_to_blk.alloc(p->NACC));
-  CK(p->tickets.alloc(4));        // [0] K2 statistics, [1] K3 reduction, [2] batch: active problems, [3] batch: status ticket
-  CK(cudaMemsetAsync(p->tickets.p, 0, 4 * sizeof(unsigned int), s));
+  CK(p->tickets.alloc(8));        // [0] K2 statistics, [1] K3 reduction, [2] batch: active problems, [3] batch: status ticket, [4..5] K2 frame counter (64 bit)
+  CK(cudaMemsetAsync(p->tickets.p, 0, 8 * sizeof(unsigned int), s));
+  if (p->use_mma) {
+    const size_t n_chunks = (F + 15) / 16;
+    CK(p->frame_stat.alloc(2 * Fs)); CK(p->chunk_cnt.alloc(n_chunks));
+    CK(launch_arm(p->frame_stat.p, 2 * Fs, s));
+    CK(cudaMemsetAsync(p->chunk_cnt.p, 0, n_chunks * sizeof(unsigned int), s));
+  }
   for (int i = 0; i < 2; ++i) {
     CK(p->poses[i].alloc(F * 6));
     CK(p->blocks[i].alloc((size_t)p->NBLK * Fs));
@@ -327,8 +350,9 @@ int upload_problem(ccrs_problem* p, int n_problems, const int32_t* problem_frame
   CK(p->frame_red.alloc(std::max((size_t)p->NRED * Fs, (size_t)p->n_schur_ctas * p->NRED)));
   CK(p->pose_scale.alloc(6 * Fs));
   CK(p->frame_md.alloc(Fs));
-  CK(p->cta_part.alloc((size_t)2 * p->n_lin_ctas * kLinWarps));
-  CK(launch_arm(p->cta_part.p, (size_t)2 * p->n_lin_ctas * kLinWarps, s));
+  const size_t n_k2_warps = (size_t)std::max(p->n_lin_ctas, p->n_mma_ctas) * kLinWarps;
+  CK(p->cta_part.alloc(2 * n_k2_warps));
+  CK(launch_arm(p->cta_part.p, 2 * n_k2_warps, s));
   CK(p->red_out.alloc(P * p->NRED));
   CK(p->stat_out.alloc(P * 2));
   CK(p->intr_dev.alloc(P * p->D)); CK(p->ya_dev.alloc(P * p->D)); CK(p->u_dev.alloc(P)); CK(p->scale_dev.alloc(P * p->D));
@@ -604,10 +628,10 @@ int do_linearize(ccrs_problem* p, const double* intr, int which, bool cost_only,
     if (seq_out) *seq_out = p->seq;
   }
 #ifdef CCRS_K2_TIMING
-  if (!p->k2_dbg.p) CK(p->k2_dbg.alloc((size_t)12 * p->n_lin_ctas * kLinWarps));
+  if (!p->k2_dbg.p) CK(p->k2_dbg.alloc((size_t)12 * std::max(p->n_lin_ctas, p->n_mma_ctas) * kLinWarps));
   prm.dbg = reinterpret_cast<long long*>(p->k2_dbg.p);
 #endif
-  CK(launch_linearize(p->model, p->one_focal, p->batch, cost_only, prm, p->n_lin_ctas, p->stream));
+  CK(launch_k2(p, p->batch, cost_only, prm));
   p->launches++;
   if (!p->batch && publish && p->comm && !use_peer(p, 2)) {
     int st = exchange(p, p->stat_out.p, 2, p->h_stat.p, p->seq);   // h_stat[0..1] = sums, h_stat[2] = seq
@@ -889,7 +913,7 @@ int loop_launch_k2(DeviceLoop& L) {
   prm.cta_part = p->cta_part.p;
   prm.ticket = p->tickets.p;
   prm.stat_dev = p->stat_out.p;
-  CK(launch_linearize(p->model, p->one_focal, false, false, prm, p->n_lin_ctas, p->stream));
+  CK(launch_k2(p, false, false, prm));
   p->launches++;
   return 0;
 }
@@ -1021,7 +1045,7 @@ int batch_launch_k2(ccrs_problem* p, int which, int backsub, bool use_pose_scale
   prm.active = p->mask_dev.p;
   prm.frame_md = p->frame_md.p;
   prm.intr_dev = p->intr_dev.p;
-  CK(launch_linearize(p->model, p->one_focal, true, false, prm, p->n_lin_ctas, p->stream));
+  CK(launch_k2(p, true, false, prm));
   p->launches++;
   return 0;
 }
@@ -1201,6 +1225,7 @@ int ccrs_problem_destroy(ccrs_problem* p) {
   p->cur.release(); p->acc_to_blk.release(); p->tickets.release();
   for (int i = 0; i < 2; ++i) { p->poses[i].release(); p->blocks[i].release(); p->frame_cost[i].release(); }
   p->elim.release(); p->frame_red.release(); p->pose_scale.release(); p->frame_md.release(); p->cta_part.release();
+  p->frame_stat.release(); p->chunk_cnt.release();
   p->red_out.release(); p->stat_out.release(); p->gather.release(); p->intr_dev.release(); p->ya_dev.release();
   p->u_dev.release(); p->scale_dev.release(); p->l2_flush.release(); p->mask_dev.release();
   p->h_red.release(); p->h_stat.release(); p->h_colsq.release();
@@ -1251,7 +1276,7 @@ extern "C" int ccrs_debug_k3_timing(ccrs_problem* p, long long* out, int cap_war
 // debug builds only (make timing): per-warp phase clocks of the last K2 launch, [n_warps][10] int64
 extern "C" int ccrs_debug_k2_timing(ccrs_problem* p, long long* out, int cap_warps) {
   if (!p || !p->k2_dbg.p) return -1;
-  const int nw = p->n_lin_ctas * kLinWarps;
+  const int nw = (p->use_mma ? p->n_mma_ctas : p->n_lin_ctas) * kLinWarps;
   cudaStreamSynchronize(p->stream);
   cudaMemcpy(out, p->k2_dbg.p, (size_t)12 * std::min(nw, cap_warps) * sizeof(long long), cudaMemcpyDeviceToHost);
   return nw;

@@ -111,6 +111,38 @@ CCRS_D double sqrt_fast(double x) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// theta = atan2(r, z) for r > 0 (the angle of a point off the optical axis: KB4 / FTHETA), straight-line code instead of
+// the library's atan2 (range tests, a division with a slow path, a 19-term polynomial: ~2.4x the instructions and a
+// chain several times as deep). With rho = |(r, z)| given as 1/rho:
+//   key   t = tan(theta'/2) = r / (rho + |z|) in [0, 1], evaluated in FP32 from FP32 square roots; i = round(64 t)
+//   table theta_i = 2 atan(i/64), sin theta_i, cos theta_i  (ccrs_atan_tab.inc, 65 entries)
+//   sin(theta' - theta_i) = (r cos theta_i - |z| sin theta_i) / rho,  |theta' - theta_i| <= 1/64 + FP32 error
+//   theta' = theta_i + asin(.)  (odd series to x^9: truncation < 3e-20),  theta = z < 0 ? pi - theta' : theta'
+// Absolute error ~2e-16 (the rounding of the table's sin / cos), i.e. <= 1e-14 relative for theta >= 1/64 and full
+// precision below (entry 0 is exact).
+// ---------------------------------------------------------------------------------------------
+static __device__ const double kAtanTab[65][4] = {
+#include "ccrs_atan_tab.inc"
+};
+CCRS_D double atan2_pos(double r, double z, double r2, double rho2, double irho) {
+  const double za = fabs(z);
+  float rf, rhof, inv;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)r2));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rhof) : "f"((float)rho2));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(rhof + (float)za));
+  const unsigned i = min((unsigned)__float2int_rn(rf * inv * 64.0f), 64u);
+  const double2 e0 = *reinterpret_cast<const double2*>(&kAtanTab[i][0]);   // theta_i, sin
+  const double ci = kAtanTab[i][2];
+  const double xs = fma(r, ci, -(za * e0.y)) * irho;
+  const double x2 = xs * xs;
+  double p = fma(x2, 35.0 / 1152.0, 5.0 / 112.0);
+  p = fma(x2, p, 3.0 / 40.0);
+  p = fma(x2, p, 1.0 / 6.0);
+  const double thp = e0.x + fma(xs * x2, p, xs);
+  return z < 0.0 ? 3.141592653589793 - thp : thp;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Camera models. k = distortion parameters (params[4..]). WITH_J selects value-only evaluation.
 // Outputs: m[2]; dP[2][3] = dm/dP; dk[2][ND] = dm/dk.
 // ---------------------------------------------------------------------------------------------
@@ -177,8 +209,10 @@ CCRS_D void model_eval(const double* __restrict__ k, double x, double y, double 
       }
     }
   } else if constexpr (MODEL == KB4 || MODEL == FTHETA) {
-    const double r2 = x * x + y * y;
-    const double r = sqrt_fast(fmax(r2, 1e-300));   // branch-free; r2 = 0 lands in the pinhole-limit branch below
+    const double r2 = fma(x, x, y * y);
+    const double r2c = fmax(r2, 1e-300);            // branch-free; r2 = 0 lands in the pinhole-limit branch below
+    const double ir = rsqrt_fast(r2c);
+    const double r = r2c * ir;
     if (r < kSmallR) {
       const double iz = 1.0 / z;
       m[0] = x * iz; m[1] = y * iz;
@@ -190,8 +224,9 @@ CCRS_D void model_eval(const double* __restrict__ k, double x, double y, double 
       }
       return;
     }
-    const double th = atan2(r, z);
-    const double ir = rcp_fast(r);
+    const double rho2 = fma(z, z, r2);
+    const double irho = rsqrt_fast(rho2);
+    const double th = atan2_pos(r, z, r2c, rho2, irho);
     double d, dd, pw[4];  // d(theta), d'(theta), d d/d k_i
     if constexpr (MODEL == KB4) {
       const double t2 = th * th;
@@ -206,7 +241,7 @@ CCRS_D void model_eval(const double* __restrict__ k, double x, double y, double 
     const double s = d * ir;  // m = s * (x, y)
     m[0] = x * s; m[1] = y * s;
     if constexpr (WITH_J) {
-      const double irho2 = rcp_fast(r2 + z * z);
+      const double irho2 = irho * irho;
       // theta_x = x z / (r rho2), theta_y = y z / (r rho2), theta_z = -r / rho2
       const double cxy = (dd * z * irho2 - s) * ir * ir;  // (d' theta_x / r - d x / r^3) / x
       const double sz = -dd * irho2;                      // ds/dz = d' theta_z / r

@@ -107,6 +107,10 @@ struct LinParams {
   int which;                // 0 = current point, 1 = trial point
   int G;                    // lanes per frame
   int FPW;                  // frames per warp = 32 / G
+  // ---- tensor-core variant (ccrs_linmma.cu): frames are handed out dynamically, statistics summed per chunk of 16 frames
+  unsigned long long* frame_ctr;  // next frame to hand out (reset by the launch's last grab)
+  double* frame_stat;       // [Fs][2] per-frame {model decrease, cost}, self-validating slots (armed)
+  unsigned int* chunk_cnt;  // [ceil(F / 16)] frames of the chunk done so far (reset by the warp that closes the chunk)
   // ---- fused K4 (pose back-substitution) in the prologue: 0 none, 1 trial = current + step, 2 in place (GN)
   int backsub;
   const double* elim;       // [(6D+18)][Fs] from K3
@@ -228,6 +232,10 @@ bool lin_uses_pairs(int model, int one_focal);
 
 cudaError_t launch_linearize(int model, int one_focal, bool batch, bool cost_only, const LinParams& prm, int n_ctas,
                              cudaStream_t s);
+// K2 with the Gram block on the FP64 tensor path (ccrs_linmma.cu): the models with d + 7 >= 14 columns
+bool lin_mma_available(int model, int one_focal);
+int lin_mma_ctas(int n_sms, int n_frames);   // grid of the tensor-core variant
+cudaError_t launch_linearize_mma(int model, int one_focal, bool batch, const LinParams& prm, int n_ctas, cudaStream_t s);
 cudaError_t launch_eval_rj(int model, int one_focal, const ProblemDev& pb, const double* intr_dev, const double* poses,
                            int apply_loss, double* r, double* J, int64_t n_obs, cudaStream_t s);
 cudaError_t launch_schur(int D, const SchurParams& prm, cudaStream_t s);

@@ -3,9 +3,9 @@
 // tests/test_rust_sys.py checks that SOURCES below lists every translation unit of csrc/Makefile.
 use std::{env, path::PathBuf, process::Command};
 
-const CUDA_SOURCES: [&str; 6] = ["ccrs_kernels.cu", "ccrs_loop.cu", "ccrs_api.cu", "ccrs_joint.cu", "ccrs_select.cu", "ccrs_pnp.cu"];
+const CUDA_SOURCES: [&str; 7] = ["ccrs_kernels.cu", "ccrs_linmma.cu", "ccrs_loop.cu", "ccrs_api.cu", "ccrs_joint.cu", "ccrs_select.cu", "ccrs_pnp.cu"];
 const HOST_SOURCES: [&str; 1] = ["ccrs_controller.cpp"];
-const HEADERS: [&str; 4] = ["ccrs_kernels.cuh", "ccrs_device.cuh", "ccrs_devutil.cuh", "ccrs_rule.h"];
+const HEADERS: [&str; 6] = ["ccrs_kernels.cuh", "ccrs_device.cuh", "ccrs_atan_tab.inc", "ccrs_devutil.cuh", "ccrs_lincommon.cuh", "ccrs_rule.h"];
 
 fn main() {
     let manifest = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap());
