@@ -115,12 +115,14 @@ __global__ void __launch_bounds__(kLinThreads, kMmaCtasPerSm) k_linearize_mma(co
   // alone, latency-bound, for a third of the kernel). Every warp makes exactly one failed grab, so the counter has seen
   // n_frames + n_warps grabs when the launch is over: the warp that makes the last one resets it.
   const unsigned long long n_grabs = (unsigned long long)pb.n_frames + (unsigned long long)gridDim.x * kLinWarps;
-  auto grab = [&]() -> int {
+  // issued by lane 0 (the value is consumed later: the atomic's round trip overlaps whatever comes in between)
+  auto grab_issue = [&]() -> unsigned long long {
     unsigned long long t = 0;
-    if (lane == 0) {
-      t = atomicAdd(prm.frame_ctr, 1ull);
-      if (t == n_grabs - 1) *prm.frame_ctr = 0ull;
-    }
+    if (lane == 0) t = atomicAdd(prm.frame_ctr, 1ull);
+    return t;
+  };
+  auto grab_take = [&](unsigned long long t) -> int {
+    if (lane == 0 && t == n_grabs - 1) *prm.frame_ctr = 0ull;   // the launch's last grab
     t = __shfl_sync(0xffffffffu, t, 0);
     return t < (unsigned long long)pb.n_frames ? (int)t : -1;
   };
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(kLinThreads, kMmaCtasPerSm) k_linearize_mma(co
   tk_mark = tk_setup;
   long long tk_frames = 0;
 #endif
-  for (int f = grab(); f >= 0;) {
+  for (int f = grab_take(grab_issue()); f >= 0;) {
 #ifdef CCRS_K2_TIMING
     ++tk_frames;
 #endif
@@ -243,7 +245,10 @@ __global__ void __launch_bounds__(kLinThreads, kMmaCtasPerSm) k_linearize_mma(co
     };
 
     CCRS_TKM(tk_pro);
+    unsigned long long next_raw = 0;
+    bool next_issued = false;
     for (int base = fo_beg; base < fo_end; base += 32) {
+      if (base + 32 >= fo_end) { next_raw = grab_issue(); next_issued = true; }   // last round: ask for the next frame now
 #ifdef CCRS_K2_TIMING
       ++tk_iters;
 #endif
@@ -281,7 +286,7 @@ __global__ void __launch_bounds__(kLinThreads, kMmaCtasPerSm) k_linearize_mma(co
     constexpr int ri = C::N - 8;   // (r, r) sits in tile (1,1) at (ri, ri): lane 4 ri + ri / 2, element ri % 2
     const double fcost = __shfl_sync(0xffffffffu, cs[4 + (ri & 1)], 4 * ri + (ri >> 1));
     const int f_done = f;
-    f = grab();   // the next frame (the atomic's round trip overlaps the statistics below)
+    if (!next_issued) next_raw = grab_issue();   // a frame without observations
     // ---- fused statistics (single problem): {model decrease, cost} per frame in self-validating slots; the warp that
     //      completes a chunk of 16 consecutive frames sums the chunk in frame order, the warp that completes the last
     //      chunk sums the chunks in chunk order (stats_finalize): a fixed order whoever computed what ----
@@ -293,6 +298,7 @@ __global__ void __launch_bounds__(kLinThreads, kMmaCtasPerSm) k_linearize_mma(co
         reinterpret_cast<double2*>(prm.frame_stat)[f_done] = make_double2(md, fcost);
         oldc = atomicAdd(prm.chunk_cnt + chunk, 1u);
       }
+      f = grab_take(next_raw);
       if (__shfl_sync(0xffffffffu, (unsigned)(oldc == (unsigned)c_cnt - 1), 0)) {
         double2* slot = reinterpret_cast<double2*>(prm.frame_stat) + c_beg + (lane < c_cnt ? lane : 0);
         double2 v = make_double2(0.0, 0.0);
@@ -320,6 +326,7 @@ __global__ void __launch_bounds__(kLinThreads, kMmaCtasPerSm) k_linearize_mma(co
         if (__shfl_sync(0xffffffffu, (unsigned)(t_old == n_chunks - 1), 0)) stats_finalize(prm, n_chunks, lane, phase);
       }
     }
+    if constexpr (BATCH) f = grab_take(next_raw);
     CCRS_TKM(tk_epi);
   }
 #ifdef CCRS_K2_TIMING
