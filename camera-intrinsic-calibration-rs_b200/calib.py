@@ -160,8 +160,14 @@ class Problem:
         assert p.size == 6 * self.n_frames
         check(self.lib.ccrs_set_poses(self.h, _dp(p)))
 
-    def get_poses(self) -> np.ndarray:
-        p = np.empty(6 * self.n_frames)
+    def get_poses(self, out: np.ndarray | None = None) -> np.ndarray:
+        """Current poses [n_frames, 6]. `out`: a caller-owned float64 buffer of 6 * n_frames values to download into
+        (page-locked memory makes the D2H copy a single DMA instead of a staged copy)."""
+        if out is None:
+            p = np.empty(6 * self.n_frames)
+        else:
+            p = out.reshape(-1)
+            assert p.dtype == np.float64 and p.size == 6 * self.n_frames and p.flags["C_CONTIGUOUS"]
         check(self.lib.ccrs_get_poses(self.h, _dp(p)))
         return p.reshape(-1, 6)
 
@@ -275,6 +281,19 @@ class Problem:
         check(self.lib.ccrs_bench_lm_steps(self.h, _dp(a), _dp(pz), int(warmup), int(steps), int(reset_every),
                                            int(flush_l2), _dp(ms), C.byref(n)))
         return ms, int(n.value)
+
+    @staticmethod
+    def bench_lm_steps_rotating(replicas, intr0, poses0, warmup=3, steps=20):
+        """`replicas`: Problem handles of one shape (together larger than the L2 cache). Returns (total ms of the
+        `steps` timed LM iterations, kernel launches inside them)."""
+        lib = replicas[0].lib
+        a = _f64(intr0).reshape(-1)
+        pz = _f64(poses0).reshape(-1)
+        hs = (C.c_void_p * len(replicas))(*[r.h.value for r in replicas])
+        ms = np.zeros(1)
+        n = C.c_int64(0)
+        check(lib.ccrs_bench_lm_steps_rotating(hs, len(replicas), _dp(a), _dp(pz), int(warmup), int(steps), _dp(ms), C.byref(n)))
+        return float(ms[0]), int(n.value)
 
     def launch_count(self) -> int:
         return int(self.lib.ccrs_launch_count(self.h))

@@ -2055,6 +2055,91 @@ int ccrs_bench_lm_steps(ccrs_problem* p, const double* intr0, const double* pose
   return st;
 }
 
+int ccrs_bench_lm_steps_rotating(ccrs_problem** ps, int n_ps, const double* intr0, const double* poses0, int warmup, int steps,
+                                 double* total_ms, int64_t* timed_launches) {
+  if (!ps || n_ps <= 0 || n_ps > 64 || !intr0 || !poses0 || !total_ms || steps <= 0 || warmup < 0) return fail(CCRS_ERR_INVALID, "bad args");
+  for (int h = 0; h < n_ps; ++h)
+    if (!ps[h] || ps[h]->batch || ps[h]->device != ps[0]->device || ps[h]->n_frames != ps[0]->n_frames || ps[h]->D != ps[0]->D)
+      return fail(CCRS_ERR_INVALID, "replicas must be single-problem handles of one shape on one device");
+  CK(cudaSetDevice(ps[0]->device));
+  ccrs_options opt;
+  ccrs_default_options(&opt);
+  opt.min_abs_decrease = -1.0; opt.min_rel_decrease = -1.0; opt.min_error = -1.0;   // never stop: every step does full work
+  opt.max_iteration = 1 << 30;
+  if (!device_loop_ok(ps[0], true, opt)) return fail(CCRS_ERR_INVALID, "the rotating bench needs the device-driven loop");
+  // one stream for all replicas: the steps of different replicas run back to back, in enqueue order
+  std::vector<cudaStream_t> own(n_ps);
+  for (int h = 0; h < n_ps; ++h) { own[h] = ps[h]->stream; CK(cudaStreamSynchronize(own[h])); ps[h]->stream = ps[0]->stream; }
+  cudaStream_t s = ps[0]->stream;
+  std::vector<DeviceLoop> L(n_ps);
+  std::vector<double> intr((size_t)ps[0]->D);
+  ccrs_summary sum;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int st = 0, done = 0;
+  int64_t timed = 0;
+  double total = 0.0;
+  auto restore = [&]() { for (int h = 0; h < n_ps; ++h) ps[h]->stream = own[h]; if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); };
+  auto run = [&]() -> int {
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return fail(CCRS_ERR_CUDA, "event");
+    for (int h = 0; h < n_ps && !st; ++h) {   // start point, first linearisation, first reduction (Jacobi scaling, first solve)
+      st = ccrs_set_poses(ps[h], poses0);
+      std::memset(&sum, 0, sizeof(sum));
+      if (!st) st = loop_begin(L[h], ps[h], true, intr0, nullptr, nullptr, nullptr, opt);
+      if (!st) st = loop_launch_k2(L[h]);
+      if (!st) st = loop_launch_k3(L[h]);
+    }
+    if (st) return st;
+    CK(cudaStreamSynchronize(s));
+    for (int h = 0; h < n_ps && !st; ++h) st = loop_consume(L[h], &sum, nullptr, &done, intr.data());
+    if (st) return st;
+    // a record ring holds kRecSlots records per replica: at most kRecSlots - 8 unconsumed iterations per replica and bracket
+    const int chunk_max = n_ps * (kRecSlots - 8);
+    int next = 0;   // replica of the next step
+    auto steps_block = [&](int n, bool timed_block) -> int {
+      while (n > 0 && !st) {
+        const int c = std::min(n, chunk_max);
+        const int first = next;
+        if (timed_block && ps[0]->comm && ps[0]->world > 1) {
+          // rendezvous outside the event bracket: absorbs the ranks' skew (every step waits for all ranks' partial systems)
+          if (!ps[0]->l2_flush.p) CK(ps[0]->l2_flush.alloc(16));
+          if (nccl().AllReduce(ps[0]->l2_flush.p, ps[0]->l2_flush.p, 1, kNcclFloat64, kNcclSum, ps[0]->comm, s) != 0)
+            return fail(CCRS_ERR_COMM, "bench rendezvous all-reduce failed");
+        }
+        int64_t l0 = 0;
+        for (int h = 0; h < n_ps; ++h) l0 += ps[h]->launches;
+        if (timed_block) CK(cudaEventRecord(e0, s));
+        for (int i = 0; i < c && !st; ++i) {
+          st = loop_launch_k2(L[next]);
+          if (!st) st = loop_launch_k3(L[next]);
+          next = (next + 1) % n_ps;
+        }
+        if (st) return st;
+        if (timed_block) CK(cudaEventRecord(e1, s));
+        CK(cudaStreamSynchronize(s));
+        if (timed_block) {
+          float ms = 0.f;
+          CK(cudaEventElapsedTime(&ms, e0, e1));
+          total += ms;
+          for (int h = 0; h < n_ps; ++h) timed += ps[h]->launches;
+          timed -= l0;
+        }
+        for (int i = 0, h = first; i < c && !st; ++i, h = (h + 1) % n_ps) st = loop_consume(L[h], &sum, nullptr, &done, intr.data());
+        n -= c;
+      }
+      return st;
+    };
+    st = steps_block(warmup, false);
+    if (!st) st = steps_block(steps, true);
+    return st;
+  };
+  st = run();
+  cudaStreamSynchronize(s);
+  restore();
+  *total_ms = total;
+  if (timed_launches) *timed_launches = timed;
+  return st;
+}
+
 int ccrs_time_linearize(ccrs_problem* p, const double* intr, int reps, int flush_l2, double* avg_ms) {
   if (!p || !intr || !avg_ms || reps <= 0) return fail(CCRS_ERR_INVALID, "bad args");
   CK(cudaSetDevice(p->device));

@@ -10,7 +10,10 @@ constexpr int kLinWarps = kLinThreads / 32;
 constexpr double kLinOverheadIters = 6.0;  // K2 per-warp prologue + reduction cost in main-loop iterations (slicing cost model)
 constexpr int kLinCtasPerSm = 2;     // K2 __launch_bounds__ occupancy target (255 regs x 128 x 2 = one register file)
 constexpr int kRedChunk = 48;        // accumulators staged per smem reduction round (48 x 32 x 8 B = 12 KB / warp)
-constexpr int kObsStages = 4;        // cp.async ring depth of K2's observation prefetch (distance 3 iterations)
+#ifndef CCRS_OBS_STAGES
+#define CCRS_OBS_STAGES 4
+#endif
+constexpr int kObsStages = CCRS_OBS_STAGES;   // cp.async ring depth of K2's observation prefetch (distance 3 iterations; 5, 6, 8 measured slower warm AND cold)
 constexpr int kFrameConst = 21;      // R(9) t(3) Jl(9) per frame in shared memory
 
 // Observation arrays and per-frame state as the kernels see them.

@@ -346,6 +346,13 @@ int ccrs_time_linearize(ccrs_problem* p, const double* intr, int reps, int flush
  * timed_launches = kernels launched inside the timed iterations. */
 int ccrs_bench_lm_steps(ccrs_problem* p, const double* intr0, const double* poses0, int warmup, int steps,
                         int reset_every, int flush_l2, double* step_ms, int64_t* timed_launches);
+/* The same LM iteration measured the way a solve runs it — K2, K3, K2, K3, ... enqueued back to back, no host
+ * synchronisation in between — with cold caches: `n_ps` replicas of one single-problem handle (create them with the same
+ * arguments; together they must exceed the L2 cache) are visited round-robin, step i on replica i mod n_ps, so that a
+ * replica's arrays have left the L2 cache when its turn comes again. `warmup` untimed steps, then `steps` timed steps
+ * inside ONE CUDA-event bracket (total_ms); stop tests disabled; device-driven loop only. */
+int ccrs_bench_lm_steps_rotating(ccrs_problem** ps, int n_ps, const double* intr0, const double* poses0, int warmup, int steps,
+                                 double* total_ms, int64_t* timed_launches);
 /* Host-side phase trace of single-problem LM iterations (process-wide). Returns the averages accumulated since the
  * last call, in microseconds per iteration, then resets and enables/disables tracing:
  *   [0] K3 launch call  [1] K3 execution + publish latency  [2] host: unpack, d x d solve, trial point
