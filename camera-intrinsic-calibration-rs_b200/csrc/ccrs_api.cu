@@ -195,6 +195,7 @@ struct ccrs_problem {
   DevBuf<double> k3_dbg;   // [n_warps][8]
 #endif
   DevBuf<double> red_out, stat_out, gather, intr_dev, ya_dev, u_dev, scale_dev, l2_flush;
+  DevBuf<double> rdv;             // one word for the bench's cross-rank rendezvous
   DevBuf<double> ctl_dev;         // LoopCtl of the device-driven loop (single problem)
   DevBuf<double> s2_part;         // K3 (k_schur2) per-CTA partials [n_ctas][NRED]: self-validating slots, armed
   DevBuf<double> bctl_dev, hist_dev;   // batch: per-problem controller state (BatchCtl), error history of problem 0
@@ -1225,7 +1226,7 @@ int ccrs_problem_destroy(ccrs_problem* p) {
   p->cur.release(); p->acc_to_blk.release(); p->tickets.release();
   for (int i = 0; i < 2; ++i) { p->poses[i].release(); p->blocks[i].release(); p->frame_cost[i].release(); }
   p->elim.release(); p->frame_red.release(); p->pose_scale.release(); p->frame_md.release(); p->cta_part.release();
-  p->frame_stat.release(); p->chunk_cnt.release();
+  p->frame_stat.release(); p->chunk_cnt.release(); p->rdv.release();
   p->red_out.release(); p->stat_out.release(); p->gather.release(); p->intr_dev.release(); p->ya_dev.release();
   p->u_dev.release(); p->scale_dev.release(); p->l2_flush.release(); p->mask_dev.release();
   p->h_red.release(); p->h_stat.release(); p->h_colsq.release();
@@ -2101,8 +2102,8 @@ int ccrs_bench_lm_steps_rotating(ccrs_problem** ps, int n_ps, const double* intr
         const int first = next;
         if (timed_block && ps[0]->comm && ps[0]->world > 1) {
           // rendezvous outside the event bracket: absorbs the ranks' skew (every step waits for all ranks' partial systems)
-          if (!ps[0]->l2_flush.p) CK(ps[0]->l2_flush.alloc(16));
-          if (nccl().AllReduce(ps[0]->l2_flush.p, ps[0]->l2_flush.p, 1, kNcclFloat64, kNcclSum, ps[0]->comm, s) != 0)
+          if (!ps[0]->rdv.p) CK(ps[0]->rdv.alloc(16));
+          if (nccl().AllReduce(ps[0]->rdv.p, ps[0]->rdv.p, 1, kNcclFloat64, kNcclSum, ps[0]->comm, s) != 0)
             return fail(CCRS_ERR_COMM, "bench rendezvous all-reduce failed");
         }
         int64_t l0 = 0;

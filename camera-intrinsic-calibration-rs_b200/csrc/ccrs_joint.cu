@@ -359,11 +359,18 @@ __global__ void k_joint_sum(const double* __restrict__ fs, int F, int NV, double
   if (host_out) host_out[v] = s;
 }
 
-// one warp per frame: lane (i, part) sums a strided part of row i of X y; five lanes per row, fixed combine order
-__global__ void __launch_bounds__(128) k_joint_backsub(JointDev jd, const double* __restrict__ el, const double* __restrict__ y, int M) {
+// The iteration's new state — intrinsics | extrinsics | shared step y — travels as a KERNEL ARGUMENT (<= 1.2 KB): no
+// host-to-device copy (copy-engine hand-over between two kernels) on the iteration path.
+struct JointState { double v[2 * kMaxShared + 8]; };
+// one warp per frame: lane (i, part) sums a strided part of row i of X y; five lanes per row, fixed combine order.
+// CTA 0 also leaves intr | extr (the first n_head values of the state) where the next linearisation reads them.
+__global__ void __launch_bounds__(128) k_joint_backsub(JointDev jd, const double* __restrict__ el, const __grid_constant__ JointState st,
+                                                       int n_head, double* __restrict__ state_dev, int M) {
+  if (blockIdx.x == 0) for (int i = threadIdx.x; i < n_head; i += blockDim.x) state_dev[i] = st.v[i];
   const int f = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (f >= jd.n_frames) return;
   const double* e = el + (size_t)f * (6 * M + 6);
+  const double* y = st.v + n_head;
   const int i = lane / 5, part = lane - 5 * i;     // lanes 0..29: row i, part 0..4; lanes 30, 31 idle
   double s = 0.0;
   if (i < 6) for (int a = part; a < M; a += 5) s += e[i * M + a] * y[a];
@@ -493,7 +500,7 @@ int ccrs_joint_create(ccrs_joint** out, int model, int xy_same_focal, int n_cams
   model_dims(model, p->one_focal, &p->d, nullptr, nullptr, nullptr);
   p->NAJ = p->d + 13; p->NBJ = p->NAJ * (p->NAJ + 1) / 2;
   p->M = n_cams * p->d + 6 * (n_cams - 1); p->NS = p->M * (p->M + 1) / 2;
-  if (p->M > kMaxShared) { delete p; return jfail(CCRS_ERR_INVALID, "shared system of %d unknowns exceeds %d", p->M, kMaxShared); }
+  if (p->M > kMaxShared || n_cams * p->d + n_cams * 6 + p->M > 2 * kMaxShared + 8) { delete p; return jfail(CCRS_ERR_INVALID, "shared system of %d unknowns exceeds %d", p->M, kMaxShared); }
   for (int b = 0; b < n_blocks; ++b)
     if (block_cam[b] < 0 || block_cam[b] >= n_cams || block_frame[b] < 0 || block_frame[b] >= n_frames || block_offsets[b + 1] < block_offsets[b]) {
       delete p; return jfail(CCRS_ERR_INVALID, "bad block %d", b);
@@ -652,9 +659,15 @@ int ccrs_joint_solve_gn(ccrs_joint* p, double* intr, double* extr, double* poses
       intr[i] = v;
     }
     for (int c = 1; c < C; ++c) for (int i = 0; i < 6; ++i) extr[6 * c + i] += y[C * d + 6 * (c - 1) + i];
-    st = upload_state(p, intr, extr, nullptr, y.data());   // y | new intr | new extr in one copy
-    if (st) return st;
-    k_joint_backsub<<<(F + 3) / 4, 128, 0, p->stream>>>(jd, p->el, p->ydev, M);
+    {
+      JointState js;
+      const int n_head = C * d + C * 6;
+      std::memcpy(js.v, intr, (size_t)C * d * 8);
+      std::memcpy(js.v + C * d, extr, (size_t)C * 6 * 8);
+      for (int i = 0; i < 6; ++i) js.v[C * d + i] = 0.0;   // cam0 is the reference frame (util.rs:689-690)
+      std::memcpy(js.v + n_head, y.data(), (size_t)M * 8);
+      k_joint_backsub<<<(F + 3) / 4, 128, 0, p->stream>>>(jd, p->el, js, n_head, p->state_dev, M);
+    }
     JCK(cudaGetLastError());
     p->launches++;
   }
