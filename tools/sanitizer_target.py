@@ -12,6 +12,14 @@ for name in ("solve_lm", "solve_gn"):
     intr, summ, _ = getattr(gp, name)(s.init_params)
     print(name, summ.iterations, summ.status)
 gp.set_poses(s.init_poses); gp.linearize(s.init_params); gp.reduce(0); gp.close()
+# tensor-core K2 variant (d >= 8 models) in the device-driven loop: dynamic frame hand-out, per-chunk statistics (37 = 2 x 16 + 5 frames)
+sk = c.synth.make_calib("kb4", 37, seed=6, drop_fraction=0.2)
+gk = c.Problem.from_synth(sk)
+for name in ("solve_lm", "solve_gn"):
+    gk.set_poses(sk.init_poses)
+    intr, summ, _ = getattr(gk, name)(sk.init_params)
+    print("kb4", name, summ.iterations, summ.status)
+gk.close()
 probs = [c.synth.make_calib("kb4", 12, seed=20 + i) for i in range(5)]
 fo = np.concatenate([[0]] + [p.frame_offsets[1:] + sum(q.n_obs for q in probs[:i]) for i, p in enumerate(probs)]).astype(np.int32)
 pfo = np.cumsum([0] + [p.n_frames for p in probs]).astype(np.int32)
