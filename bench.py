@@ -74,14 +74,17 @@ def workload_config(n_total: int):
             "l2": "GPU arm: inputs larger than L2 (replicas of the problem visited round-robin, >= 2.5 x L2 in total); no flush kernel"}
 
 
+K2_SOURCES = ("ccrs_kernels.cu", "ccrs_lincommon.cuh", "ccrs_kernels.cuh", "ccrs_device.cuh", "ccrs_devutil.cuh", "ccrs_atan_tab.inc")
+
+
 def kernel_source_hash() -> str:
-    """sha256 over the kernel sources: ties profiles/k2_dram_bytes_per_launch.json to the build that ran."""
+    """sha256 over K2's translation unit and the headers it includes: ties profiles/k2_dram_bytes_per_launch.json to
+    the kernel build that ran."""
     h = hashlib.sha256()
     d = os.path.join(ROOT, "camera-intrinsic-calibration-rs_b200", "csrc")
-    for name in sorted(os.listdir(d)):
-        if name.endswith((".cu", ".cuh")):
-            h.update(name.encode())
-            h.update(open(os.path.join(d, name), "rb").read())
+    for name in K2_SOURCES:
+        h.update(name.encode())
+        h.update(open(os.path.join(d, name), "rb").read())
     return h.hexdigest()[:16]
 
 

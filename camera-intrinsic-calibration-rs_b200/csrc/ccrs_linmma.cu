@@ -24,8 +24,8 @@ constexpr int kMmaRowStride = 18;   // doubles between the four row classes (u /
 constexpr int kMmaBuf = 16 * kMmaColStride;   // doubles of the staging buffer
 constexpr int kMmaCtasPerSm = 4;
 // staging buffer + frame constants (21) + intrinsics (<= 10), rounded so that every warp's buffer stays 128-byte aligned
-CCRS_HD constexpr int mma_warp_smem_doubles() { return kMmaBuf + 32; }
-static_assert(kFrameConst + kMaxFull + 1 <= 32, "per-warp constants do not fit");
+CCRS_HD constexpr int mma_warp_smem_doubles() { return kMmaBuf + 48; }
+static_assert(kFrameConst + kMaxFull + 1 + kMaxFull <= 48, "per-warp constants do not fit");
 
 CCRS_D void dmma884(double& c0, double& c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(kLinThreads, kMmaCtasPerSm) k_linearize_mma(co
   double* const s_rows = smem + (size_t)wid * mma_warp_smem_doubles();   // [16 columns][4 row classes][16 pairs] (padded)
   double* const s_fc = s_rows + kMmaBuf;                                  // R t Jl of the frame
   double* const s_intr = s_fc + kFrameConst;                              // full intrinsic vector
+  double* const s_ya = s_intr + kMaxFull + 1;                             // intrinsic step of the pending back-substitution (single problem)
   // Staging layout: value of column c for row class q (0: u of the even observation of a pair, 1: its v, 2 / 3: the odd
   // observation) and pair g sits at c * 72 + q * 18 + g. Lane l reads, as one 16-byte load, pairs g, g + 1 of class
   // l % 4 and column 8 b + l / 4: the eight lanes of a quarter-warp hit 16-byte bank groups 0..7 (18 * 8 B = 16 mod 128,
@@ -67,7 +68,6 @@ __global__ void __launch_bounds__(kLinThreads, kMmaCtasPerSm) k_linearize_mma(co
   // ---- which point, which step: from the launch (host-driven) or the device control block ----
   int which = prm.which, backsub = prm.backsub, phase = -1, cur = pb.cur_val;
   double u_bs = prm.u;
-  double ya_bs[C::D];
   if constexpr (!BATCH) {
     if (prm.ctl) {
       asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(kLinThreads, kMmaCtasPerSm) k_linearize_mma(co
       u_bs = __ldcg(&ctl->u_used);
       double lin_intr[C::D];
 #pragma unroll
-      for (int a = 0; a < C::D; ++a) { ya_bs[a] = __ldcg(&ctl->step[a]); lin_intr[a] = __ldcg(&ctl->trial[a]); }
+      for (int a = 0; a < C::D; ++a) lin_intr[a] = __ldcg(&ctl->trial[a]);
+      if (lane < C::D) s_ya[lane] = __ldcg(&ctl->step[lane]);
       phase = ph;
       if (phase != PH_LIN0 && phase != PH_TRIAL) return;   // not this slot's turn (re-reduction pending, or the loop is done)
       if (gw == 0 && lane == 0) prm.ctl->t_k2_begin = stamp_ns();
@@ -89,27 +90,14 @@ __global__ void __launch_bounds__(kLinThreads, kMmaCtasPerSm) k_linearize_mma(co
         else { for (int i = 0; i < C::D; ++i) s_intr[i] = lin_intr[i]; }
       }
     } else {
-#pragma unroll
-      for (int a = 0; a < C::D; ++a) ya_bs[a] = prm.y_a[a];
+      if (lane < C::D) s_ya[lane] = prm.y_a[lane];
       if (lane == 0) {
 #pragma unroll
         for (int i = 0; i < C::DFULL; ++i) s_intr[i] = prm.intr[i];
       }
     }
   }
-  // block entries this lane stores: tile (0,0), (0,1), (1,1), two columns each
-  const int ti = lane >> 2, tj = 2 * (lane & 3);
-  int st_off[6];
-  bool st_ok[6];
-#pragma unroll
-  for (int t = 0; t < 3; ++t)
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int gi = ti + (t == 2 ? 8 : 0), gj = tj + e + (t >= 1 ? 8 : 0);
-      st_ok[2 * t + e] = gi <= gj && gj < C::NA && gi < C::NA;
-      st_off[2 * t + e] = st_ok[2 * t + e] ? tri_idx(C::NA, gi, gj) : 0;
-    }
-
+  __syncwarp();   // s_ya, s_intr and the zeroed staging buffer are visible to the whole warp
   // Frames are handed out one at a time from a device counter: a warp that the scheduler favours simply takes more of
   // them, so all warps finish within one frame of each other (with a static split the slowest warp of a sub-partition ran
   // alone, latency-bound, for a third of the kernel). Every warp makes exactly one failed grab, so the counter has seen
@@ -167,7 +155,7 @@ __global__ void __launch_bounds__(kLinThreads, kMmaCtasPerSm) k_linearize_mma(co
         const size_t Fs = pb.Fs;
         const double* el = prm.elim + f;
         const double* elx = el + (size_t)(pi * C::D) * Fs;
-        const double* ya = BATCH ? prm.ya_dev + (size_t)prob * C::D : ya_bs;
+        const double* ya = BATCH ? prm.ya_dev + (size_t)prob * C::D : s_ya;
         const double u = BATCH ? (prm.u_dev ? prm.u_dev[prob] : 0.0) : u_bs;
         double yp = __ldcg(el + (size_t)(6 * C::D + pi) * Fs);
         double xv[C::D];
@@ -278,10 +266,18 @@ __global__ void __launch_bounds__(kLinThreads, kMmaCtasPerSm) k_linearize_mma(co
 #pragma unroll
     for (int i = 0; i < 6; ++i) cs[i] = ca[i] + cb[i];
     {
+      // block entries this lane holds: tiles (0,0), (0,1), (1,1), two columns each (index arithmetic per frame: keeping
+      // the six offsets live across the main loop costs the registers that make it spill)
       double* const out = pb.blocks[cur ^ which] + f;
       const size_t Fs = pb.Fs;
+      const int ti = lane >> 2, tj = 2 * (lane & 3);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) if (st_ok[i]) out[(size_t)st_off[i] * Fs] = cs[i];
+      for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int gi = ti + (t == 2 ? 8 : 0), gj = tj + e + (t >= 1 ? 8 : 0);
+          if (gi <= gj && gj < C::NA && gi < C::NA) out[(size_t)tri_idx(C::NA, gi, gj) * Fs] = cs[2 * t + e];
+        }
     }
     constexpr int ri = C::N - 8;   // (r, r) sits in tile (1,1) at (ri, ri): lane 4 ri + ri / 2, element ri % 2
     const double fcost = __shfl_sync(0xffffffffu, cs[4 + (ri & 1)], 4 * ri + (ri >> 1));
