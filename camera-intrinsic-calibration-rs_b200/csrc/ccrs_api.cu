@@ -881,7 +881,7 @@ int loop_begin(DeviceLoop& L, ccrs_problem* p, bool lm, const double* intr, cons
   L.p = p; L.lm = lm; L.D = p->D; L.opt = opt; L.enq = L.got = 0;
   LoopCtl* c = reinterpret_cast<LoopCtl*>(p->h_ctl.p);
   std::memset(c, 0, sizeof(LoopCtl));
-  c->mode = lm ? 1 : 0; c->D = p->D; c->max_iteration = opt.max_iteration; c->fixed_mode = opt.fixed_mode;
+  c->mode = lm ? 1 : 0; c->mode_k2 = c->mode; c->D = p->D; c->max_iteration = opt.max_iteration; c->fixed_mode = opt.fixed_mode;
   c->has_bounds = (lo && hi) ? 1 : 0; c->has_fixed = fixed ? 1 : 0;
   c->min_abs = opt.min_abs_decrease; c->min_rel = opt.min_rel_decrease; c->min_error = opt.min_error;
   c->min_diag = opt.lm_min_diag; c->max_diag = opt.lm_max_diag; c->block_huber = lm ? 0.0 : opt.block_huber_delta;

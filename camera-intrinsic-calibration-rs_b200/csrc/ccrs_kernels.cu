@@ -188,6 +188,12 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   const ProblemDev& pb = prm.pb;
   // a K3 enqueued behind this grid as a programmatic dependent may start launching now (it waits for our completion)
   asm volatile("griddepcontrol.launch_dependents;");
+  // the only CTA-wide barrier of the kernel, at its very top: zeroes the counter the CTA's warps combine their statistics
+  // with at the end
+  __shared__ double2 s_wpart[kLinWarps];
+  __shared__ unsigned s_wcnt;
+  if (threadIdx.x == 0) s_wcnt = 0u;
+  __syncthreads();
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = prm.G, FPW = prm.FPW;
   const int gw = blockIdx.x * kLinWarps + wid;          // warp index in the grid
@@ -281,10 +287,9 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const LoopCtl* ctl = prm.ctl;
     if (gw == 0 && lane == 0) prm.ctl->t_k2_wake = stamp_ns();
-    const int ph = __ldcg(&ctl->phase), lm = __ldcg(&ctl->mode), cu = __ldcg(&ctl->cur);
-    u_bs = __ldcg(&ctl->u_used);
-#pragma unroll
-    for (int a = 0; a < C::D; ++a) { ya_bs[a] = __ldcg(&ctl->step[a]); lin_intr[a] = __ldcg(&ctl->trial[a]); }
+    const CtlHot hot = load_ctl_hot<C::D>(ctl, lane, lin_intr, ya_bs);   // one request per warp, not 4 + 2 d
+    const int ph = hot.phase, lm = hot.lm, cu = hot.cur;
+    u_bs = hot.u_used;
     double r0[6], r1[6];
     if (active) {
       const double *p0 = pb.poses[0] + 6 * (size_t)f, *p1 = pb.poses[1] + 6 * (size_t)f;
@@ -507,8 +512,7 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   // ---- fused statistics (single problem): {model decrease, cost} summed over frames in a fixed order: per-warp
   //      partials in frame order, published with a release-atomic ticket BEFORE the block reduction so the atomic's
   //      round trip overlaps it; the last warp to take a ticket sums the warp partials (fixed tree) at the very end.
-  unsigned ticket_old = 0;
-  const unsigned n_warps = gridDim.x * kLinWarps;
+  unsigned ticket_old = 0xffffffffu;   // stays so unless this warp is the last of its CTA
   if constexpr (!BATCH) {
     // all shuffles first (independent), then the two fixed-order sums: a warp owns at most 32 frames, usually 4-8
     double wmd = 0.0, wcost = 0.0;
@@ -529,10 +533,21 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
       }
     }
     if (lane == 0) {
-      // no fence: the two partial words validate themselves (armed with kArmBits by the previous launch's last
-      // warp / at creation); the relaxed ticket only elects the warp that sums, its round trip overlaps the reduction
-      reinterpret_cast<double2*>(prm.cta_part)[gw] = make_double2(wmd, wcost);
-      ticket_old = atomicAdd(prm.ticket, 1u);
+      // The CTA's four warps combine in warp order through shared memory (the last of them to arrive sums), so the grid
+      // leaves one partial per CTA: the final sum reads 292 slots in one round of loads instead of 1,167 in three.
+      // Global side, no fence: the two partial words validate themselves (armed with kArmBits by the previous launch's
+      // last warp / at creation); the relaxed ticket only elects the warp that sums, its round trip overlaps the reduction.
+      s_wpart[wid] = make_double2(wmd, wcost);
+      __threadfence_block();
+      if (atomicAdd(&s_wcnt, 1u) == kLinWarps - 1) {
+        __threadfence_block();
+        const volatile double2* wp = s_wpart;
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int w = 0; w < kLinWarps; ++w) { a += wp[w].x; b += wp[w].y; }
+        reinterpret_cast<double2*>(prm.cta_part)[blockIdx.x] = make_double2(a, b);
+        ticket_old = atomicAdd(prm.ticket, 1u);
+      }
     }
   }
 
@@ -551,9 +566,9 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
 
   CCRS_TCK(4);
   if constexpr (!BATCH) {
-    const unsigned last = __shfl_sync(0xffffffffu, (unsigned)(ticket_old == n_warps - 1), 0);
+    const unsigned last = __shfl_sync(0xffffffffu, (unsigned)(ticket_old == gridDim.x - 1), 0);
     if (last) {
-      stats_finalize(prm, n_warps, lane, phase);
+      stats_finalize(prm, gridDim.x, lane, phase);
     }
   }
 #ifdef CCRS_K2_TIMING

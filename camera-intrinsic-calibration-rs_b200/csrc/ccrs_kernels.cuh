@@ -85,12 +85,17 @@ struct LoopCtl {
   double lo[9], hi[9];
   unsigned char fixed[16];
   // ---- state
-  int phase, cur, it, iterations, first, seq, status, stop_reason, n_acc, n_rej;
+  // Hot window: everything a K2 warp needs from this block, kCtlHotWords consecutive 8-byte words that the warp reads
+  // with ONE lane-distributed load (lane i <- word i). Read field by field, every one of the ~1,200 warps of a K2 grid
+  // sent 16-22 requests to the same two L2 lines right after the K3 -> K2 hand-off.
+  int phase, cur;           // word 0
+  int mode_k2, pad_k2;      // word 1: copy of `mode`
+  double u_used;            // word 2: damping of the reduction whose elimination record K2 back-substitutes with
+  double trial[9];          // words 3..11: intrinsics K2 linearises at next
+  double step[9];           // words 12..20: intrinsic step in unscaled units (Jacobi scale x y_a): what K2's back-substitution uses
+  int it, iterations, first, seq, status, stop_reason, n_acc, n_rej;
   double u, v;              // LM damping (1 / radius) and reject factor
-  double u_used;            // damping of the reduction whose elimination record K2 back-substitutes with
   double intr[9];           // current intrinsics (optimised vector)
-  double trial[9];          // intrinsics K2 linearises at next
-  double step[9];           // intrinsic step in unscaled units (Jacobi scale x y_a): what K2's back-substitution uses
   double scale[9];          // Jacobi scaling of the intrinsic columns (LM; 1 for GN)
   double md_a;              // intrinsic part of the model decrease of the pending trial step
   double sq_cur, cur_err, last_err, final_err;
@@ -99,6 +104,7 @@ struct LoopCtl {
   double t_k2_wake;              // ... its first warp straight after the dependency wait (before the prologue loads)
 };
 static_assert(sizeof(LoopCtl) % 8 == 0, "LoopCtl is copied as 8-byte words");
+constexpr int kCtlHotWords = 21;
 static_assert(REC_LAST_SCALAR <= REC_INTR && REC_OUT + 9 * 9 + 3 * 9 + 1 <= kRecStride, "record layout overlaps");
 
 struct LinParams {

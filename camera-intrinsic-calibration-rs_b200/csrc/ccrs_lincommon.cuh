@@ -6,6 +6,7 @@
 #include "ccrs_devutil.cuh"
 
 #include <algorithm>
+#include <cstddef>
 #include <type_traits>
 
 namespace ccrs {
@@ -190,6 +191,24 @@ CCRS_D double obs_rows(const double* __restrict__ ip /* full intrinsics */, cons
   }
   return s * w * w;
   }
+}
+
+
+// The hot window of the control block (LoopCtl, ccrs_kernels.cuh) read by a whole warp with ONE lane-distributed load;
+// the fields are then handed to all lanes by shuffle.
+struct CtlHot { int phase, cur, lm; double u_used; };
+template <int D>
+CCRS_D CtlHot load_ctl_hot(const LoopCtl* ctl, int lane, double (&trial)[D], double (&step)[D]) {
+  const double* hot = reinterpret_cast<const double*>(ctl) + offsetof(LoopCtl, phase) / 8;
+  const double w = lane < kCtlHotWords ? __ldcg(hot + lane) : 0.0;
+  const long long w0 = __double_as_longlong(__shfl_sync(0xffffffffu, w, 0));
+  const long long w1 = __double_as_longlong(__shfl_sync(0xffffffffu, w, 1));
+  CtlHot h;
+  h.phase = (int)(w0 & 0xffffffffLL); h.cur = (int)(w0 >> 32); h.lm = (int)(w1 & 0xffffffffLL);
+  h.u_used = __shfl_sync(0xffffffffu, w, 2);
+#pragma unroll
+  for (int a = 0; a < D; ++a) { trial[a] = __shfl_sync(0xffffffffu, w, 3 + a); step[a] = __shfl_sync(0xffffffffu, w, 12 + a); }
+  return h;
 }
 
 // Executed by the whole warp that took the last ticket: every producer of a {model decrease, cost} partial has taken

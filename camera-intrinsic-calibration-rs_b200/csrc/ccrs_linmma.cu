@@ -73,12 +73,14 @@ __global__ void __launch_bounds__(kLinThreads, kMmaCtasPerSm) k_linearize_mma(co
       asm volatile("griddepcontrol.wait;" ::: "memory");
       const LoopCtl* ctl = prm.ctl;
       if (gw == 0 && lane == 0) prm.ctl->t_k2_wake = stamp_ns();
-      const int ph = __ldcg(&ctl->phase), lm = __ldcg(&ctl->mode), cu = __ldcg(&ctl->cur);
-      u_bs = __ldcg(&ctl->u_used);
-      double lin_intr[C::D];
+      double lin_intr[C::D], ya_ld[C::D];
+      const CtlHot hot = load_ctl_hot<C::D>(ctl, lane, lin_intr, ya_ld);   // one request per warp
+      const int ph = hot.phase, lm = hot.lm, cu = hot.cur;
+      u_bs = hot.u_used;
+      if (lane == 0) {
 #pragma unroll
-      for (int a = 0; a < C::D; ++a) lin_intr[a] = __ldcg(&ctl->trial[a]);
-      if (lane < C::D) s_ya[lane] = __ldcg(&ctl->step[lane]);
+        for (int a = 0; a < C::D; ++a) s_ya[a] = ya_ld[a];
+      }
       phase = ph;
       if (phase != PH_LIN0 && phase != PH_TRIAL) return;   // not this slot's turn (re-reduction pending, or the loop is done)
       if (gw == 0 && lane == 0) prm.ctl->t_k2_begin = stamp_ns();
