@@ -188,12 +188,9 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
   const ProblemDev& pb = prm.pb;
   // a K3 enqueued behind this grid as a programmatic dependent may start launching now (it waits for our completion)
   asm volatile("griddepcontrol.launch_dependents;");
-  // the only CTA-wide barrier of the kernel, at its very top: zeroes the counter the CTA's warps combine their statistics
-  // with at the end
+  // per-warp {model decrease, cost} of the CTA, combined by warp 0 at the end (named barrier 1: the only CTA-level
+  // synchronisation of the kernel, and only warp 0 ever waits on it)
   __shared__ double2 s_wpart[kLinWarps];
-  __shared__ unsigned s_wcnt;
-  if (threadIdx.x == 0) s_wcnt = 0u;
-  __syncthreads();
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = prm.G, FPW = prm.FPW;
   const int gw = blockIdx.x * kLinWarps + wid;          // warp index in the grid
@@ -532,23 +529,12 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
         wcost += __shfl_sync(0xffffffffu, fcost, i * G);
       }
     }
-    if (lane == 0) {
-      // The CTA's four warps combine in warp order through shared memory (the last of them to arrive sums), so the grid
-      // leaves one partial per CTA: the final sum reads 292 slots in one round of loads instead of 1,167 in three.
-      // Global side, no fence: the two partial words validate themselves (armed with kArmBits by the previous launch's
-      // last warp / at creation); the relaxed ticket only elects the warp that sums, its round trip overlaps the reduction.
-      s_wpart[wid] = make_double2(wmd, wcost);
-      __threadfence_block();
-      if (atomicAdd(&s_wcnt, 1u) == kLinWarps - 1) {
-        __threadfence_block();
-        const volatile double2* wp = s_wpart;
-        double a = 0.0, b = 0.0;
-#pragma unroll
-        for (int w = 0; w < kLinWarps; ++w) { a += wp[w].x; b += wp[w].y; }
-        reinterpret_cast<double2*>(prm.cta_part)[blockIdx.x] = make_double2(a, b);
-        ticket_old = atomicAdd(prm.ticket, 1u);
-      }
-    }
+    // The CTA's four warps combine in warp order through shared memory, so the grid leaves one partial per CTA: the
+    // final sum reads 292 slots in one round of loads instead of 1,167 in three. Warps 1-3 post their partial and arrive
+    // at named barrier 1 without waiting; warp 0 waits on it after its own block reduction (below).
+    if (lane == 0) s_wpart[wid] = make_double2(wmd, wcost);
+    __syncwarp();
+    if (wid != 0) asm volatile("bar.arrive 1, %0;" ::"n"(kLinThreads) : "memory");
   }
 
   CCRS_TCK(6);
@@ -566,9 +552,19 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtasPerSm) k_linearize(const 
 
   CCRS_TCK(4);
   if constexpr (!BATCH) {
-    const unsigned last = __shfl_sync(0xffffffffu, (unsigned)(ticket_old == gridDim.x - 1), 0);
-    if (last) {
-      stats_finalize(prm, gridDim.x, lane, phase);
+    if (wid == 0) {
+      asm volatile("bar.sync 1, %0;" ::"n"(kLinThreads) : "memory");   // the other warps' partials are posted
+      if (lane == 0) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int w = 0; w < kLinWarps; ++w) { a += s_wpart[w].x; b += s_wpart[w].y; }
+        // no fence: the two partial words validate themselves (armed with kArmBits by the previous launch's last warp /
+        // at creation); the relaxed ticket only elects the warp that sums
+        reinterpret_cast<double2*>(prm.cta_part)[blockIdx.x] = make_double2(a, b);
+        ticket_old = atomicAdd(prm.ticket, 1u);
+      }
+      const unsigned last = __shfl_sync(0xffffffffu, (unsigned)(ticket_old == gridDim.x - 1), 0);
+      if (last) stats_finalize(prm, gridDim.x, lane, phase);
     }
   }
 #ifdef CCRS_K2_TIMING
