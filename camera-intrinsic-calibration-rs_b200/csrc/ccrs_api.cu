@@ -267,8 +267,11 @@ void choose_slicing(ccrs_problem* p) {
     const int waves = (ctas + slots - 1) / slots;
     const int per_lane = (max_cnt + G - 1) / G;
     // cost model: per-lane observations dominate; a per-warp constant covers prologue (pose maths), pipeline fill,
-    // basis change and the shared-memory reduction (in units of main-loop iterations)
-    const double cost = (double)waves * (per_lane + kLinOverheadIters);
+    // basis change and the shared-memory reduction (in units of main-loop iterations); the reduction sums G slices per
+    // entry (+0.1 G) and has an unrolled form only for the slice counts listed in slices_reduce_store (+7 otherwise:
+    // tools/k2_sweep.py at 875 frames — G = 16: 13.2 us, G = 32: 14.6 us, where the constant alone picked 32)
+    const bool unrolled = G <= 6 || G == 8 || G == 10 || G == 16;
+    const double cost = (double)waves * (per_lane + kLinOverheadIters + 0.1 * G + (unrolled ? 0.0 : 7.0));
     if (cost < best - 1e-12) { best = cost; bestG = G; }
   }
   if (const char* e = getenv("CCRS_FORCE_G")) { const int g = atoi(e); if (g >= 1 && g <= 32 && !(pairs && (g & 1))) bestG = g; }

@@ -5,7 +5,7 @@ import ccrs_b200 as c
 model = sys.argv[1] if len(sys.argv) > 1 else "eucm"
 nf = int(sys.argv[2]) if len(sys.argv) > 2 else 7000
 s = c.synth.make_calib(model, nf, seed=3)
-for g in (0, 1, 2, 3, 4, 5, 6, 8, 10, 16):
+for g in (0, 1, 2, 3, 4, 5, 6, 8, 10, 16, 32):
     if g: os.environ["CCRS_FORCE_G"] = str(g)
     else: os.environ.pop("CCRS_FORCE_G", None)
     gp = c.Problem.from_synth(s)
