@@ -495,7 +495,30 @@ def run_ours(args):
         total = R.max(float(np.sum(times)))
         return evals / total, total / e2e_steps * 1e3, intr, summ
 
+    def e2e_reuse():
+        """the same calibration on a handle that is kept: new detections -> ccrs_problem_update_observations"""
+        q = pkg.Problem(MODEL, s.width, s.height, hfo, None, None, None, hu, hv, device=dev, corner_id=hid, board=hboard)
+        if world > 1:
+            q.comm_init(None)
+        evals, times = 0, []
+        for i in range(2 + e2e_steps):
+            R.barrier()
+            t0 = time.perf_counter()
+            q.update_observations(hfo, hu, hv, corner_id=hid)
+            q.set_poses(hp)
+            _, sm, _ = q.solve_lm(s.init_params)
+            q.get_poses(out=hout)
+            dt = time.perf_counter() - t0
+            R.barrier()
+            if i >= 2:
+                times.append(dt)
+                evals += n_total * (1 + sm.iterations)
+        q.close()
+        total = R.max(float(np.sum(times)))
+        return evals / total, total / e2e_steps * 1e3
+
     e2e_value, e2e_ms, intr, summ = e2e_run("board")
+    e2e_reuse_value, e2e_reuse_ms = e2e_reuse()
     e2e_xyz_value, e2e_xyz_ms, _, _ = e2e_run("xyz")
     h2d = hid.nbytes + hu.nbytes + hv.nbytes + hboard.nbytes + hfo.nbytes + hp.nbytes
     h2d_xyz = hx.nbytes * 5 + hfo.nbytes + hp.nbytes
@@ -538,6 +561,8 @@ def run_ours(args):
                     "ms_per_call": e2e_ms, "lm_iterations_per_call": int(summ.iterations),
                     "what": "ccrs_problem_create_board_f32 (H2D from pinned memory of corner ids + f32 p2d + the board table: the reference's FrameFeature / Board data model) + set_poses + ccrs_solve_lm to convergence + get_poses (D2H) + destroy",
                     "converged_rel_err_vs_gt": rel_err,
+                    "reused_handle": {"value": e2e_reuse_value, "ms_per_call": e2e_reuse_ms, "h2d_bytes_per_step": int(h2d - hboard.nbytes),
+                                      "what": "the handle is kept between calibrations: ccrs_problem_update_observations (H2D of corner ids + f32 p2d) + set_poses + ccrs_solve_lm to convergence + get_poses (D2H)"},
                     "xyz_f32_format": {"value": e2e_xyz_value, "ms_per_call": e2e_xyz_ms, "h2d_bytes_per_step": int(h2d_xyz),
                                        "what": "same call sequence through ccrs_problem_create_f32 (x, y, z, u, v f32 arrays: round 1's format)"}},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,

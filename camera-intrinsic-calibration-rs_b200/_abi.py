@@ -22,7 +22,7 @@ SYMBOLS = [
     "ccrs_comm_unique_id", "ccrs_comm_init", "ccrs_comm_finalize", "ccrs_comm_set_deterministic", "ccrs_comm_uses_peer_memory", "ccrs_default_options",
     "ccrs_solve_gn", "ccrs_solve_lm", "ccrs_controller_gn", "ccrs_controller_lm", "ccrs_calib_camera",
     "ccrs_joint_create", "ccrs_joint_destroy", "ccrs_joint_dim", "ccrs_joint_last_error", "ccrs_joint_launch_count",
-    "ccrs_joint_eval_rj", "ccrs_joint_solve_gn", "ccrs_init_poses", "ccrs_set_fixed_poses", "ccrs_init_ucm", "ccrs_convert_model", "ccrs_model_bounds", "ccrs_measure_fp64_peak", "ccrs_time_linearize", "ccrs_bench_lm_steps", "ccrs_bench_lm_steps_rotating", "ccrs_launch_count", "ccrs_step_trace", "ccrs_spec_k3_counters", "ccrs_loop_counters", "ccrs_loop_trace",
+    "ccrs_joint_eval_rj", "ccrs_joint_solve_gn", "ccrs_init_poses", "ccrs_set_fixed_poses", "ccrs_init_ucm", "ccrs_convert_model", "ccrs_model_bounds", "ccrs_measure_fp64_peak", "ccrs_time_linearize", "ccrs_bench_lm_steps", "ccrs_bench_lm_steps_rotating", "ccrs_problem_update_observations", "ccrs_launch_count", "ccrs_step_trace", "ccrs_spec_k3_counters", "ccrs_loop_counters", "ccrs_loop_trace",
 ]
 
 STATUS = {0: "CCRS_OK", -1: "CCRS_ERR_INVALID", -2: "CCRS_ERR_CUDA", -3: "CCRS_ERR_NO_DEVICE",
@@ -142,6 +142,7 @@ def load():
     lib.ccrs_measure_fp64_peak.argtypes = [C.c_int, _dp]
     lib.ccrs_time_linearize.argtypes = [vp, _dp, C.c_int, C.c_int, _dp]
     lib.ccrs_bench_lm_steps.argtypes = [vp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.POINTER(C.c_int64)]
+    lib.ccrs_problem_update_observations.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp, vp, vp, vp, vp]
     lib.ccrs_bench_lm_steps_rotating.argtypes = [C.POINTER(vp), C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, C.POINTER(C.c_int64)]
     _lib = lib
     return lib

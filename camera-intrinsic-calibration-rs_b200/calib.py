@@ -95,6 +95,7 @@ class Problem:
             check(self.lib.ccrs_problem_create_board_f32(C.byref(self.h), self.model, width, height, int(xy_same_focal), len(fo) - 1,
                                                          fo.ctypes.data_as(ip), ids.ctypes.data_as(ip), fp(us), fp(vs), fp(bd),
                                                          len(bd), float(huber_delta), int(device)))
+            self._storage = "board"
             self._finish_init()
             return
         f32 = all(isinstance(a, np.ndarray) and a.dtype == np.float32 for a in (x, y, z, u, v)) and problem_frame_offsets is None
@@ -120,6 +121,7 @@ class Problem:
             check(self.lib.ccrs_batch_create(C.byref(self.h), self.model, width, height, int(xy_same_focal),
                                              len(pfo) - 1, pfo.ctypes.data_as(ip), len(fo) - 1, fo.ctypes.data_as(ip),
                                              _dp(xs), _dp(ys), _dp(zs), _dp(us), _dp(vs), float(huber_delta), int(device)))
+        self._storage = "f32" if f32 else "f64"
         self._finish_init()
 
     def _finish_init(self):
@@ -155,6 +157,22 @@ class Problem:
         self.close()
 
     # ---- state ----
+    def update_observations(self, frame_offsets, u, v, x=None, y=None, z=None, corner_id=None):
+        """New detections for this handle (same frame count and total observation count): ccrs_problem_update_observations.
+        Board-format handles take corner_id; the others x, y, z. Poses and solver state are reset."""
+        fo = np.ascontiguousarray(frame_offsets, dtype=np.int32)
+        dt = np.float64 if self._storage == "f64" else np.float32
+        us, vs = (np.ascontiguousarray(a, dtype=dt) for a in (u, v))
+        vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        ids = np.ascontiguousarray(corner_id, dtype=np.int32) if corner_id is not None else None
+        xs, ys, zs = ((np.ascontiguousarray(a, dtype=dt) if a is not None else None) for a in (x, y, z))
+        for a in (us, vs, ids, xs, ys, zs):
+            if a is not None and a.shape != (int(fo[-1]),):
+                raise ValueError("observation arrays must have frame_offsets[-1] entries")
+        check(self.lib.ccrs_problem_update_observations(self.h, fo.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                        ids.ctypes.data_as(C.POINTER(C.c_int32)) if ids is not None else None,
+                                                        vp(xs), vp(ys), vp(zs), vp(us), vp(vs)))
+
     def set_poses(self, poses):
         p = _f64(poses).reshape(-1)
         assert p.size == 6 * self.n_frames

@@ -1209,6 +1209,42 @@ int ccrs_problem_create_board_f32(ccrs_problem** out, int model, int width, int 
                        u, v, huber_delta, device_id, false, true, corner_id, board_xyz, n_board);
 }
 
+int ccrs_problem_update_observations(ccrs_problem* p, const int32_t* frame_offsets, const int32_t* corner_id, const void* x,
+                                     const void* y, const void* z, const void* u, const void* v) {
+  if (!p || !frame_offsets || !u || !v) return fail(CCRS_ERR_INVALID, "null");
+  if (p->batch) return fail(CCRS_ERR_INVALID, "update_observations: single-problem handles only");
+  const bool board = p->corner_id.p != nullptr;
+  if (board ? !corner_id : (!x || !y || !z)) return fail(CCRS_ERR_INVALID, "update_observations: the handle was created %s", board ? "in board format: corner ids required" : "from x, y, z arrays: they are required");
+  const int F = p->n_frames;
+  if (frame_offsets[0] != 0 || (int64_t)frame_offsets[F] != p->n_obs)
+    return fail(CCRS_ERR_INVALID, "update_observations: the handle holds %lld observations in %d frames; the new detections must have the same totals", (long long)p->n_obs, F);
+  for (int f = 0; f < F; ++f)
+    if (frame_offsets[f + 1] <= frame_offsets[f]) return fail(CCRS_ERR_INVALID, "frame %d has no observations / offsets not monotone", f);
+  CK(cudaSetDevice(p->device));
+  cudaStream_t s = p->stream;
+  const size_t N = (size_t)p->n_obs, esz = p->f32 ? 4 : 8;
+  // any step still deferred into the next linearisation belongs to the old observations
+  p->pend = false; p->cur_val = 0; p->spec.valid = false; p->have_last_reduce = false; p->have_scale = false; p->have_obs_frame = false;
+  if (board) {
+    CK(cudaMemcpyAsync(p->corner_id.p, corner_id, N * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    p->h_colsq.p[0] = 0.0;
+    CK(launch_expand_board(p->corner_id.p, p->board_dev.p, p->n_board, (int64_t)N, reinterpret_cast<float*>(p->x.p),
+                           reinterpret_cast<float*>(p->y.p), reinterpret_cast<float*>(p->z.p), p->h_colsq.p, s));
+    p->launches++;
+  } else {
+    CK(cudaMemcpyAsync(p->x.p, x, N * esz, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->y.p, y, N * esz, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->z.p, z, N * esz, cudaMemcpyHostToDevice, s));
+  }
+  CK(cudaMemcpyAsync(p->u.p, u, N * esz, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(p->v.p, v, N * esz, cudaMemcpyHostToDevice, s));
+  p->h_frame_offsets.assign(frame_offsets, frame_offsets + F + 1);
+  CK(cudaMemcpyAsync(p->frame_offsets.p, p->h_frame_offsets.data(), (size_t)(F + 1) * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));   // the caller's buffers are free again
+  if (board && p->h_colsq.p[0] != 0.0) return fail(CCRS_ERR_INVALID, "a corner id lies outside the board table (%d corners)", p->n_board);
+  return 0;
+}
+
 int ccrs_batch_create(ccrs_problem** out, int model, int width, int height, int xy_same_focal, int n_problems,
                       const int32_t* problem_frame_offsets, int n_frames, const int32_t* frame_offsets, const double* x,
                       const double* y, const double* z, const double* u, const double* v, double huber_delta,

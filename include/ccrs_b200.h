@@ -88,6 +88,15 @@ int ccrs_problem_create_board_f32(ccrs_problem** out, int model, int width, int 
                                   const float* u, const float* v, const float* board_xyz, int n_board,
                                   double huber_delta, int device_id);
 
+/* New detections for an existing single-problem handle — a calibration service that re-runs calib_camera
+ * (src/util.rs:384-490) on fresh detections of the same recording keeps its device buffers, pools and kernel
+ * configuration: only the observations cross PCIe again. Same number of frames and the same total number of
+ * observations as at creation (frame_offsets may distribute them differently); the arrays have the element type the
+ * handle was created with (double / float); handles created in board format take corner_id (x, y, z ignored), the others
+ * x, y, z (corner_id ignored). Poses and the solver state are reset like after ccrs_problem_create*. */
+int ccrs_problem_update_observations(ccrs_problem* p, const int32_t* frame_offsets, const int32_t* corner_id, const void* x,
+                                     const void* y, const void* z, const void* u, const void* v);
+
 /* Batch of independent calibrations in one handle (BASELINE config 5): problem b owns frames
  * [problem_frame_offsets[b], problem_frame_offsets[b+1]). Same model/size/flags for all problems.
  * Intrinsic arrays passed to the calls below are then [n_problems][d]; scalars become [n_problems]. */

@@ -85,3 +85,39 @@ def test_rotating_replica_bench_entry(pkg):
     assert summ.status == 0 and np.max(np.abs(intr - s.gt_params) / np.abs(s.gt_params)) < 1e-6
     for q in reps:
         q.close()
+
+
+@pytest.mark.parametrize("fmt", ["board", "f32", "f64"])
+def test_update_observations_equals_a_fresh_handle(pkg, fmt):
+    """ccrs_problem_update_observations: new detections (same frame structure) into an existing handle give, bit for bit,
+    what a handle created from them gives; a different total is refused."""
+    s = pkg.synth.make_calib("eucm", 48, seed=9, drop_fraction=0.1)
+    rng = np.random.default_rng(1)
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    u2, v2 = f32(s.u + rng.normal(0, 0.2, s.u.shape)), f32(s.v + rng.normal(0, 0.2, s.v.shape))
+
+    def make(u, v):
+        if fmt == "board":
+            return pkg.Problem("eucm", s.width, s.height, s.frame_offsets, None, None, None, f32(u), f32(v), corner_id=s.extra["corner_id"], board=s.extra["board"])
+        if fmt == "f32":
+            return pkg.Problem("eucm", s.width, s.height, s.frame_offsets, f32(s.x), f32(s.y), f32(s.z), f32(u), f32(v))
+        return pkg.Problem("eucm", s.width, s.height, s.frame_offsets, s.x, s.y, s.z, np.float64(f32(u)), np.float64(f32(v)))
+
+    gp = make(s.u, s.v)
+    gp.set_poses(s.init_poses)
+    gp.solve_lm(s.init_params)
+    kw = dict(corner_id=s.extra["corner_id"]) if fmt == "board" else dict(x=s.x, y=s.y, z=s.z)
+    gp.update_observations(s.frame_offsets, u2, v2, **kw)
+    gp.set_poses(s.init_poses)
+    intr_a, summ_a, _ = gp.solve_lm(s.init_params)
+    poses_a = gp.get_poses()
+    fresh = make(u2, v2)
+    fresh.set_poses(s.init_poses)
+    intr_b, summ_b, _ = fresh.solve_lm(s.init_params)
+    assert summ_a.status == 0 and summ_a.iterations == summ_b.iterations
+    assert np.array_equal(intr_a, intr_b) and np.array_equal(poses_a, fresh.get_poses())
+    fo_short = s.frame_offsets.copy(); fo_short[-1] -= 1          # one observation fewer than the handle holds
+    n1 = int(fo_short[-1])
+    with pytest.raises(pkg.CcrsError):
+        gp.update_observations(fo_short, u2[:n1], v2[:n1], **{k: a[:n1] for k, a in kw.items()})
+    gp.close(); fresh.close()
