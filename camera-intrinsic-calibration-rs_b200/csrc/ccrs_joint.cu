@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 #include <vector>
@@ -193,6 +194,92 @@ __global__ void __launch_bounds__(32 * kJWarps) k_joint_linearize(JointDev jd, c
   }
 }
 
+// The same block on the FP64 tensor path (the form K2 uses for the d >= 8 models, ccrs_linmma.cu): lanes = observations,
+// the 2 x 32 rows of a round staged in shared memory as [24 columns][4 row classes][16 pairs], H (24 x 24, six upper
+// 8 x 8 tiles) += J^T J with mma.sync.m8n8k4.f64, four rows = two observations per instruction. The scalar version above
+// read four shared-memory values per FMA pair (32 rows x 8 entries per lane and round) and was bound by that.
+constexpr int kJMmaWarps = 4;     // warps per (camera, frame) block: warp w takes the rounds w, w + 4, ... of 32 observations
+constexpr int kJMmaColStride = 72, kJMmaRowStride = 18, kJMmaCols = 24;
+constexpr size_t kJMmaSmem = (size_t)kJMmaWarps * kJMmaCols * kJMmaColStride * sizeof(double);
+CCRS_D void jdmma884(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+template <int MODEL, bool OF>
+__global__ void __launch_bounds__(32 * kJMmaWarps) k_joint_linearize_mma(JointDev jd, double* __restrict__ jblk) {
+  using C = JCfg<MODEL, OF>;
+  static_assert(C::NA <= kJMmaCols, "three column blocks of eight cover the joint block");
+  extern __shared__ __align__(16) double s_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // launched as a programmatic dependent of the kernel before it
+  double* const sr = s_all + (size_t)warp * kJMmaCols * kJMmaColStride;
+  for (int i = lane; i < kJMmaCols * kJMmaColStride; i += 32) sr[i] = 0.0;   // columns >= NA stay zero
+  const int c = jd.block_cam[b], f = jd.block_frame[b];
+  double ip[kMaxFull];
+  load_full_intr<MODEL, OF>(jd.intr + (size_t)c * C::D, ip);
+  FramePose f0, fc;
+  pose_from_rvec_tvec(jd.poses + 6 * (size_t)f, f0);
+  pose_from_rvec_tvec(jd.extr + 6 * (size_t)c, fc);
+  // lane l reads row class l % 4 of column 8 blk + l / 4 (pairs g, g + 1 as one 16-byte load); lane o writes class
+  // 2 (o % 2) (u) and the next one (v) of pair o / 2
+  const double* const rd = sr + (lane >> 2) * kJMmaColStride + (lane & 3) * kJMmaRowStride;
+  double* const wr_u = sr + (2 * (lane & 1)) * kJMmaRowStride + (lane >> 1);
+  double* const wr_v = wr_u + kJMmaRowStride;
+  // tiles (0,0) (0,1) (0,2) (1,1) (1,2) (2,2), two accumulator sets (even / odd pairs) summed at the end
+  double ca[12], cb[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) { ca[i] = 0.0; cb[i] = 0.0; }
+  __syncwarp();
+  const int beg = jd.block_offsets[b], end = jd.block_offsets[b + 1];
+  for (int base = beg + 32 * warp; base < end; base += 32 * kJMmaWarps) {
+    const int k = base + lane;
+    const int cnt = min(32, end - base);
+    {
+      double au[C::NA], av[C::NA];
+      const int kk = min(k, end - 1);
+      joint_rows<MODEL, OF>(ip, f0, fc, c > 0, jd.x[kk], jd.y[kk], jd.z[kk], jd.u[kk], jd.v[kk], jd.huber_delta, au, av);
+      const bool valid = k < end;
+#pragma unroll
+      for (int i = 0; i < C::NA; ++i) {
+        wr_u[i * kJMmaColStride] = valid ? au[i] : 0.0;
+        wr_v[i * kJMmaColStride] = valid ? av[i] : 0.0;
+      }
+    }
+    __syncwarp();
+    const int np2 = (cnt + 3) >> 2;   // pairs of pairs holding at least one observation
+    for (int g2 = 0; g2 < np2; ++g2) {
+      const double2 a0 = *reinterpret_cast<const double2*>(rd + 2 * g2);
+      const double2 a1 = *reinterpret_cast<const double2*>(rd + 8 * kJMmaColStride + 2 * g2);
+      const double2 a2 = *reinterpret_cast<const double2*>(rd + 16 * kJMmaColStride + 2 * g2);
+      jdmma884(ca[0], ca[1], a0.x, a0.x); jdmma884(ca[2], ca[3], a0.x, a1.x); jdmma884(ca[4], ca[5], a0.x, a2.x);
+      jdmma884(ca[6], ca[7], a1.x, a1.x); jdmma884(ca[8], ca[9], a1.x, a2.x); jdmma884(ca[10], ca[11], a2.x, a2.x);
+      jdmma884(cb[0], cb[1], a0.y, a0.y); jdmma884(cb[2], cb[3], a0.y, a1.y); jdmma884(cb[4], cb[5], a0.y, a2.y);
+      jdmma884(cb[6], cb[7], a1.y, a1.y); jdmma884(cb[8], cb[9], a1.y, a2.y); jdmma884(cb[10], cb[11], a2.y, a2.y);
+    }
+    __syncwarp();
+  }
+  // the four warps' partial tiles are summed in warp order by warp 0 (fixed order: deterministic); a warp's partial goes
+  // through its own staging buffer, which it no longer needs
+#pragma unroll
+  for (int i = 0; i < 12; ++i) sr[i * 32 + lane] = ca[i] + cb[i];
+  __syncthreads();
+  if (warp != 0) return;
+  // lane holds (row l / 4, columns 2 (l % 4) + {0, 1}) of every tile
+  const int ti = lane >> 2, tj = 2 * (lane & 3);
+  constexpr int trow[6] = {0, 0, 0, 1, 1, 2}, tcol[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+  for (int t = 0; t < 6; ++t)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int gi = 8 * trow[t] + ti, gj = 8 * tcol[t] + tj + e;
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < kJMmaWarps; ++w) v += s_all[(size_t)w * kJMmaCols * kJMmaColStride + (2 * t + e) * 32 + lane];
+      if (gi <= gj && gj < C::NA) jblk[(size_t)b * C::NB + tri_idx(C::NA, gi, gj)] = v;
+    }
+}
+
 // per frame: gather the blocks of every camera, eliminate T_0_b_f. Output per frame:
 // fs[f][NS + M + 1] = packed upper S_f (shared x shared), g_s (M), sum r^2 ; el[f][6*M + 6] = X (6 x M), C^-1 g_p
 // One WARP per frame (a thread per frame spent ~200 us in serial read-modify-write of its 250-entry system): the
@@ -206,6 +293,9 @@ __host__ __device__ inline int jschur_warp_doubles(int M) { return M * (M + 1) /
 __global__ void __launch_bounds__(32 * kJSchurWarps) k_joint_schur(JointDev jd, const double* __restrict__ jblk,
                                                                   const uint16_t* __restrict__ ij_table, int NAJ, int M,
                                                                   double u_damp, double* __restrict__ fs, double* __restrict__ el) {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // launched as a programmatic dependent of the kernel before it
+
   extern __shared__ double jsm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int f = blockIdx.x * kJSchurWarps + warp;
@@ -339,24 +429,26 @@ __global__ void __launch_bounds__(32 * kJSchurWarps) k_joint_schur(JointDev jd, 
   }
 }
 
-// out[v] = sum_f fs[f][v], f ascending (fixed order)
-// out[v] = sum over frames (frame order: deterministic), eight loads in flight; published straight to mapped host memory
-// (host_out: the host armed the NV words with a sentinel and spins until all of them changed — no memcpy, no sync)
-__global__ void k_joint_sum(const double* __restrict__ fs, int F, int NV, double* __restrict__ out, volatile double* host_out) {
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+// out[v] = sum over frames of fs[f][v]: one WARP per value — lane-strided partial sums in frame order, then a fixed
+// butterfly (deterministic) — so a value costs one round of loads instead of F / 8 dependent ones (a thread per value took
+// 20 us for 198 frames). Published straight to mapped host memory (host_out: the host armed the NV words with a sentinel
+// and spins until all of them changed — no memcpy, no sync).
+constexpr int kJSumWarps = 8;
+__global__ void __launch_bounds__(32 * kJSumWarps) k_joint_sum(const double* __restrict__ fs, int F, int NV, double* __restrict__ out,
+                                                              volatile double* host_out) {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // launched as a programmatic dependent of the kernel before it
+
+  const int v = blockIdx.x * kJSumWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (v >= NV) return;
   double s = 0.0;
-  int f = 0;
-  for (; f + 8 <= F; f += 8) {
-    double t[8];
+  for (int f = lane; f < F; f += 32) s += fs[(size_t)f * NV + v];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) t[q] = fs[(size_t)(f + q) * NV + v];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) s += t[q];
+  for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    out[v] = s;
+    if (host_out) host_out[v] = s;
   }
-  for (; f < F; ++f) s += fs[(size_t)f * NV + v];
-  out[v] = s;
-  if (host_out) host_out[v] = s;
 }
 
 // The iteration's new state — intrinsics | extrinsics | shared step y — travels as a KERNEL ARGUMENT (<= 1.2 KB): no
@@ -366,6 +458,9 @@ struct JointState { double v[2 * kMaxShared + 8]; };
 // CTA 0 also leaves intr | extr (the first n_head values of the state) where the next linearisation reads them.
 __global__ void __launch_bounds__(128) k_joint_backsub(JointDev jd, const double* __restrict__ el, const __grid_constant__ JointState st,
                                                        int n_head, double* __restrict__ state_dev, int M) {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // launched as a programmatic dependent of the kernel before it
+
   if (blockIdx.x == 0) for (int i = threadIdx.x; i < n_head; i += blockDim.x) state_dev[i] = st.v[i];
   const int f = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (f >= jd.n_frames) return;
@@ -377,6 +472,19 @@ __global__ void __launch_bounds__(128) k_joint_backsub(JointDev jd, const double
   const double s1 = __shfl_down_sync(0xffffffffu, s, 1), s2 = __shfl_down_sync(0xffffffffu, s, 2);
   const double s3 = __shfl_down_sync(0xffffffffu, s, 3), s4 = __shfl_down_sync(0xffffffffu, s, 4);
   if (i < 6 && part == 0) jd.poses[6 * (size_t)f + i] += e[6 * M + i] - ((((s + s1) + s2) + s3) + s4);
+}
+
+// every kernel of the joint iteration is launched as a programmatic dependent of the one before it (its CTAs become
+// resident while the predecessor drains and wait at griddepcontrol.wait): the launch latency leaves the critical path
+template <class K, class... A>
+static cudaError_t jlaunch(K kern, int grid, int block, size_t smem, cudaStream_t s, A... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
 template <class F>
@@ -613,7 +721,18 @@ int ccrs_joint_solve_gn(ccrs_joint* p, double* intr, double* extr, double* poses
   for (int it = 0; it < opt.max_iteration; ++it) {
     JointDev jd = p->dev();
     cudaError_t e = jdispatch(p->model, p->one_focal, [&](auto Mo, auto OF) {
-      k_joint_linearize<decltype(Mo)::value, decltype(OF)::value><<<(p->n_blocks + kJWarps - 1) / kJWarps, 32 * kJWarps, 0, p->stream>>>(jd, p->ij_table, p->jblk);
+      static const bool scalar = [] { const char* e = getenv("CCRS_JOINT_MMA"); return e && atoi(e) == 0; }();   // A/B switch
+      if (scalar) k_joint_linearize<decltype(Mo)::value, decltype(OF)::value><<<(p->n_blocks + kJWarps - 1) / kJWarps, 32 * kJWarps, 0, p->stream>>>(jd, p->ij_table, p->jblk);
+      else {
+        auto kern = k_joint_linearize_mma<decltype(Mo)::value, decltype(OF)::value>;
+        static bool configured = false;   // per instantiation
+        if (!configured) {
+          cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJMmaSmem);
+          if (ce != cudaSuccess) return ce;
+          configured = true;
+        }
+        return jlaunch(kern, p->n_blocks, 32 * kJMmaWarps, kJMmaSmem, p->stream, jd, p->jblk);
+      }
       return cudaGetLastError();
     });
     JCK(e);
@@ -624,11 +743,11 @@ int ccrs_joint_solve_gn(ccrs_joint* p, double* intr, double* extr, double* poses
         JCK(cudaFuncSetAttribute(k_joint_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
       }
-      k_joint_schur<<<(F + kJSchurWarps - 1) / kJSchurWarps, 32 * kJSchurWarps, smem, p->stream>>>(jd, p->jblk, p->ij_table, p->NAJ, M, 0.0, p->fs, p->el);
+      JCK(jlaunch(k_joint_schur, (F + kJSchurWarps - 1) / kJSchurWarps, 32 * kJSchurWarps, smem, p->stream, jd, (const double*)p->jblk, (const uint16_t*)p->ij_table, p->NAJ, M, 0.0, p->fs, p->el));
     }
     JCK(cudaGetLastError());
     jarm(p->h_red, NV);
-    k_joint_sum<<<(NV + 31) / 32, 32, 0, p->stream>>>(p->fs, F, NV, p->red, p->h_red);
+    JCK(jlaunch(k_joint_sum, (NV + kJSumWarps - 1) / kJSumWarps, 32 * kJSumWarps, 0, p->stream, (const double*)p->fs, F, NV, p->red, (volatile double*)p->h_red));
     JCK(cudaGetLastError());
     p->launches += 3;
     st = jwait(p, p->h_red, NV);     // mapped-memory publication: no memcpy, no stream synchronise
@@ -666,7 +785,7 @@ int ccrs_joint_solve_gn(ccrs_joint* p, double* intr, double* extr, double* poses
       std::memcpy(js.v + C * d, extr, (size_t)C * 6 * 8);
       for (int i = 0; i < 6; ++i) js.v[C * d + i] = 0.0;   // cam0 is the reference frame (util.rs:689-690)
       std::memcpy(js.v + n_head, y.data(), (size_t)M * 8);
-      k_joint_backsub<<<(F + 3) / 4, 128, 0, p->stream>>>(jd, p->el, js, n_head, p->state_dev, M);
+      JCK(jlaunch(k_joint_backsub, (F + 3) / 4, 128, 0, p->stream, jd, (const double*)p->el, js, n_head, p->state_dev, M));
     }
     JCK(cudaGetLastError());
     p->launches++;
