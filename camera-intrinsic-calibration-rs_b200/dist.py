@@ -11,11 +11,14 @@ def shard_frames(frame_offsets, rank: int, world: int):
     """Contiguous frame range [lo, hi) of `rank`, balancing observations (ragged frames) not frame counts."""
     fo = np.asarray(frame_offsets, dtype=np.int64)
     n_frames = len(fo) - 1
+    if world > n_frames:
+        raise ValueError(f"{world} ranks for {n_frames} frames: every rank needs at least one frame (an empty shard cannot be "
+                         "created, and its peers would wait for its partial system)")
     total = fo[-1]
     cuts = [int(np.searchsorted(fo, total * r / world, side="left")) for r in range(world + 1)]
     cuts[0], cuts[-1] = 0, n_frames
-    for i in range(1, world + 1):
-        cuts[i] = max(cuts[i], cuts[i - 1])
+    for i in range(1, world):       # at least one frame per rank, also when a few frames hold most of the observations
+        cuts[i] = min(max(cuts[i], cuts[i - 1] + 1), n_frames - (world - i))
     return cuts[rank], cuts[rank + 1]
 
 

@@ -22,6 +22,40 @@ FIELDS = {"ucm": ["alpha"], "eucm": ["alpha", "beta"], "eucmt": ["alpha", "beta"
 _BY_VARIANT = {v: k for k, v in VARIANT.items()}
 
 
+def ryu_float(x: float) -> str:
+    """A float as serde_json (ryu) prints it: the shortest digits that round-trip — what Python's repr finds too — laid
+    out by ryu's rules: plain decimals for 1e-5 <= |x| < 1e16 (Python switches to an exponent below 1e-4), an exponent
+    without padding or sign otherwise (1e-7, 1.5e16, not 1e-07 / 1.5e+16)."""
+    x = float(x)
+    if x != x or x in (float("inf"), float("-inf")):
+        return "null"                                   # serde_json writes non-finite floats as null
+    r = repr(x)
+    if "e" in r or "E" in r:
+        mant, exp = r.lower().split("e")
+        e = int(exp)
+        if -5 <= e < 0:                                 # Python: 5e-05; ryu: 0.00005
+            digits = mant.replace("-", "").replace(".", "")
+            return ("-" if x < 0 else "") + "0." + "0" * (-e - 1) + digits
+        return f"{mant}e{e}"
+    return r
+
+
+def _dumps(obj, indent=2, level=0) -> str:
+    """json.dumps(obj, indent=2) with floats printed by ryu_float (serde_json::to_string_pretty)."""
+    pad, pad_in = " " * (indent * level), " " * (indent * (level + 1))
+    if isinstance(obj, dict):
+        if not obj:
+            return "{}"
+        return "{\n" + ",\n".join(f"{pad_in}{json.dumps(str(k))}: {_dumps(v, indent, level + 1)}" for k, v in obj.items()) + "\n" + pad + "}"
+    if isinstance(obj, (list, tuple)):
+        if not obj:
+            return "[]"
+        return "[\n" + ",\n".join(pad_in + _dumps(v, indent, level + 1) for v in obj) + "\n" + pad + "]"
+    if isinstance(obj, bool) or obj is None or isinstance(obj, (int, str)):
+        return json.dumps(obj)
+    return ryu_float(obj)
+
+
 def model_to_dict(cam: GenericModel) -> dict:
     names = ["fx", "fy", "cx", "cy"] + FIELDS[cam.model]
     body = {n: float(v) for n, v in zip(names, np.asarray(cam.params, dtype=np.float64))}
@@ -38,7 +72,7 @@ def model_from_dict(d: dict) -> GenericModel:
 
 def model_to_json(path: str, cam: GenericModel) -> None:
     with open(path, "w") as f:
-        f.write(json.dumps(model_to_dict(cam), indent=2))     # serde_json::to_string_pretty: two-space indent
+        f.write(_dumps(model_to_dict(cam)))     # serde_json::to_string_pretty: two-space indent, ryu floats
 
 
 def model_from_json(path: str) -> GenericModel:
@@ -49,7 +83,7 @@ def model_from_json(path: str) -> GenericModel:
 def poses_to_json(path: str, rtvecs: Dict[int, RvecTvec]) -> None:
     ordered = {str(k): {"rvec": [float(x) for x in rtvecs[k].rvec], "tvec": [float(x) for x in rtvecs[k].tvec]} for k in sorted(rtvecs)}
     with open(path, "w") as f:
-        f.write(json.dumps(ordered, indent=2))
+        f.write(_dumps(ordered))
 
 
 def poses_from_json(path: str) -> Dict[int, RvecTvec]:

@@ -55,3 +55,38 @@ def test_poses_and_report(pkg, tmp_path):
     assert r.read_text() == ("Calibrate with extrinsics: true\n\ncam0:\n    average reprojection error: 0.12346 px\n"
                              "    median  reprojection error: 0.10000 px\n\ncam1:\n    average reprojection error: 1.00000 px\n"
                              "    median  reprojection error: 0.98765 px\n\n")
+
+
+def test_floats_are_printed_like_serde_json(pkg, tmp_path):
+    """ryu / serde_json layout of the shortest round-trip digits: no padded or signed exponents, plain
+    decimals down to 1e-5; the files still parse to the same values."""
+    import json
+    f = pkg.io.ryu_float
+    assert f(1e-5) == "0.00001" and f(5e-5) == "0.00005" and f(-2.5e-5) == "-0.000025"
+    assert f(1e-7) == "1e-7" and f(1.5e16) == "1.5e16" and f(1e16) == "1e16" and f(-3.25e-9) == "-3.25e-9"
+    assert f(0.1) == "0.1" and f(1.0) == "1.0" and f(123456.789) == "123456.789" and f(1e15) == "1000000000000000.0"
+    for x in (1e-5, 5e-5, 1e-7, 1.5e16, 0.1, 2.0 / 3.0, 1e-300, 1.7976931348623157e308):
+        assert float(f(x)) == x
+    cam = pkg.GenericModel("kb4", [400.0, 401.5, 512.0, 500.25, 1e-5, -3.5e-7, 2e-9, 0.0], 1024, 1024)
+    p = tmp_path / "cam0.json"
+    pkg.io.model_to_json(str(p), cam)
+    txt = p.read_text()
+    assert "e-0" not in txt and "e+" not in txt and '"k1": 0.00001' in txt and '"k2": -3.5e-7' in txt
+    assert json.loads(txt) == pkg.io.model_to_dict(cam)
+    back = pkg.io.model_from_json(str(p))
+    assert list(back.params) == list(cam.params)
+
+
+def test_shard_frames_refuses_more_ranks_than_frames(pkg):
+    import numpy as np, pytest
+    with pytest.raises(ValueError):
+        pkg.dist.shard_frames(np.array([0, 10, 20, 30]), 0, 4)
+    assert pkg.dist.shard_frames(np.array([0, 10, 20, 30]), 2, 3) == (2, 3)
+
+
+def test_shard_frames_never_hands_out_an_empty_shard(pkg):
+    import numpy as np
+    fo = np.array([0, 1000, 1001, 1002, 1003, 1004])          # one frame holds nearly everything
+    cuts = [pkg.dist.shard_frames(fo, r, 4) for r in range(4)]
+    assert cuts[0][0] == 0 and cuts[-1][1] == 5 and all(hi > lo for lo, hi in cuts)
+    assert all(cuts[i][1] == cuts[i + 1][0] for i in range(3))
