@@ -428,12 +428,18 @@ int create_common(ccrs_problem** out, int model, int width, int height, int xy_s
     return fail(CCRS_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
   }
   if (device_id < 0 || device_id >= n_dev || device_id >= 64) return fail(CCRS_ERR_INVALID, "device %d out of range", device_id);
-  DevInfo& di = g_dev_info[device_id];
-  if (!di.known) {
-    CK(cudaDeviceGetAttribute(&di.major, cudaDevAttrComputeCapabilityMajor, device_id));
-    CK(cudaDeviceGetAttribute(&di.minor, cudaDevAttrComputeCapabilityMinor, device_id));
-    CK(cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, device_id));
-    di.known = true;
+  DevInfo di;
+  {
+    static std::mutex dev_info_mu;
+    std::lock_guard<std::mutex> dev_info_lock(dev_info_mu);   // handles are created from several host threads
+    DevInfo& g = g_dev_info[device_id];
+    if (!g.known) {
+      CK(cudaDeviceGetAttribute(&g.major, cudaDevAttrComputeCapabilityMajor, device_id));
+      CK(cudaDeviceGetAttribute(&g.minor, cudaDevAttrComputeCapabilityMinor, device_id));
+      CK(cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, device_id));
+      g.known = true;
+    }
+    di = g;
   }
   if (di.major != 10) return fail(CCRS_ERR_NO_DEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only", device_id, di.major, di.minor);
   CK(cudaSetDevice(device_id));
@@ -1712,8 +1718,12 @@ static int timed_solve(ccrs_problem* p, bool lm, double* intr, const double* lo,
                        const unsigned char* fixed, const ccrs_options* opt, ccrs_summary* summary, double* err_hist) {
   if (!p || !intr) return fail(CCRS_ERR_INVALID, "null");
   CK(cudaSetDevice(p->device));
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  struct Events {   // destroyed on every return path
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  } ev;
+  CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b));
+  cudaEvent_t e0 = ev.a, e1 = ev.b;
   CK(cudaEventRecord(e0, p->stream));
   ccrs_backend be = cuda_backend(p);
   ccrs_summary local;
@@ -1730,7 +1740,6 @@ static int timed_solve(ccrs_problem* p, bool lm, double* intr, const double* lo,
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
   summary->device_ms = ms;
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (st == CCRS_ERR_CHOLESKY) fail(st, "Cholesky failure (non-positive pivot)");
   if (st == CCRS_ERR_NUMERIC) fail(st, "NaN error");
   return st;
