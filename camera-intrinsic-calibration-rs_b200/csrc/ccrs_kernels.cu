@@ -7,8 +7,11 @@
 //  K4 k_backsub      pose back-substitution, trial poses, LM model-decrease
 // They replace, per iteration, tiny-solver's Problem::compute_residual_and_jacobian (num-dual autodiff of
 // ReprojectionFactor::residual_func, reference src/optimization/factors.rs:152-173), the sparse J^T J product and
-// the sparse LLT (call sites src/util.rs:455,463,670). No tensor cores: there is no dense contraction, the
-// per-frame blocks are 6x6 / 6xd. Determinism: no floating-point atomics anywhere; every sum has a fixed order.
+// the sparse LLT (call sites src/util.rs:455,463,670). The kernels in this file run on the FP64 CUDA cores: the per-frame
+// blocks are 6x6 / 6xd and the packed sparse Gram update of the small models needs a third of the FMAs of a tiled J^T J
+// on the (same) FP64 engine; the models with d >= 8 use the tensor-core variant in ccrs_linmma.cu, the single-problem
+// reduction + controller rule is k_schur2 in ccrs_loop.cu. Determinism: no floating-point atomics anywhere; every sum has
+// a fixed order.
 #include "ccrs_lincommon.cuh"
 
 namespace ccrs {
