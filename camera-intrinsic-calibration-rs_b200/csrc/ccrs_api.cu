@@ -353,6 +353,10 @@ int upload_problem(ccrs_problem* p, int n_problems, const int32_t* problem_frame
   CK(p->elim.alloc((size_t)(6 * p->D + 18) * Fs));
   CK(p->frame_red.alloc(std::max((size_t)p->NRED * Fs, (size_t)p->n_schur_ctas * p->NRED)));
   CK(p->pose_scale.alloc(6 * Fs));
+  // K2 requests a frame's elimination record and pose scales together with the control block, before it knows whether a
+  // step is pending (one memory round trip instead of two): defined values for the first linearisation, which discards them
+  CK(cudaMemsetAsync(p->elim.p, 0, (size_t)(6 * p->D + 18) * Fs * sizeof(double), s));
+  CK(cudaMemsetAsync(p->pose_scale.p, 0, 6 * Fs * sizeof(double), s));
   CK(p->frame_md.alloc(Fs));
   const size_t n_k2_warps = (size_t)std::max(p->n_lin_ctas, p->n_mma_ctas) * kLinWarps;
   CK(p->cta_part.alloc(2 * n_k2_warps));
