@@ -418,6 +418,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) k_schur2(const __grid_constant_
     if (h < SEG) {
       double a = 0.0;
       constexpr int kFly = 20;   // loads in flight per thread (one round for 7,000 frames: 146 CTAs <= 9 x 20)
+      bool poison = false;
       for (int b0 = h; b0 < nb; b0 += kFly * SEG) {
         double t[kFly];
         bool ok;
@@ -430,11 +431,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) k_schur2(const __grid_constant_
             t[q] = b < nb ? ld_spin(prm.partials + (size_t)b * NRED + v) : 0.0;
             ok = ok && (__double_as_longlong(t[q]) != kArmBits);
           }
-          if (!ok && clock64() - t_spin > 4000000000LL) {   // ~2 s: a partial never arrived -> poison, not a hang
-#pragma unroll
-            for (int q = 0; q < kFly; ++q) t[q] = nan("");
-            ok = true;
-          }
+          if (!ok && clock64() - t_spin > 4000000000LL) { poison = true; ok = true; }   // ~2 s: a partial never arrived -> poison, not a hang
         } while (!ok);
 #pragma unroll
         for (int q = 0; q < kFly; ++q) {
@@ -443,6 +440,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) k_schur2(const __grid_constant_
           if (b < nb) prm.partials[(size_t)b * NRED + v] = __longlong_as_double(kArmBits);
         }
       }
+      if (poison) a = nan("");
       s_seg[h * NRED + v] = a;
     }
   }
