@@ -399,7 +399,14 @@ def run_ours(args):
     # ---- the LM loop as a caller runs it: no synchronisation or flush between iterations
     prob.set_poses(poses0)
     o = pkg.default_options(max_iteration=40, min_abs_decrease=-1.0, min_rel_decrease=-1.0, min_error=-1.0)
+    import ctypes as C
+    lib = pkg._abi.load()
+    lib.ccrs_loop_trace(1, None, None)          # device stamps carried by the iteration records (globaltimer)
     _, loop_summ, _ = prob.solve_lm(s.init_params, options=o)
+    tr_avg = (C.c_double * 13)(); tr_cnt = C.c_int64(0)
+    lib.ccrs_loop_trace(0, tr_avg, C.byref(tr_cnt))
+    loop_trace = {"iterations_traced": int(tr_cnt.value), "k2_us": tr_avg[0], "k2_to_k3_us": tr_avg[1], "k3_per_frame_us": tr_avg[2],
+                  "k3_tail_us": tr_avg[3], "k3_to_k2_us": tr_avg[4]} if tr_cnt.value > 0 else None
     loop_ms = R.max(loop_summ.device_ms) / max(loop_summ.iterations, 1)
     # ... and the loop the reference actually runs (Gauss-Newton, src/util.rs:443-458)
     prob.set_poses(poses0)
@@ -425,6 +432,10 @@ def run_ours(args):
                 "counted": {"flop_per_obs": FLOP_PER_OBS_COUNTED, "achieved": round(tf_counted, 2), "frac": round(tf_counted / fp64_peak, 4),
                             "what": "FP64 instructions counted in the kernel's SASS (DFMA=2, DMUL/DADD=1), DESIGN §3"},
                 "k2_ms": round(k2_ms, 5), "k2_ms_l2_warm": round(k2_ms_warm, 5), "obs_per_launch": int(n_k2),
+                "in_loop": ({"k2_ms": round(loop_trace["k2_us"] * 1e-3, 5),
+                             "frac": round(FLOP_PER_OBS_NOMINAL * n_local / (loop_trace["k2_us"] * 1e-6) / 1e12 / fp64_peak, 4),
+                             "what": "K2 inside the device-driven LM loop of this rank (L2 warm, device globaltimer stamps: first warp past its dependency wait -> last warp done, no launch latency); `frac` above is the isolated, L2-flushed launch"}
+                            if loop_trace else None),
                 "hbm": {"achieved": round(achieved_gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(achieved_gbs / peaks["hbm_gbs"], 4),
                         "bytes_per_obs": round(bytes_per_obs, 2), "peak_source": f"{peak_kind} MEASURED_PEAKS.json hbm_gbs (burst: kernel timed alone)"},
                 "note": "K2 (EUCM) is bound by the FP64 pipe (CUDA cores: the packed sparse Gram update beats tensor tiles at 13 columns); the HBM fraction is secondary"}
@@ -560,6 +571,7 @@ def run_ours(args):
             "isolated_step_l2_flushed": {"ms_per_step": iso_ms_per_step, "value": iso_value,
                                          "what": "rounds 1-2 method: 512 MB flush before every step, one CUDA-event bracket per step, host synchronisation between steps"},
             "lm_loop_l2_warm": {"ms_per_iteration": loop_ms, "iterations": int(loop_summ.iterations), "lm_iterations_per_s": 1e3 / loop_ms,
+                                "device_phases_us": loop_trace,
                                 "value": n_total / (loop_ms * 1e-3),
                                 "what": "ccrs_solve_lm with the stop tests disabled, 40 back-to-back iterations incl. the initial linearisation and Jacobi scaling, CUDA events around the whole loop"},
             "gn_loop_l2_warm": {"ms_per_iteration": gn_ms, "iterations": int(gn_summ.iterations),
