@@ -384,11 +384,13 @@ def run_ours(args):
     t_wall0 = time.perf_counter()
     pkg.Problem.bench_lm_steps_rotating(replicas, s.init_params, poses0, warmup=args.warmup, steps=args.steps)   # page-in, pools
     R.barrier()
-    total_ms, launches = pkg.Problem.bench_lm_steps_rotating(replicas, s.init_params, poses0, warmup=args.warmup, steps=args.steps)
+    total_ms, launches, executed = pkg.Problem.bench_lm_steps_rotating(replicas, s.init_params, poses0, warmup=args.warmup, steps=args.steps)
     R.barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
-    ms_per_step = R.max(total_ms) / args.steps
+    if executed <= 0:
+        raise RuntimeError("no timed LM iteration executed")
+    ms_per_step = R.max(total_ms) / executed          # `executed` is the same on every rank (bitwise-identical decisions)
     value = n_total / (ms_per_step * 1e-3)
     for q in replicas[1:]:
         q.close()
@@ -466,9 +468,9 @@ def run_ours(args):
         R.barrier()
         pkg.Problem.bench_lm_steps_rotating(reps_w, sw.init_params, poses_w, warmup=args.warmup, steps=args.steps)
         R.barrier()
-        w_total, _ = pkg.Problem.bench_lm_steps_rotating(reps_w, sw.init_params, poses_w, warmup=args.warmup, steps=args.steps)
+        w_total, _, w_exec = pkg.Problem.bench_lm_steps_rotating(reps_w, sw.init_params, poses_w, warmup=args.warmup, steps=args.steps)
         R.barrier()
-        w_ms = R.max(w_total) / args.steps
+        w_ms = R.max(w_total) / max(w_exec, 1)
         w_value = sw.n_obs / (w_ms * 1e-3)
         weak = {"frames_per_gpu": FRAMES_TOTAL, "obs_total": int(sw.n_obs), "ms_per_step": w_ms, "value": w_value, "lm_iterations_per_s": 1e3 / w_ms,
                 "replicas": n_rep_w, "what": "one problem of N x 7000 frames, frame-sharded; same rotating-replica method as `value`"}
@@ -568,6 +570,7 @@ def run_ours(args):
             "run": {"frames_per_gpu": int(hi - lo), "obs_per_gpu": int(n_local), "parallelism": f"frame-sharded x{world}", "exchange": exch},
             "lm_iterations_per_s": 1e3 / ms_per_step,
             "replicas": {"n": n_rep, "bytes_per_replica": int(bytes_per_replica), "l2_bytes": l2_bytes},
+            "steps_executed": int(executed),
             "isolated_step_l2_flushed": {"ms_per_step": iso_ms_per_step, "value": iso_value,
                                          "what": "rounds 1-2 method: 512 MB flush before every step, one CUDA-event bracket per step, host synchronisation between steps"},
             "lm_loop_l2_warm": {"ms_per_iteration": loop_ms, "iterations": int(loop_summ.iterations), "lm_iterations_per_s": 1e3 / loop_ms,

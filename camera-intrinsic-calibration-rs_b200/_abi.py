@@ -143,7 +143,7 @@ def load():
     lib.ccrs_time_linearize.argtypes = [vp, _dp, C.c_int, C.c_int, _dp]
     lib.ccrs_bench_lm_steps.argtypes = [vp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.POINTER(C.c_int64)]
     lib.ccrs_problem_update_observations.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp, vp, vp, vp, vp]
-    lib.ccrs_bench_lm_steps_rotating.argtypes = [C.POINTER(vp), C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, C.POINTER(C.c_int64)]
+    lib.ccrs_bench_lm_steps_rotating.argtypes = [C.POINTER(vp), C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     _lib = lib
     return lib
 

@@ -303,15 +303,15 @@ class Problem:
     @staticmethod
     def bench_lm_steps_rotating(replicas, intr0, poses0, warmup=3, steps=20):
         """`replicas`: Problem handles of one shape (together larger than the L2 cache). Returns (total ms of the
-        `steps` timed LM iterations, kernel launches inside them)."""
+        timed slots, kernel launches inside them, LM iterations they really executed)."""
         lib = replicas[0].lib
         a = _f64(intr0).reshape(-1)
         pz = _f64(poses0).reshape(-1)
         hs = (C.c_void_p * len(replicas))(*[r.h.value for r in replicas])
         ms = np.zeros(1)
-        n = C.c_int64(0)
-        check(lib.ccrs_bench_lm_steps_rotating(hs, len(replicas), _dp(a), _dp(pz), int(warmup), int(steps), _dp(ms), C.byref(n)))
-        return float(ms[0]), int(n.value)
+        n, ex = C.c_int64(0), C.c_int64(0)
+        check(lib.ccrs_bench_lm_steps_rotating(hs, len(replicas), _dp(a), _dp(pz), int(warmup), int(steps), _dp(ms), C.byref(n), C.byref(ex)))
+        return float(ms[0]), int(n.value), int(ex.value)
 
     def launch_count(self) -> int:
         return int(self.lib.ccrs_launch_count(self.h))

@@ -2109,7 +2109,7 @@ int ccrs_bench_lm_steps(ccrs_problem* p, const double* intr0, const double* pose
 }
 
 int ccrs_bench_lm_steps_rotating(ccrs_problem** ps, int n_ps, const double* intr0, const double* poses0, int warmup, int steps,
-                                 double* total_ms, int64_t* timed_launches) {
+                                 double* total_ms, int64_t* timed_launches, int64_t* executed_steps) {
   if (!ps || n_ps <= 0 || n_ps > 64 || !intr0 || !poses0 || !total_ms || steps <= 0 || warmup < 0) return fail(CCRS_ERR_INVALID, "bad args");
   for (int h = 0; h < n_ps; ++h)
     if (!ps[h] || ps[h]->batch || ps[h]->device != ps[0]->device || ps[h]->n_frames != ps[0]->n_frames || ps[h]->D != ps[0]->D)
@@ -2132,25 +2132,39 @@ int ccrs_bench_lm_steps_rotating(ccrs_problem** ps, int n_ps, const double* intr
   int64_t timed = 0;
   double total = 0.0;
   auto restore = [&]() { for (int h = 0; h < n_ps; ++h) ps[h]->stream = own[h]; if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); };
-  auto run = [&]() -> int {
-    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return fail(CCRS_ERR_CUDA, "event");
+  // Every replica runs LM iterations 1..kItersPerReplica of the problem (the ones a converging solve runs; the old
+  // per-step bench reset every 4 too); then all replicas return to the start point, untimed. After every consumed
+  // record the LM decisions of that replica are counted: *executed_steps is the number of linearisations the timed
+  // slots really executed (across GPUs a mis-speculated reduction re-reduces first and the K2 slot behind it exits at
+  // once: such a slot is time spent, not a step).
+  constexpr int kItersPerReplica = 4;
+  std::vector<int> given(n_ps, 0), decided(n_ps, 0);
+  int64_t executed = 0;
+  int used = 0, next = 0;   // steps since the last (re)start; replica of the next step
+  auto begin_all = [&]() -> int {
     for (int h = 0; h < n_ps && !st; ++h) {   // start point, first linearisation, first reduction (Jacobi scaling, first solve)
       st = ccrs_set_poses(ps[h], poses0);
       std::memset(&sum, 0, sizeof(sum));
       if (!st) st = loop_begin(L[h], ps[h], true, intr0, nullptr, nullptr, nullptr, opt);
       if (!st) st = loop_launch_k2(L[h]);
       if (!st) st = loop_launch_k3(L[h]);
+      given[h] = 0; decided[h] = 0;
     }
     if (st) return st;
     CK(cudaStreamSynchronize(s));
     for (int h = 0; h < n_ps && !st; ++h) st = loop_consume(L[h], &sum, nullptr, &done, intr.data());
+    used = 0; next = 0;
+    return st;
+  };
+  auto run = [&]() -> int {
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return fail(CCRS_ERR_CUDA, "event");
+    st = begin_all();
     if (st) return st;
-    // a record ring holds kRecSlots records per replica: at most kRecSlots - 8 unconsumed iterations per replica and bracket
-    const int chunk_max = n_ps * (kRecSlots - 8);
-    int next = 0;   // replica of the next step
+    const int per_start = n_ps * kItersPerReplica;
     auto steps_block = [&](int n, bool timed_block) -> int {
       while (n > 0 && !st) {
-        const int c = std::min(n, chunk_max);
+        if (used == per_start) { st = begin_all(); if (st) return st; }
+        const int c = std::min(n, per_start - used);
         const int first = next;
         if (timed_block && ps[0]->comm && ps[0]->world > 1) {
           // rendezvous outside the event bracket: absorbs the ranks' skew (every step waits for all ranks' partial systems)
@@ -2176,7 +2190,18 @@ int ccrs_bench_lm_steps_rotating(ccrs_problem** ps, int n_ps, const double* intr
           for (int h = 0; h < n_ps; ++h) timed += ps[h]->launches;
           timed -= l0;
         }
-        for (int i = 0, h = first; i < c && !st; ++i, h = (h + 1) % n_ps) st = loop_consume(L[h], &sum, nullptr, &done, intr.data());
+        for (int i = 0, h = first; i < c && !st; ++i, h = (h + 1) % n_ps) {
+          st = loop_consume(L[h], &sum, nullptr, &done, intr.data());
+          given[h]++;
+          if (!st && timed_block) {   // LM decisions taken = linearisations executed (a slot behind a re-reduction exits at once)
+            const int dec = sum.n_accepted + sum.n_rejected;
+            executed += dec - decided[h];
+            decided[h] = dec;
+          } else if (!st) {
+            decided[h] = sum.n_accepted + sum.n_rejected;
+          }
+        }
+        used += c;
         n -= c;
       }
       return st;
@@ -2190,6 +2215,7 @@ int ccrs_bench_lm_steps_rotating(ccrs_problem** ps, int n_ps, const double* intr
   restore();
   *total_ms = total;
   if (timed_launches) *timed_launches = timed;
+  if (executed_steps) *executed_steps = executed;
   return st;
 }
 

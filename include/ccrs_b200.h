@@ -359,9 +359,12 @@ int ccrs_bench_lm_steps(ccrs_problem* p, const double* intr0, const double* pose
  * synchronisation in between — with cold caches: `n_ps` replicas of one single-problem handle (create them with the same
  * arguments; together they must exceed the L2 cache) are visited round-robin, step i on replica i mod n_ps, so that a
  * replica's arrays have left the L2 cache when its turn comes again. `warmup` untimed steps, then `steps` timed steps
- * inside ONE CUDA-event bracket (total_ms); stop tests disabled; device-driven loop only. */
+ * inside CUDA-event brackets (total_ms; one bracket per 4 x n_ps steps: every replica runs LM iterations 1-4 of the
+ * problem and is then returned to the start point, untimed); stop tests disabled; device-driven loop only.
+ * executed_steps = linearisations the timed slots really executed (across GPUs the slot behind a mis-speculated
+ * reduction exits at once: time spent, not a step). */
 int ccrs_bench_lm_steps_rotating(ccrs_problem** ps, int n_ps, const double* intr0, const double* poses0, int warmup, int steps,
-                                 double* total_ms, int64_t* timed_launches);
+                                 double* total_ms, int64_t* timed_launches, int64_t* executed_steps);
 /* Host-side phase trace of single-problem LM iterations (process-wide). Returns the averages accumulated since the
  * last call, in microseconds per iteration, then resets and enables/disables tracing:
  *   [0] K3 launch call  [1] K3 execution + publish latency  [2] host: unpack, d x d solve, trial point

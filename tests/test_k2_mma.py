@@ -77,8 +77,8 @@ def test_table_driven_atan2_at_wide_angles(pkg, oracle, model):
 def test_rotating_replica_bench_entry(pkg):
     s = pkg.synth.make_calib("eucm", 64, seed=3)
     reps = [pkg.Problem.from_synth(s) for _ in range(3)]
-    total_ms, launches = pkg.Problem.bench_lm_steps_rotating(reps, s.init_params, s.init_poses, warmup=2, steps=7)
-    assert total_ms > 0.0 and launches == 14          # K2 + K3 per timed step
+    total_ms, launches, executed = pkg.Problem.bench_lm_steps_rotating(reps, s.init_params, s.init_poses, warmup=2, steps=17)
+    assert total_ms > 0.0 and launches == 34 and executed == 17   # K2 + K3 per timed slot; 17 > 3 replicas x 4: one restart inside
     # the handles are usable afterwards (their own streams restored)
     reps[1].set_poses(s.init_poses)
     intr, summ, _ = reps[1].solve_lm(s.init_params)
